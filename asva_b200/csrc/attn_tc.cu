@@ -1,0 +1,367 @@
+// Fused attention  O = softmax(Q K^T * scale [+ mask]) V  on tcgen05 for sm_100a.
+//
+// One CTA owns 128 query rows of one (group, head) and streams the keys/values of that group in tiles of KV keys:
+//   warp 0      TMA producer: Q tile once, then per key tile the K box(es) (K-major) and V box(es) (MN-major,
+//               read straight from the token-major [rows][channels] projection output - no transposed copy)
+//   warp 1      TMEM allocator + single-thread MMA issuer:  S = Q K^T  (TMEM cols [0,KV)),  O += P V (cols [KV,..))
+//   warps 2..5  softmax: thread = query row (TMEM lane). Pass 1 reads S for the row maximum, pass 2 re-reads S,
+//               exponentiates (exp2, log2e folded into the scale), writes P as bf16 into a 128B-swizzled smem
+//               tile (the A operand of the second MMA) and rescales O in TMEM when the running maximum moved.
+// K/V tiles are double buffered; S/P are single buffered, so MMA/softmax overlap comes from co-resident CTAs
+// (2 per SM for head_dim <= 80).
+// Reference semantics: F.scaled_dot_product_attention with an optional boolean keep-mask
+// (avgen/models/unets/utils.py:151-153 and diffusers AttnProcessor2_0).
+#include "common.cuh"
+#include "host_common.h"
+#include <string.h>
+
+namespace asva {
+
+struct AttnKParams {
+  CUtensorMap tmQ, tmKV;
+  const uint8_t* mask;
+  __nv_bfloat16* out;
+  int64_t ldo, mask_ld;
+  int32_t R, Nk, d, dN, heads, k_col0, v_col0, mask_rows;
+  int32_t ksteps_qk;  // ceil(d/16)
+  int32_t nvb;        // number of 64-wide V column blocks = ceil(dN/64)
+  float scale_log2;   // scale * log2(e)
+};
+
+template <int DKA, int KV>
+struct AttnCfg {
+  static constexpr int kQBytes = DKA * 128 * 128;
+  static constexpr int kKBytes = DKA * KV * 128;
+  static constexpr int kVBytes = DKA * KV * 128;  // nvb <= DKA
+  static constexpr int kStageBytes = kKBytes + kVBytes;
+  static constexpr int kPBytes = (KV / 64) * 128 * 128;
+  static constexpr int kSmemBytes = kQBytes + 2 * kStageBytes + kPBytes + 1024 + 128;
+  static constexpr int kTmemCols = 256;
+};
+
+// idesc for P(bf16, K-major, from smem) x V(bf16, MN-major): b_major bit 16 set
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t M, uint32_t N) {
+  return make_idesc_bf16(M, N) | (1u << 16);
+}
+// smem descriptor for an MN-major, 128B-swizzled B operand stored as [64-col block][key][64 cols]:
+//   LBO = byte pitch between 64-column blocks, SBO = 1024 (8-key groups)
+__device__ __forceinline__ uint64_t make_sdesc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int DKA, int KV>
+__global__ void __launch_bounds__(192, (DKA <= 2) ? 2 : 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<DKA, KV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Cfg::kQBytes;
+  uint8_t* sP = sKV + 2 * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int g = blockIdx.z;
+  const int n_tiles = (p.Nk + KV - 1) / KV;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmKV);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + KV;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+#pragma unroll
+      for (int a = 0; a < DKA; ++a) tma_load_3d(sQ + a * 128 * 128, &p.tmQ, q_full, a * 64, row0, g * p.heads + head);
+      const uint32_t tx = static_cast<uint32_t>(DKA + p.nvb) * KV * 128u;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[s], tx);
+        uint8_t* sk = sKV + s * Cfg::kStageBytes;
+        uint8_t* sv = sk + Cfg::kKBytes;
+#pragma unroll
+        for (int a = 0; a < DKA; ++a)
+          tma_load_3d(sk + a * KV * 128, &p.tmKV, &kv_full[s], p.k_col0 + head * p.d + a * 64, j * KV, g);
+        for (int a = 0; a < p.nvb; ++a)
+          tma_load_3d(sv + a * KV * 128, &p.tmKV, &kv_full[s], p.v_col0 + head * p.d + a * 64, j * KV, g);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, KV);
+      const uint32_t idesc_o = make_idesc_bf16_bmn(128, static_cast<uint32_t>(p.dN));
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      auto issue_s = [&](int j) {
+        const uint32_t k_addr = smem_u32(sKV + (j & 1) * Cfg::kStageBytes);
+        for (int ks = 0; ks < p.ksteps_qk; ++ks) {
+          const uint32_t a = ks >> 2, o = (ks & 3) * 32u;
+          umma_bf16_ss(tmem_S, make_sdesc_sw128(q_addr + a * 128u * 128u + o),
+                       make_sdesc_sw128(k_addr + a * KV * 128u + o), idesc_s, ks != 0 ? 1u : 0u);
+        }
+        tc_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) {
+          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(s_empty, j & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sKV + (j & 1) * Cfg::kStageBytes + Cfg::kKBytes);
+#pragma unroll
+        for (int ks = 0; ks < KV / 16; ++ks) {
+          const uint64_t adesc = make_sdesc_sw128(p_addr + (ks >> 2) * 128u * 128u + (ks & 3) * 32u);
+          const uint64_t bdesc = make_sdesc_sw128_mn(v_addr + ks * 16u * 128u, KV * 128u);
+          umma_bf16_ss(tmem_O, adesc, bdesc, idesc_o, (j | ks) != 0 ? 1u : 0u);
+        }
+        tc_commit(&kv_empty[j & 1]);
+        tc_commit(pv_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- softmax + output ----------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int row = row0 + r;
+    const bool valid = row < p.R;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const uint8_t* mrow = nullptr;
+    if (p.mask != nullptr && valid)
+      mrow = p.mask + ((static_cast<int64_t>(g) * p.R + row) / p.mask_rows) * p.mask_ld;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int key0 = j * KV;
+      // pass 1: row maximum
+      float m_tile = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < KV; c += 32) {
+        uint32_t sv[32];
+        tmem_ld_x32(tmem_S + lane_base + c, sv);
+        tmem_ld_wait();
+        uint32_t mbits = 0xffffffffu;
+        if (mrow != nullptr) {
+          mbits = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
+          const float x = keep ? __uint_as_float(sv[i]) * p.scale_log2 : -INFINITY;
+          m_tile = fmaxf(m_tile, x);
+        }
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f(m_run - m_safe);  // m_run = -inf -> 0
+      const bool changed = (m_new > m_run) && (j > 0);
+      m_run = m_new;
+      l_run *= alpha;
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // PV of the previous tile finished: O is stable, P smem is free
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, changed)) {
+#pragma unroll 1
+          for (int c = 0; c < p.dN; c += 16) {
+            uint32_t ov[16];
+            tmem_ld_x16(tmem_O + lane_base + c, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_x16(tmem_O + lane_base + c, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: probabilities -> bf16 P tile in smem (K-major, 128B swizzle), row sum
+      float l_tile = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < KV; c += 32) {
+        uint32_t sv[32];
+        tmem_ld_x32(tmem_S + lane_base + c, sv);
+        tmem_ld_wait();
+        uint32_t mbits = 0xffffffffu;
+        if (mrow != nullptr) {
+          mbits = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
+        }
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
+          const float e = keep ? exp2f(__uint_as_float(sv[i]) * p.scale_log2 - m_safe) : 0.f;
+          pv[i] = e;
+        }
+        // round to bf16 first so that the row sum matches what the tensor core will accumulate
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+          const float2 back = unpack_bf16x2(pk[i]);
+          l_tile += back.x + back.y;
+        }
+        uint8_t* patom = prow + (c >> 6) * (128 * 128);
+        const uint32_t chunk0 = static_cast<uint32_t>((c & 63) >> 3);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint32_t phys = (chunk0 + v) ^ sw;
+          *reinterpret_cast<uint4*>(patom + phys * 16) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+        }
+      }
+      l_run += l_tile;
+      tc_fence_before();
+      mbar_arrive(s_empty);      // S consumed (next QK^T may overwrite it)
+      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+      mbar_arrive(p_full);
+    }
+    // ---------------- output ----------------
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+    __nv_bfloat16* orow = p.out + (static_cast<int64_t>(g) * p.R + row) * p.ldo + head * p.d;
+#pragma unroll 1
+    for (int c = 0; c < p.dN; c += 16) {
+      uint32_t ov[16];
+      tmem_ld_x16(tmem_O + lane_base + c, ov);
+      tmem_ld_wait();
+      if (!valid) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (c + h * 8 < p.d) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(ov[h * 8 + 0]) * inv, __uint_as_float(ov[h * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(ov[h * 8 + 2]) * inv, __uint_as_float(ov[h * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(ov[h * 8 + 4]) * inv, __uint_as_float(ov[h * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(ov[h * 8 + 6]) * inv, __uint_as_float(ov[h * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c + h * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int DKA, int KV>
+static int launch_attn(const AttnKParams& kp, dim3 grid, cudaStream_t stream) {
+  using Cfg = AttnCfg<DKA, KV>;
+  static bool configured = false;
+  if (!configured) {
+    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::kSmemBytes));
+    configured = true;
+  }
+  attn_tc_kernel<DKA, KV><<<grid, 192, Cfg::kSmemBytes, stream>>>(kp);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace asva
+
+extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(d != nullptr && d->q && d->kv && d->out, "asva_attention: null operand");
+  ASVA_REQUIRE(d->d >= 8 && d->d % 8 == 0 && d->d <= 192, "asva_attention: head dim %d unsupported", d->d);
+  ASVA_REQUIRE(d->dpad % 64 == 0 && d->dpad >= d->d && d->dpad <= 192, "asva_attention: dpad %d invalid", d->dpad);
+  ASVA_REQUIRE(d->G >= 1 && d->heads >= 1 && d->R >= 1 && d->Nk >= 1, "asva_attention: empty problem");
+  ASVA_REQUIRE(d->ldkv % 8 == 0 && d->ldo % 8 == 0 && d->k_col0 % 8 == 0 && d->v_col0 % 8 == 0,
+               "asva_attention: ldkv/ldo/k_col0/v_col0 must be multiples of 8");
+  ASVA_REQUIRE(d->mask == nullptr || d->mask_rows >= 1, "asva_attention: mask_rows must be >= 1");
+  ASVA_REQUIRE(d->kv_rows_per_group >= d->Nk, "asva_attention: kv_rows_per_group < Nk");
+
+  AttnKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.mask = d->mask;
+  kp.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  kp.ldo = d->ldo;
+  kp.mask_ld = d->mask_ld;
+  kp.R = d->R;
+  kp.Nk = d->Nk;
+  kp.d = d->d;
+  kp.dN = ((d->d + 15) / 16) * 16;
+  kp.heads = d->heads;
+  kp.k_col0 = d->k_col0;
+  kp.v_col0 = d->v_col0;
+  kp.mask_rows = d->mask_rows > 0 ? d->mask_rows : 1;
+  kp.ksteps_qk = (d->d + 15) / 16;
+  kp.nvb = (kp.dN + 63) / 64;
+  kp.scale_log2 = d->scale * 1.4426950408889634f;
+  const int dka = d->dpad / 64;
+  const int kv = (dka == 1) ? 128 : 64;
+  {
+    uint64_t dims[3] = {(uint64_t)d->dpad, (uint64_t)d->R, (uint64_t)d->G * (uint64_t)d->heads};
+    uint64_t strides[2] = {(uint64_t)d->dpad * 2u, (uint64_t)d->R * (uint64_t)d->dpad * 2u};
+    uint32_t box[3] = {64u, 128u, 1u};
+    uint32_t el[3] = {1u, 1u, 1u};
+    int rc = make_tmap_bf16(&kp.tmQ, d->q, 3, dims, strides, box, el);
+    if (rc != 0) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->ldkv, (uint64_t)d->Nk, (uint64_t)d->G};
+    uint64_t strides[2] = {(uint64_t)d->ldkv * 2u, (uint64_t)d->kv_rows_per_group * (uint64_t)d->ldkv * 2u};
+    uint32_t box[3] = {64u, (uint32_t)kv, 1u};
+    uint32_t el[3] = {1u, 1u, 1u};
+    int rc = make_tmap_bf16(&kp.tmKV, d->kv, 3, dims, strides, box, el);
+    if (rc != 0) return rc;
+  }
+  dim3 grid((d->R + 127) / 128, d->heads, d->G);
+  ASVA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "asva_attention: grid too large");
+  switch (dka) {
+    case 1: return launch_attn<1, 128>(kp, grid, stream);
+    case 2: return launch_attn<2, 64>(kp, grid, stream);
+    default: return launch_attn<3, 64>(kp, grid, stream);
+  }
+}

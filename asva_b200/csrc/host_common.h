@@ -1,0 +1,35 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, driver entry point for
+// cuTensorMapEncodeTiled (looked up at run time so the library does not link libcuda), launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/asva_b200.h"
+
+namespace asva {
+
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+// Builds a bf16 tiled tensor map with 128-byte swizzle. dims/box/elem_strides have `rank` entries (innermost
+// first); strides_bytes has rank-1 entries (dims 1..rank-1). Returns 0 or a negative asva_status.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+
+#define ASVA_CUDA_OK(expr)                                                                         \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::asva::fail(ASVA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                          __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define ASVA_REQUIRE(cond, ...)                                        \
+  do {                                                                 \
+    if (!(cond)) return ::asva::fail(ASVA_ERR_INVALID, __VA_ARGS__);   \
+  } while (0)
+
+}  // namespace asva

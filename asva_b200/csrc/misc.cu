@@ -1,0 +1,356 @@
+// Small HBM/latency-bound kernels around the tensor-core path: conv_in im2col, conv_out temporal finish,
+// skinny linears (timestep embedding MLP, the 22 time_emb_proj), sinusoidal features, the temporal attention
+// core over the frame axis, and the fused CFG + sampler update.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace asva {
+
+// ------------------------------------------------------------------------------------------------
+// conv_in im2col: fp32 latents [Bs][Cl][F][h][w] -> bf16 rows [B*F*h*w][64], column = tap*Cl + c
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_in_im2col_kernel(const float* __restrict__ lat,
+                                                             __nv_bfloat16* __restrict__ out, int B, int Bs, int Cl,
+                                                             int F, int h, int w) {
+  const int64_t total = static_cast<int64_t>(B) * F * h * w * 8;  // 8 chunks of 8 columns per row
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int chunk = static_cast<int>(i & 7);
+  const int64_t row = i >> 3;
+  const int x = static_cast<int>(row % w);
+  const int y = static_cast<int>((row / w) % h);
+  const int f = static_cast<int>((row / (static_cast<int64_t>(w) * h)) % F);
+  const int b = static_cast<int>(row / (static_cast<int64_t>(w) * h * F));
+  const int bs = b % Bs;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = chunk * 8 + j;
+    float val = 0.f;
+    if (k < 9 * Cl) {
+      const int tap = k / Cl, c = k % Cl;
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+        val = __ldg(lat + (((static_cast<int64_t>(bs) * Cl + c) * F + f) * h + yy) * w + xx);
+    }
+    v[j] = val;
+  }
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + row * 64 + chunk * 8) = u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_out finish: y fp32 [B*F*hw][ldy] -> out[b][c][f][n] = y_f + Wt [y_0 ; y_{max(f-1,0)} ; y_f] + bt
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_out_finish_kernel(const float* __restrict__ y, int ldy,
+                                                              const float* __restrict__ wt,
+                                                              const float* __restrict__ bt, float* __restrict__ out,
+                                                              int B, int Co, int F, int hw) {
+  const int64_t total = static_cast<int64_t>(B) * F * hw;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = static_cast<int>(i % hw);
+  const int f = static_cast<int>((i / hw) % F);
+  const int b = static_cast<int>(i / (static_cast<int64_t>(hw) * F));
+  const int fp = f > 0 ? f - 1 : 0;
+  const float* y0 = y + ((static_cast<int64_t>(b) * F + 0) * hw + n) * ldy;
+  const float* yp = y + ((static_cast<int64_t>(b) * F + fp) * hw + n) * ldy;
+  const float* yc = y + ((static_cast<int64_t>(b) * F + f) * hw + n) * ldy;
+  float cat[24];
+  for (int c = 0; c < Co; ++c) {
+    cat[c] = y0[c];
+    cat[Co + c] = yp[c];
+    cat[2 * Co + c] = yc[c];
+  }
+  for (int c = 0; c < Co; ++c) {
+    float acc = bt[c];
+    for (int j = 0; j < 3 * Co; ++j) acc += wt[c * 3 * Co + j] * cat[j];
+    out[((static_cast<int64_t>(b) * Co + c) * F + f) * hw + n] = yc[c] + acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skinny linear (M <= 32 rows): one warp per output column, 16-byte weight loads, rows in groups of 4.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x,
+                                                           const __nv_bfloat16* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           int M, int N, int K, int act_in, int act_out) {
+  extern __shared__ float xs[];  // [4][K]
+  const int m0 = blockIdx.y * 4;
+  const int mrows = min(4, M - m0);
+  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) {
+    const int r = i / K, k = i % K;
+    float v = (r < mrows) ? x[static_cast<int64_t>(m0 + r) * K + k] : 0.f;
+    if (act_in == 1) v = silu_f(v);
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* wr = w + static_cast<int64_t>(n) * K;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = lane * 8; k < K; k += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(wr + k);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    const float wv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float* xr = xs + r * K + k;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[r] += wv[j] * xr[j];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
+  if (lane == 0) {
+    const float bv = bias != nullptr ? bias[n] : 0.f;
+    for (int r = 0; r < mrows; ++r) {
+      float v = acc[r] + bv;
+      if (act_out == 1) v = silu_f(v);
+      out[static_cast<int64_t>(m0 + r) * N + n] = v;
+    }
+  }
+}
+
+__global__ void timestep_features_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim,
+                                         int flip) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= B * half) return;
+  const int b = i / half, k = i % half;
+  // diffusers get_timestep_embedding: exponent = -ln(10000) * k / (half - shift), shift = 0
+  const float freq = expf(-logf(10000.f) * static_cast<float>(k) / static_cast<float>(half));
+  const float arg = t[b] * freq;
+  const float s = sinf(arg), c = cosf(arg);
+  float* o = out + static_cast<int64_t>(b) * dim;
+  if (flip) {
+    o[k] = c;
+    o[half + k] = s;
+  } else {
+    o[k] = s;
+    o[half + k] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Temporal attention core: one warp per (batch, pixel, head); F x F scores over the frame axis.
+// q/k/v rows are staged in shared memory as fp32 with odd row pitch (bank-conflict free).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) temporal_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            __nv_bfloat16* __restrict__ out, int B, int F, int N,
+                                                            int heads, int d, float scale, int64_t total_items) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pitch = d + 1;
+  const int per_warp = 3 * F * pitch + F * F;
+  float* sq = sm + warp * per_warp;
+  float* sk = sq + F * pitch;
+  float* sv = sk + F * pitch;
+  float* sp = sv + F * pitch;
+  const int C = heads * d;
+  const int dch = d >> 3;
+  for (int64_t item = static_cast<int64_t>(blockIdx.x) * 4 + warp; item < total_items;
+       item += static_cast<int64_t>(gridDim.x) * 4) {
+    const int head = static_cast<int>(item % heads);
+    const int n = static_cast<int>((item / heads) % N);
+    const int b = static_cast<int>(item / (static_cast<int64_t>(heads) * N));
+    // stage q, k, v : 3*F*dch chunks of 8 bf16
+    for (int i = lane; i < 3 * F * dch; i += 32) {
+      const int chn = i % dch;
+      const int f = (i / dch) % F;
+      const int part = i / (dch * F);
+      const __nv_bfloat16* src =
+          qkv + ((static_cast<int64_t>(b) * F + f) * N + n) * (3 * C) + part * C + head * d + chn * 8;
+      const uint4 u = *reinterpret_cast<const uint4*>(src);
+      const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), dd = unpack_bf16x2(u.w);
+      float* dst = sq + part * F * pitch + f * pitch + chn * 8;
+      dst[0] = a.x; dst[1] = a.y; dst[2] = bb.x; dst[3] = bb.y;
+      dst[4] = c.x; dst[5] = c.y; dst[6] = dd.x; dst[7] = dd.y;
+    }
+    __syncwarp();
+    // scores
+    for (int pr = lane; pr < F * F; pr += 32) {
+      const int fq = pr / F, fk = pr % F;
+      const float* qr = sq + fq * pitch;
+      const float* kr = sk + fk * pitch;
+      float acc = 0.f;
+      for (int j = 0; j < d; ++j) acc += qr[j] * kr[j];
+      sp[pr] = acc * scale;
+    }
+    __syncwarp();
+    // softmax per query row
+    for (int fq = lane; fq < F; fq += 32) {
+      float* pr = sp + fq * F;
+      float m = -INFINITY;
+      for (int k = 0; k < F; ++k) m = fmaxf(m, pr[k]);
+      float s = 0.f;
+      for (int k = 0; k < F; ++k) {
+        const float e = __expf(pr[k] - m);
+        pr[k] = e;
+        s += e;
+      }
+      const float inv = 1.f / s;
+      for (int k = 0; k < F; ++k) pr[k] *= inv;
+    }
+    __syncwarp();
+    // output: lane pairs (fq, 2 features)
+    const int dh = d >> 1;
+    for (int i = lane; i < F * dh; i += 32) {
+      const int fq = i / dh, j2 = (i % dh) * 2;
+      const float* pr = sp + fq * F;
+      float o0 = 0.f, o1 = 0.f;
+      for (int k = 0; k < F; ++k) {
+        const float pk = pr[k];
+        o0 += pk * sv[k * pitch + j2];
+        o1 += pk * sv[k * pitch + j2 + 1];
+      }
+      __nv_bfloat16* dst = out + ((static_cast<int64_t>(b) * F + fq) * N + n) * C + head * d + j2;
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o0, o1);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CFG combine + sampler update (fp32, frames 1..F-1 only).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__ eps, int k,
+                                                       float* __restrict__ lat, float* __restrict__ hist,
+                                                       const float* __restrict__ coef,
+                                                       const int32_t* __restrict__ slots, int C, int F, int hw,
+                                                       int plms) {
+  const int64_t per_c = static_cast<int64_t>(F - 1) * hw;
+  const int64_t total = per_c * C;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i / per_c);
+  const int64_t rem = i % per_c;  // (f-1)*hw + n
+  const int64_t idx = (static_cast<int64_t>(c) * F + 1) * hw + rem;
+  const int64_t stride_b = static_cast<int64_t>(C) * F * hw;
+  float e = 0.f;
+  for (int j = 0; j < k; ++j) e += coef[j] * eps[j * stride_b + idx];
+  const float cs = coef[3], ce = coef[4];
+  float ehat = e;
+  if (plms) {
+    // coef[5..8] = weights on (e, hist[slots[1]], hist[slots[2]], hist[slots[3]]); slots[0] = store slot or -1
+    ehat = coef[5] * e;
+    for (int j = 1; j < 4; ++j) {
+      const float a = coef[5 + j];
+      if (a != 0.f) ehat += a * hist[static_cast<int64_t>(slots[j]) * stride_b + idx];
+    }
+    if (slots[0] >= 0) hist[static_cast<int64_t>(slots[0]) * stride_b + idx] = e;
+  }
+  lat[idx] = cs * lat[idx] + ce * ehat;
+}
+
+}  // namespace asva
+
+extern "C" int asva_conv_in_im2col(const float* latents, void* out, int32_t B, int32_t Bs, int32_t Cl, int32_t F,
+                                   int32_t h, int32_t w, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(latents && out, "asva_conv_in_im2col: null operand");
+  ASVA_REQUIRE(Cl >= 1 && 9 * Cl <= 64, "asva_conv_in_im2col: Cl=%d unsupported (9*Cl must be <= 64)", Cl);
+  ASVA_REQUIRE(B >= 1 && Bs >= 1 && F >= 1 && h >= 1 && w >= 1, "asva_conv_in_im2col: empty problem");
+  const int64_t total = static_cast<int64_t>(B) * F * h * w * 8;
+  conv_in_im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      latents, reinterpret_cast<__nv_bfloat16*>(out), B, Bs, Cl, F, h, w);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int asva_conv_out_finish(const float* y, int32_t ldy, const float* wt, const float* bt, float* out,
+                                    int32_t B, int32_t Co, int32_t F, int32_t h, int32_t w, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(y && wt && bt && out, "asva_conv_out_finish: null operand");
+  ASVA_REQUIRE(Co >= 1 && Co <= 8 && ldy >= Co, "asva_conv_out_finish: Co=%d unsupported", Co);
+  const int64_t total = static_cast<int64_t>(B) * F * h * w;
+  conv_out_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(y, ldy, wt, bt, out, B, Co,
+                                                                                         F, h * w);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int asva_small_linear(const float* x, const void* w, const float* bias, float* out, int32_t M, int32_t N,
+                                 int32_t K, int32_t act_in, int32_t act_out, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(x && w && out, "asva_small_linear: null operand");
+  ASVA_REQUIRE(M >= 1 && M <= 32 && N >= 1 && K >= 8 && K % 8 == 0 && K <= 8192, "asva_small_linear: bad shape");
+  static bool configured = false;
+  if (!configured) {
+    ASVA_CUDA_OK(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8192 * 4));
+    configured = true;
+  }
+  dim3 grid((N + 7) / 8, (M + 3) / 4);
+  small_linear_kernel<<<grid, 256, static_cast<size_t>(4) * K * sizeof(float), stream>>>(
+      x, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N, K, act_in, act_out);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int asva_timestep_features(const float* t, float* out, int32_t B, int32_t dim, int32_t flip_sin_to_cos,
+                                      asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(t && out && B >= 1 && dim >= 2 && dim % 2 == 0, "asva_timestep_features: bad arguments");
+  const int total = B * (dim / 2);
+  timestep_features_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, out, B, dim, flip_sin_to_cos);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                       int32_t d, float scale, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(qkv && out, "asva_temporal_attention: null operand");
+  ASVA_REQUIRE(d % 8 == 0 && d >= 8 && F >= 1 && F <= 64, "asva_temporal_attention: d=%d F=%d unsupported", d, F);
+  const size_t smem = static_cast<size_t>(4) * (3 * F * (d + 1) + F * F) * sizeof(float);
+  ASVA_REQUIRE(smem <= 200 * 1024, "asva_temporal_attention: F=%d d=%d needs %zu B smem", F, d, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    ASVA_CUDA_OK(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int64_t items = static_cast<int64_t>(B) * N * heads;
+  int64_t blocks = (items + 3) / 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  temporal_attn_kernel<<<static_cast<unsigned>(blocks), 128, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), B, F, N, heads, d, scale,
+      items);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int asva_cfg_ddim_step(const float* eps, int32_t k, float* latents, const float* coef, int32_t C,
+                                  int32_t F, int32_t hw, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(eps && latents && coef && k >= 1 && k <= 3 && F >= 2, "asva_cfg_ddim_step: bad arguments");
+  const int64_t total = static_cast<int64_t>(C) * (F - 1) * hw;
+  cfg_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(eps, k, latents, nullptr, coef,
+                                                                                  nullptr, C, F, hw, 0);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int asva_cfg_plms_step(const float* eps, int32_t k, float* latents, float* hist, const float* coef,
+                                  const int32_t* slots, int32_t C, int32_t F, int32_t hw, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(eps && latents && hist && coef && slots && k >= 1 && k <= 3 && F >= 2,
+               "asva_cfg_plms_step: bad arguments");
+  const int64_t total = static_cast<int64_t>(C) * (F - 1) * hw;
+  cfg_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(eps, k, latents, hist, coef, slots,
+                                                                                  C, F, hw, 1);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}

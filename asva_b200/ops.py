@@ -1,0 +1,376 @@
+"""Tensor-level operator layer over the C ABI (include/asva_b200.h).
+
+`GemmSpec` / `AttnSpec` mirror `asva_gemm_desc` / `asva_attn_desc` field for field but hold torch tensors
+instead of raw pointers.  The builder functions (`spec_linear`, `spec_conv3x3`, `spec_tconv`, ...) encode how each
+reference operator maps onto the generic kernels; the backend object executes a spec.  The only product backend
+is `CudaBackend` (ctypes -> libasva_b200.so).  tests/sim_backend.py interprets the same specs with torch on the
+CPU so the descriptor logic can be checked against the oracle without a GPU - it is test infrastructure and is
+never importable from this package."""
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+BIG = 1 << 30
+
+
+@dataclass
+class Seg:
+    src: int
+    c0: int
+    off: Tuple[int, int, int]
+    num_kb: int
+
+
+@dataclass
+class RowAdd:
+    t: torch.Tensor  # fp32; element [arow * ld + col (+ sel_off)]
+    ld: int
+    div_outer: int
+    mul_outer: int
+    mod_inner: int
+    sel_lt: int = 0
+    sel_off: int = 0
+
+
+@dataclass
+class AView:
+    """4-D (c, d1, d2, d3) channels-innermost view of a bf16 tensor (element strides for d1..d3)."""
+    t: torch.Tensor
+    dims: Tuple[int, int, int, int]
+    strides: Tuple[int, int, int]
+
+
+@dataclass
+class GemmSpec:
+    a: List[Optional[AView]]
+    box: Tuple[int, int, int]
+    trav: Tuple[int, int, int]
+    out_dims: Tuple[int, int, int]
+    segs: List[Seg]
+    w: torch.Tensor  # bf16 [>=N, ldw]
+    ldw: int
+    N: int
+    K: int
+    out: torch.Tensor
+    bias: Optional[torch.Tensor] = None
+    add: List[Optional[RowAdd]] = field(default_factory=lambda: [None, None])
+    res: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
+    res_ld: List[int] = field(default_factory=lambda: [0, 0])
+    geglu: bool = False
+    out_fp32: bool = False
+    row_div: int = 1
+    row_s1: int = 0
+    row_s0: int = 0
+    col_div: int = BIG
+    col_s1: int = 0
+    block_n: int = 0
+
+    @property
+    def M(self) -> int:
+        return self.out_dims[0] * self.out_dims[1] * self.out_dims[2]
+
+
+@dataclass
+class AttnSpec:
+    q: torch.Tensor  # bf16 [G, heads, R, dpad]
+    kv: torch.Tensor  # bf16 rows of ldkv
+    out: torch.Tensor  # bf16 [G*R, ldo]
+    G: int
+    heads: int
+    R: int
+    Nk: int
+    d: int
+    dpad: int
+    ldkv: int
+    ldo: int
+    kv_rows_per_group: int
+    k_col0: int
+    v_col0: int
+    scale: float
+    mask: Optional[torch.Tensor] = None  # uint8 [G*R/mask_rows, mask_ld]
+    mask_ld: int = 0
+    mask_rows: int = 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# spec builders
+# ---------------------------------------------------------------------------------------------------
+def pick_box(dims: Sequence[int], limit: int = 128) -> Tuple[int, int, int]:
+    """Largest (b1, b2, b3) box with b1*b2*b3 <= limit, filling the innermost dimension first."""
+    b1 = min(dims[0], limit)
+    b2 = min(dims[1], max(1, limit // b1))
+    b3 = min(dims[2], max(1, limit // (b1 * b2)))
+    return (b1, b2, b3)
+
+
+def _plain_out(spec: GemmSpec, ldo: int) -> None:
+    spec.row_div, spec.row_s1, spec.row_s0 = 1, ldo, 0
+    spec.col_div, spec.col_s1 = BIG, 0
+
+
+def _rows_view(x: torch.Tensor) -> AView:
+    assert x.dim() == 2 and x.stride(1) == 1, "expected a [rows, channels] view with contiguous channels"
+    M, K = x.shape
+    ld = x.stride(0)
+    return AView(x, (K, M, 1, 1), (ld, ld * max(M, 1), ld * max(M, 1)))
+
+
+def spec_linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, x2: Optional[torch.Tensor] = None,
+                bias: Optional[torch.Tensor] = None, res0: Optional[torch.Tensor] = None,
+                res1: Optional[torch.Tensor] = None, geglu: bool = False, out_fp32: bool = False) -> GemmSpec:
+    """out[M, N] = [x | x2] @ w[N, K]^T (+bias, +residuals, GEGLU).  x, x2, out: 2-D row views."""
+    M, K0 = x.shape
+    N, K = w.shape
+    segs = [Seg(0, 0, (0, 0, 0), K0 // 64)]
+    a = [_rows_view(x), None]
+    if x2 is not None:
+        assert x2.shape[0] == M
+        a[1] = _rows_view(x2)
+        segs.append(Seg(1, 0, (0, 0, 0), x2.shape[1] // 64))
+    assert sum(s.num_kb for s in segs) * 64 == K, (K0, K)
+    spec = GemmSpec(a=a, box=(min(M, 128), 1, 1), trav=(1, 1, 1), out_dims=(M, 1, 1), segs=segs, w=w,
+                    ldw=w.stride(0), N=N, K=K, out=out, bias=bias, geglu=geglu, out_fp32=out_fp32)
+    spec.res = [res0, res1]
+    spec.res_ld = [r.stride(0) if r is not None else 0 for r in spec.res]
+    _plain_out(spec, out.stride(0))
+    return spec
+
+
+def spec_rows3(x: AView, box_dims: Tuple[int, int, int], w: torch.Tensor, out: torch.Tensor, *,
+               bias: Optional[torch.Tensor] = None, out_fp32: bool = False) -> GemmSpec:
+    """Plain GEMM over a strided 3-level row set (e.g. the frame-0 rows of every clip)."""
+    N, K = w.shape
+    assert K == x.dims[0]
+    spec = GemmSpec(a=[x, None], box=pick_box(box_dims), trav=(1, 1, 1), out_dims=tuple(box_dims),
+                    segs=[Seg(0, 0, (0, 0, 0), K // 64)], w=w, ldw=w.stride(0), N=N, K=K, out=out, bias=bias,
+                    out_fp32=out_fp32)
+    _plain_out(spec, out.stride(0))
+    return spec
+
+
+def spec_conv3x3(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n_img: int, h: int, wd: int,
+                 stride: int = 1, bias: Optional[torch.Tensor] = None, out_fp32: bool = False) -> GemmSpec:
+    """Implicit-GEMM 3x3 conv, padding 1.  x: [n_img*h*wd, Cin] channels-last; w: [Cout, 9*Cin] with K index
+    (ky*3 + kx)*Cin + c; out: [n_img*ho*wo, >=Cout]."""
+    Cin = x.shape[1]
+    N, K = w.shape
+    assert K == 9 * Cin and Cin % 64 == 0 and x.stride(1) == 1 and x.stride(0) == Cin
+    ho, wo = (h + 2 - 3) // stride + 1, (wd + 2 - 3) // stride + 1
+    segs = [Seg(0, 0, (kx - 1, ky - 1, 0), Cin // 64) for ky in range(3) for kx in range(3)]
+    av = AView(x, (Cin, wd, h, n_img), (Cin, wd * Cin, h * wd * Cin))
+    spec = GemmSpec(a=[av, None], box=pick_box((wo, ho, n_img)), trav=(stride, stride, 1),
+                    out_dims=(wo, ho, n_img), segs=segs, w=w, ldw=w.stride(0), N=N, K=K, out=out, bias=bias,
+                    out_fp32=out_fp32)
+    _plain_out(spec, out.stride(0))
+    return spec
+
+
+def spec_tconv(y: torch.Tensor, w2: torch.Tensor, out: torch.Tensor, *, B: int, F: int, N: int,
+               head_term: torch.Tensor, tproj: Optional[torch.Tensor] = None, tproj_ld: int = 0,
+               res1: Optional[torch.Tensor] = None) -> GemmSpec:
+    """conv_temp main GEMM (utils.py:43-53 restated):  out_f = y_f + Wc y_f + Wp y_{f-1} + H   where the frame-0
+    term H = Wh y_0 + bt (+ Wp y_0 for f = 0, whose "previous frame" is itself) comes from `head_term`
+    (fp32 [B*N, 2C]: columns [0,C) for f >= 1, [C,2C) for f = 0).  y, out: [B*F*N, C]; w2: [C, 2C] = [Wc | Wp].
+    The previous-frame segment reads frame f-1 through a -1 coordinate offset; f = 0 hits TMA zero fill."""
+    Cc = y.shape[1]
+    assert w2.shape == (Cc, 2 * Cc) and y.stride(0) == Cc
+    av = AView(y, (Cc, N, F, B), (Cc, N * Cc, F * N * Cc))
+    segs = [Seg(0, 0, (0, 0, 0), Cc // 64), Seg(0, 0, (0, -1, 0), Cc // 64)]
+    spec = GemmSpec(a=[av, None], box=pick_box((N, F, B)), trav=(1, 1, 1), out_dims=(N, F, B), segs=segs, w=w2,
+                    ldw=w2.stride(0), N=Cc, K=2 * Cc, out=out)
+    spec.add[0] = RowAdd(head_term, 2 * Cc, div_outer=F * N, mul_outer=N, mod_inner=N, sel_lt=N, sel_off=Cc)
+    if tproj is not None:
+        spec.add[1] = RowAdd(tproj, tproj_ld, div_outer=F * N, mul_outer=1, mod_inner=1)
+    spec.res = [y, res1]
+    spec.res_ld = [Cc, res1.stride(0) if res1 is not None else 0]
+    _plain_out(spec, out.stride(0))
+    return spec
+
+
+def spec_tconv_head(y: torch.Tensor, w_head: torch.Tensor, bias2: torch.Tensor, out: torch.Tensor, *, B: int,
+                    F: int, N: int) -> GemmSpec:
+    """Frame-0 term of conv_temp: out[b*N + n, :] = [Wh ; Wh + Wp] y[b, 0, n] + [bt ; bt]  (fp32 [B*N, 2C])."""
+    Cc = y.shape[1]
+    av = AView(y, (Cc, N, B, 1), (Cc, F * N * Cc, B * F * N * Cc))
+    return spec_rows3(av, (N, B, 1), w_head, out, bias=bias2, out_fp32=True)
+
+
+def set_headsplit_out(spec: GemmSpec, *, rows_per_group: int, heads: int, d: int, dpad: int) -> None:
+    """Route the GEMM output into the attention kernel's Q layout [G][heads][rows_per_group][dpad]."""
+    spec.row_div, spec.row_s1, spec.row_s0 = rows_per_group, heads * rows_per_group * dpad, dpad
+    spec.col_div, spec.col_s1 = d, rows_per_group * dpad
+
+
+# ---------------------------------------------------------------------------------------------------
+# CUDA backend
+# ---------------------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class CudaBackend:
+    """Executes specs through libasva_b200.so on the current CUDA stream. No fallback of any kind."""
+
+    name = "cuda"
+
+    def __init__(self) -> None:
+        self.lib = _lib.load()
+        self.launches = 0
+
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _chk_dev(*ts: Optional[torch.Tensor]) -> None:
+        for t in ts:
+            if t is not None and not t.is_cuda:
+                raise _lib.AsvaError("asva_b200 operators need CUDA tensors (no CPU fallback)")
+
+    def gemm(self, s: GemmSpec) -> None:
+        d = _lib.GemmDesc()
+        for i in range(2):
+            av = s.a[i]
+            if av is None:
+                d.a[i] = None
+                continue
+            self._chk_dev(av.t)
+            assert av.t.dtype == torch.bfloat16
+            d.a[i] = av.t.data_ptr()
+            for j in range(4):
+                d.a_dims[i][j] = av.dims[j]
+            for j in range(3):
+                d.a_strides[i][j] = av.strides[j]
+        for j in range(3):
+            d.box[j], d.trav[j], d.out_dims[j] = s.box[j], s.trav[j], s.out_dims[j]
+        d.nseg = len(s.segs)
+        for i, sg in enumerate(s.segs):
+            d.seg[i].src, d.seg[i].c0, d.seg[i].num_kb = sg.src, sg.c0, sg.num_kb
+            for j in range(3):
+                d.seg[i].off[j] = sg.off[j]
+        self._chk_dev(s.w, s.out, s.bias)
+        assert s.w.dtype == torch.bfloat16
+        d.w, d.ldw, d.N, d.K = s.w.data_ptr(), s.ldw, s.N, s.K
+        if s.bias is not None:
+            assert s.bias.dtype == torch.float32 and s.bias.numel() >= s.N
+        d.bias = _ptr(s.bias)
+        for i in range(2):
+            ra = s.add[i]
+            if ra is not None:
+                self._chk_dev(ra.t)
+                assert ra.t.dtype == torch.float32
+                d.add[i].ptr, d.add[i].ld = ra.t.data_ptr(), ra.ld
+                d.add[i].div_outer, d.add[i].mul_outer, d.add[i].mod_inner = ra.div_outer, ra.mul_outer, ra.mod_inner
+                d.add[i].sel_lt, d.add[i].sel_off = ra.sel_lt, ra.sel_off
+            r = s.res[i]
+            if r is not None:
+                self._chk_dev(r)
+                assert r.dtype == torch.bfloat16
+            d.res[i] = _ptr(r)
+            d.res_ld[i] = s.res_ld[i]
+        d.geglu, d.out_fp32 = int(s.geglu), int(s.out_fp32)
+        assert s.out.dtype == (torch.float32 if s.out_fp32 else torch.bfloat16)
+        d.out = s.out.data_ptr()
+        d.row_s1, d.row_s0, d.col_s1 = s.row_s1, s.row_s0, s.col_s1
+        d.row_div, d.col_div, d.block_n = s.row_div, s.col_div, s.block_n
+        _lib.check(self.lib.asva_gemm(d, self._stream()), "asva_gemm")
+        self.launches += 1
+
+    def attention(self, s: AttnSpec) -> None:
+        self._chk_dev(s.q, s.kv, s.out, s.mask)
+        d = _lib.AttnDesc()
+        d.q, d.kv, d.mask, d.out = s.q.data_ptr(), s.kv.data_ptr(), _ptr(s.mask), s.out.data_ptr()
+        d.ldkv, d.ldo, d.mask_ld = s.ldkv, s.ldo, s.mask_ld
+        d.G, d.heads, d.R, d.Nk, d.d, d.dpad = s.G, s.heads, s.R, s.Nk, s.d, s.dpad
+        d.kv_rows_per_group, d.k_col0, d.v_col0, d.mask_rows = s.kv_rows_per_group, s.k_col0, s.v_col0, s.mask_rows
+        d.scale = s.scale
+        _lib.check(self.lib.asva_attention(d, self._stream()), "asva_attention")
+        self.launches += 1
+
+    def temporal_attention(self, qkv, out, B, F, N, heads, d, scale) -> None:
+        self._chk_dev(qkv, out)
+        _lib.check(self.lib.asva_temporal_attention(qkv.data_ptr(), out.data_ptr(), B, F, N, heads, d, scale,
+                                                    self._stream()), "asva_temporal_attention")
+        self.launches += 1
+
+    def layernorm(self, x, gamma, beta, pos, out, M, C, eps, N, F) -> None:
+        self._chk_dev(x, gamma, beta, pos, out)
+        _lib.check(self.lib.asva_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(pos),
+                                           out.data_ptr(), M, C, eps, N, F, self._stream()), "asva_layernorm")
+        self.launches += 1
+
+    def groupnorm_ws_floats(self, n_inst, rows, C) -> int:
+        return int(self.lib.asva_groupnorm_ws_floats(n_inst, rows, C))
+
+    def groupnorm_stats(self, x0, C0, x1, C1, n_inst, rows, groups, eps, stats, ws) -> None:
+        self._chk_dev(x0, x1, stats, ws)
+        assert ws.numel() >= self.groupnorm_ws_floats(n_inst, rows, C0 + (C1 if x1 is not None else 0))
+        _lib.check(self.lib.asva_groupnorm_stats(x0.data_ptr(), C0, _ptr(x1), C1, n_inst, rows, groups, eps,
+                                                 stats.data_ptr(), ws.data_ptr(), self._stream()),
+                   "asva_groupnorm_stats")
+        self.launches += 2
+
+    def groupnorm_apply(self, x0, C0, x1, C1, stats, gamma, beta, groups, n_inst, n_img, h, w, silu, upsample,
+                        out) -> None:
+        self._chk_dev(x0, x1, stats, gamma, beta, out)
+        _lib.check(self.lib.asva_groupnorm_apply(x0.data_ptr(), C0, _ptr(x1), C1, _ptr(stats), _ptr(gamma),
+                                                 _ptr(beta), groups, n_inst, n_img, h, w, int(silu), int(upsample),
+                                                 out.data_ptr(), self._stream()), "asva_groupnorm_apply")
+        self.launches += 1
+
+    def conv_in_im2col(self, lat, out, B, Bs, Cl, F, h, w) -> None:
+        self._chk_dev(lat, out)
+        assert lat.dtype == torch.float32 and lat.is_contiguous()
+        _lib.check(self.lib.asva_conv_in_im2col(lat.data_ptr(), out.data_ptr(), B, Bs, Cl, F, h, w, self._stream()),
+                   "asva_conv_in_im2col")
+        self.launches += 1
+
+    def conv_out_finish(self, y, ldy, wt, bt, out, B, Co, F, h, w) -> None:
+        self._chk_dev(y, wt, bt, out)
+        _lib.check(self.lib.asva_conv_out_finish(y.data_ptr(), ldy, wt.data_ptr(), bt.data_ptr(), out.data_ptr(), B,
+                                                 Co, F, h, w, self._stream()), "asva_conv_out_finish")
+        self.launches += 1
+
+    def small_linear(self, x, w, bias, out, M, N, K, act_in, act_out) -> None:
+        self._chk_dev(x, w, bias, out)
+        _lib.check(self.lib.asva_small_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K,
+                                              act_in, act_out, self._stream()), "asva_small_linear")
+        self.launches += 1
+
+    def timestep_features(self, t, out, B, dim, flip) -> None:
+        self._chk_dev(t, out)
+        _lib.check(self.lib.asva_timestep_features(t.data_ptr(), out.data_ptr(), B, dim, int(flip), self._stream()),
+                   "asva_timestep_features")
+        self.launches += 1
+
+    def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw) -> None:
+        self._chk_dev(eps, lat, coef)
+        _lib.check(self.lib.asva_cfg_ddim_step(eps.data_ptr(), k, lat.data_ptr(), coef.data_ptr(), C, F, hw,
+                                               self._stream()), "asva_cfg_ddim_step")
+        self.launches += 1
+
+    def cfg_plms_step(self, eps, k, lat, hist, coef, slots, C, F, hw) -> None:
+        self._chk_dev(eps, lat, hist, coef, slots)
+        _lib.check(self.lib.asva_cfg_plms_step(eps.data_ptr(), k, lat.data_ptr(), hist.data_ptr(), coef.data_ptr(),
+                                               slots.data_ptr(), C, F, hw, self._stream()), "asva_cfg_plms_step")
+        self.launches += 1
+
+
+_backend = None
+
+
+def backend():
+    """The process-wide operator backend (CUDA). Raises if libasva_b200.so is unavailable."""
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def _set_backend_for_tests(b) -> None:
+    """Test hook: tests/ installs the torch simulator here to check descriptor logic on CPU."""
+    global _backend
+    _backend = b

@@ -1,0 +1,190 @@
+/*
+ * asva_b200.h — C ABI of libasva_b200.so: the B200 (sm_100a) kernels behind ASVA's denoising hot path.
+ *
+ * The reference (lzhangbj/ASVA) is pure Python/PyTorch and has no FFI of its own; its operator seams are
+ * Python callables.  Each entry point below replaces the ATen/cuDNN/cuBLAS library calls
+ * that one reference function dispatches; the reference file:line it stands in for is cited per function.
+ * All pointers are DEVICE pointers owned by the caller (borrowed from torch tensors); the library never
+ * allocates device memory, never synchronises, and is CUDA-graph capturable.  Every function returns 0 on
+ * success or a negative asva_status; asva_last_error() gives the message (thread-local).
+ *
+ * Activation layout everywhere: channels-last tokens  x[b][f][y][x][c]  (bf16), i.e. the reference's
+ * "(b f) (h w) c" token layout (ff_spatio_audio_temp_transformer_3d.py:121) kept for the whole UNet.
+ */
+#ifndef ASVA_B200_H
+#define ASVA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* asva_stream_t; /* cudaStream_t */
+
+enum asva_status {
+  ASVA_OK = 0,
+  ASVA_ERR_INVALID = -1, /* bad descriptor (shape/alignment/unsupported size) */
+  ASVA_ERR_CUDA = -2,    /* CUDA runtime / driver error at launch */
+  ASVA_ERR_DEVICE = -3   /* not an sm_100 device */
+};
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Generic tensor-core GEMM   out[M, N] = epilogue( A[M, K] * W[N, K]^T )        (tcgen05.mma, TMEM accumulators,
+ * TMA-fed).  A is described as a 4-D view (c, d1, d2, d3) of up to two bf16 sources; a tile of <=128 output rows
+ * is a box over (d1, d2, d3) and the K loop walks a table of segments, each a (source, channel offset, coordinate
+ * offset) triple -> this one kernel is the plain linear layer, the 1x1 conv, the implicit-GEMM 3x3 conv
+ * (9 segments = taps, zero padding by TMA out-of-bounds fill, stride 2 by TMA traversal strides), the two-source
+ * skip-concat 1x1 conv and the temporal 3-tap "conv_temp" GEMM (segments = current / previous frame).
+ * Replaces: nn.Conv2d + nn.Linear inside FFInflatedConv3d (avgen/models/unets/utils.py:22-57), the diffusers
+ * Attention projections and FeedForward/GEGLU linears (ff_spatio_audio_temp_transformer_3d.py:199-276).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct asva_gemm_seg {
+  int32_t src;    /* 0 -> a[0], 1 -> a[1] */
+  int32_t c0;     /* first channel inside the source */
+  int32_t off[3]; /* input-space coordinate offsets along d1..d3 (may be negative: zero fill) */
+  int32_t num_kb; /* number of 64-wide K blocks in this segment */
+} asva_gemm_seg;
+
+typedef struct asva_rowadd { /* fp32 addend broadcast over part of the output-row index */
+  const float* ptr;          /* NULL = disabled */
+  int64_t ld;
+  int32_t div_outer, mul_outer, mod_inner; /* arow = (row / div_outer) * mul_outer + (row % mod_inner) */
+  int32_t sel_lt, sel_off;                 /* if ((row % div_outer) < sel_lt) column += sel_off */
+} asva_rowadd;
+
+#define ASVA_GEMM_MAX_SEG 10
+
+typedef struct asva_gemm_desc {
+  /* A operand */
+  const void* a[2];        /* bf16 sources; a[1] may be NULL */
+  int64_t a_dims[2][4];    /* per source: extents (c, d1, d2, d3) in input space */
+  int64_t a_strides[2][3]; /* per source: element strides of d1, d2, d3 (c is contiguous) */
+  int32_t box[3];          /* tile extents along d1..d3 in output space; product <= 128 */
+  int32_t trav[3];         /* traversal stride (1 or 2) along d1..d3: in = out * trav + off */
+  int32_t out_dims[3];     /* output-space extents along d1..d3; M = product; row = (o3*D2 + o2)*D1 + o1 */
+  int32_t nseg;
+  asva_gemm_seg seg[ASVA_GEMM_MAX_SEG];
+  /* W operand: [N, K] row-major bf16 */
+  const void* w;
+  int64_t ldw;
+  int32_t N;
+  int32_t K; /* = 64 * sum(seg.num_kb) */
+  /* epilogue */
+  const float* bias; /* [N] fp32 or NULL */
+  asva_rowadd add[2];
+  const void* res[2]; /* bf16 residuals addressed res[i][row * res_ld[i] + col]; NULL = disabled */
+  int64_t res_ld[2];
+  int32_t geglu; /* 1: each 128-column tile holds [64 value | 64 gate] columns; writes N/2 columns */
+  int32_t out_fp32;
+  /* output addressing: off = (row/row_div)*row_s1 + (row%row_div)*row_s0 + (col/col_div)*col_s1 + (col%col_div) */
+  void* out;
+  int64_t row_s1, row_s0, col_s1;
+  int32_t row_div, col_div;
+  int32_t block_n; /* 0 = auto; 64 / 128 / 160 */
+  int32_t reserved;
+} asva_gemm_desc;
+
+int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused softmax(Q K^T * scale [+ mask]) V on tcgen05 (flash-style online softmax, S and O in TMEM).
+ * Replaces F.scaled_dot_product_attention in FFAttnProcessor (utils.py:151-153: first-frame spatial attention,
+ * all frames of a clip share the keys/values of frame 0) and in diffusers AttnProcessor2_0 for attn_audio /
+ * attn2 (ff_spatio_audio_temp_transformer_3d.py:315-341; bool mask, True = attend).
+ *   q   : bf16 [G][heads][R][dpad]   head-split, columns >= d are zero (written by asva_gemm's addressing)
+ *   kv  : bf16 rows of ldkv elements; key j of group g is row g*kv_rows_per_group + j; K at column
+ *         k_col0 + head*d, V at column v_col0 + head*d
+ *   mask: uint8 [G*R / mask_rows][mask_ld] (1 = attend) or NULL; query row r of group g uses mask row
+ *         (g*R + r) / mask_rows
+ *   out : bf16 [G*R][ldo], head h at columns h*d .. h*d+d-1
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct asva_attn_desc {
+  const void* q;
+  const void* kv;
+  const uint8_t* mask;
+  void* out;
+  int64_t ldkv, ldo, mask_ld;
+  int32_t G, heads, R, Nk, d, dpad;
+  int32_t kv_rows_per_group, k_col0, v_col0, mask_rows;
+  float scale;
+  int32_t reserved;
+} asva_attn_desc;
+
+int asva_attention(const asva_attn_desc* d, asva_stream_t stream);
+
+/* Temporal self-attention core over the frame axis (F x F per pixel and head), CUDA cores.
+ * Replaces the SDPA inside attn_temp (ff_spatio_audio_temp_transformer_3d.py:352-358).
+ *   qkv : bf16 [B][F][N][3C] (q | k | v), out: bf16 [B][F][N][C] */
+int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                            int32_t d, float scale, asva_stream_t stream);
+
+/* LayerNorm over C (eps, affine) of x[M][C] (+ optional positional rows pos[F][C] added BEFORE the norm, frame
+ * index = (row / N) % F) -> bf16.  Replaces nn.LayerNorm norm1/norm_audio/norm2/norm_temp/norm3
+ * (ff_spatio_audio_temp_transformer_3d.py:288-362; pos added at :352). */
+int asva_layernorm(const void* x, const float* gamma, const float* beta, const float* pos, void* out, int64_t M,
+                   int32_t C, float eps, int32_t N, int32_t F, asva_stream_t stream);
+
+/* GroupNorm statistics over channels-last data.  Instance i covers rows [i*rows, (i+1)*rows) of the (virtually
+ * concatenated) sources x0[.,C0] | x1[.,C1]; group g covers channels [g*(C0+C1)/groups, ...).  Writes
+ * stats[i][g] = (mean, rstd).  Replaces the statistics half of nn.GroupNorm in FFSpatioTempResnetBlock3D
+ * (resnets/ff_spatio_temp_resnet_3d.py:164,175; instance = one clip, all frames), the per-frame GroupNorm of
+ * the transformer (ff_spatio_audio_temp_transformer_3d.py:117) and conv_norm_out
+ * (audio_cond_unet_3d_condition.py:791). */
+int asva_groupnorm_stats(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t n_inst, int64_t rows,
+                         int32_t groups, float eps, float* stats, float* partial_ws, asva_stream_t stream);
+/* number of floats asva_groupnorm_stats needs in partial_ws */
+int64_t asva_groupnorm_ws_floats(int32_t n_inst, int64_t rows, int32_t C /* C0 + C1 */);
+
+/* GroupNorm apply (+ optional SiLU, + optional nearest 2x spatial upsample, + channel concat of two sources)
+ * -> bf16 [n_img][h_out][w_out][C0+C1].  upsample=1 replicates each source pixel 2x2
+ * (F.interpolate nearest, ff_spatio_temp_resnet_3d.py:47); stats==NULL skips the normalisation. */
+int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* stats,
+                         const float* gamma, const float* beta, int32_t groups, int32_t n_inst, int32_t n_img,
+                         int32_t h, int32_t w, int32_t silu, int32_t upsample, void* out, asva_stream_t stream);
+
+/* conv_in front end: fp32 latents [Bs][Cl][F][h][w] (Cl<=7) -> bf16 im2col rows [B*F*h*w][64] for the 3x3, pad 1
+ * conv (column = tap*Cl + c, zero padded to 64); batch b reads latent b % Bs (CFG duplication,
+ * pipeline_audio_cond_animation.py:331-336). */
+int asva_conv_in_im2col(const float* latents, void* out, int32_t B, int32_t Bs, int32_t Cl, int32_t F, int32_t h,
+                        int32_t w, asva_stream_t stream);
+
+/* conv_out back end: y fp32 [B*F*h*w][ldy] (first Co columns valid) -> conv_temp (Linear(3Co -> Co) over
+ * [frame 0 | previous frame | current frame], utils.py:43-53) -> fp32 [B][Co][F][h][w]. */
+int asva_conv_out_finish(const float* y, int32_t ldy, const float* wt, const float* bt, float* out, int32_t B,
+                         int32_t Co, int32_t F, int32_t h, int32_t w, asva_stream_t stream);
+
+/* Skinny linear for M <= 32 rows, fp32 activations, bf16 weights [N][K]: out = act_out(act_in(x) W^T + b).
+ * act: 0 none, 1 SiLU.  Replaces TimestepEmbedding and the 22 time_emb_proj linears
+ * (audio_cond_unet_3d_condition.py:673-681, ff_spatio_temp_resnet_3d.py:170-171) in three launches. */
+int asva_small_linear(const float* x, const void* w, const float* bias, float* out, int32_t M, int32_t N,
+                      int32_t K, int32_t act_in, int32_t act_out, asva_stream_t stream);
+
+/* Sinusoidal timestep features (diffusers get_timestep_embedding, flip_sin_to_cos, shift 0): out[B][dim] fp32 =
+ * [cos(t w_i) | sin(t w_i)], w_i = exp(-ln(10000) i / (dim/2)).  t is read from device memory. */
+int asva_timestep_features(const float* t, float* out, int32_t B, int32_t dim, int32_t flip_sin_to_cos,
+                           asva_stream_t stream);
+
+/* Classifier-free guidance + sampler update on frames 1..F-1 (frame 0 is the conditioning image and is never
+ * written, pipeline_audio_cond_animation.py:363-364).  eps: fp32 [k][C][F][h][w] UNet outputs (k <= 3 CFG
+ * branches); latents: fp32 [C][F][h][w] updated in place.  All scalars live in DEVICE memory so the launch can
+ * sit inside a replayed CUDA graph:  coef fp32[9] = {w0, w1, w2, c_sample, c_eps, a0, a1, a2, a3}
+ *   e = w0*eps[0] + w1*eps[1] + w2*eps[2]                                   (CFG combine, :349-361)
+ *   DDIM (eta = 0, epsilon prediction):  x <- c_sample * x + c_eps * e
+ *   PLMS (PNDMScheduler.step_plms):      e_hat = a0*e + a1*hist[slots[1]] + a2*hist[slots[2]] + a3*hist[slots[3]];
+ *                                        if slots[0] >= 0: hist[slots[0]] <- e;   x <- c_sample * x + c_eps * e_hat
+ * hist: fp32 [4][C][F][h][w] ring of past e; slots: int32[4] in device memory. */
+int asva_cfg_ddim_step(const float* eps, int32_t k, float* latents, const float* coef, int32_t C, int32_t F,
+                       int32_t hw, asva_stream_t stream);
+int asva_cfg_plms_step(const float* eps, int32_t k, float* latents, float* hist, const float* coef,
+                       const int32_t* slots, int32_t C, int32_t F, int32_t hw, asva_stream_t stream);
+
+const char* asva_last_error(void);
+int asva_version(void);
+/* 0 if the current device is sm_100, ASVA_ERR_DEVICE otherwise */
+int asva_device_check(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASVA_B200_H */

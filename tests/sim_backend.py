@@ -1,0 +1,238 @@
+"""Torch interpreter of the operator specs in asva_b200/ops.py  —  TEST INFRASTRUCTURE ONLY.
+
+It restates, in plain torch (any device), what each C-ABI entry point of include/asva_b200.h computes from the same
+descriptor.  Uses: (1) on CPU, run the whole engine through it and compare with the oracle, which checks the
+host-side logic (weight repacking, descriptor construction, op sequencing) without a GPU; (2) on the GPU box, serve
+as the per-kernel reference that the CUDA kernels are compared against on identical inputs.  The product package
+never imports this file."""
+import math
+from typing import Optional
+
+import torch
+
+from asva_b200.ops import AttnSpec, GemmSpec
+
+
+def _flat(t: torch.Tensor) -> torch.Tensor:
+    """1-D view of the tensor's storage starting at its first element (so offsets mirror raw pointers)."""
+    n = t.untyped_storage().nbytes() // t.element_size() - t.storage_offset()
+    return torch.as_strided(t, (n,), (1,))
+
+
+class SimBackend:
+    name = "sim"
+
+    def __init__(self, round_bf16_accum: bool = False) -> None:
+        self.launches = 0
+
+    # ------------------------------------------------------------------ gemm
+    def _gather_a(self, s: GemmSpec) -> torch.Tensor:
+        D1, D2, D3 = s.out_dims
+        dev = s.out.device
+        o1 = torch.arange(D1, device=dev).view(1, 1, D1).expand(D3, D2, D1).reshape(-1)
+        o2 = torch.arange(D2, device=dev).view(1, D2, 1).expand(D3, D2, D1).reshape(-1)
+        o3 = torch.arange(D3, device=dev).view(D3, 1, 1).expand(D3, D2, D1).reshape(-1)
+        cols = []
+        for sg in s.segs:
+            av = s.a[sg.src]
+            flat = _flat(av.t)
+            c_ext, e1, e2, e3 = av.dims
+            i1 = o1 * s.trav[0] + sg.off[0]
+            i2 = o2 * s.trav[1] + sg.off[1]
+            i3 = o3 * s.trav[2] + sg.off[2]
+            ok = (i1 >= 0) & (i1 < e1) & (i2 >= 0) & (i2 < e2) & (i3 >= 0) & (i3 < e3)
+            base = i1.clamp(0, e1 - 1) * av.strides[0] + i2.clamp(0, e2 - 1) * av.strides[1] + \
+                i3.clamp(0, e3 - 1) * av.strides[2]
+            kk = torch.arange(sg.num_kb * 64, device=dev) + sg.c0
+            okc = kk < c_ext
+            idx = base.view(-1, 1) + kk.clamp(max=c_ext - 1).view(1, -1)
+            vals = flat[idx].float()
+            vals = vals * (ok.view(-1, 1) & okc.view(1, -1)).float()
+            cols.append(vals)
+        return torch.cat(cols, dim=1)
+
+    def gemm(self, s: GemmSpec) -> None:
+        self.launches += 1
+        A = self._gather_a(s)  # [M, K] fp32 (bf16 values)
+        M = A.shape[0]
+        W = torch.as_strided(s.w, (s.N, s.K), (s.ldw, 1)).float()
+        acc = A @ W.t()
+        dev = acc.device
+        rows = torch.arange(M, device=dev)
+        if s.geglu:
+            assert s.N % 128 == 0
+            if s.bias is not None:
+                acc = acc + s.bias[: s.N].float().view(1, -1)
+            t = acc.view(M, s.N // 128, 2, 64)
+            hv, gv = t[:, :, 0, :], t[:, :, 1, :]
+            val = (hv * torch.nn.functional.gelu(gv)).reshape(M, s.N // 2)
+            n_out = s.N // 2
+        else:
+            val = acc
+            if s.bias is not None:
+                val = val + s.bias[: s.N].float().view(1, -1)
+            colsN = torch.arange(s.N, device=dev)
+            for ra in s.add:
+                if ra is None:
+                    continue
+                arow = (rows // ra.div_outer) * ra.mul_outer + (rows % ra.mod_inner)
+                sel = ((rows % ra.div_outer) < ra.sel_lt).long() * ra.sel_off
+                idx = (arow * ra.ld + sel).view(-1, 1) + colsN.view(1, -1)
+                val = val + _flat(ra.t)[idx].float()
+            for r, ld in zip(s.res, s.res_ld):
+                if r is None:
+                    continue
+                idx = (rows * ld).view(-1, 1) + colsN.view(1, -1)
+                val = val + _flat(r)[idx].float()
+            n_out = s.N
+        cols = torch.arange(n_out, device=dev)
+        off = ((rows // s.row_div) * s.row_s1 + (rows % s.row_div) * s.row_s0).view(-1, 1) + \
+            ((cols // s.col_div) * s.col_s1 + (cols % s.col_div)).view(1, -1)
+        outf = _flat(s.out)
+        outf[off.reshape(-1)] = val.reshape(-1).to(s.out.dtype)
+
+    # ------------------------------------------------------------------ attention
+    def attention(self, s: AttnSpec) -> None:
+        self.launches += 1
+        G, H, R, d = s.G, s.heads, s.R, s.d
+        q = s.q.view(G, H, R, s.dpad)[..., :d].float()
+        kvf = _flat(s.kv)
+        kv = torch.as_strided(kvf, (G, s.Nk, s.ldkv), (s.kv_rows_per_group * s.ldkv, s.ldkv, 1))
+        k = kv[:, :, s.k_col0: s.k_col0 + H * d].reshape(G, s.Nk, H, d).permute(0, 2, 1, 3).float()
+        v = kv[:, :, s.v_col0: s.v_col0 + H * d].reshape(G, s.Nk, H, d).permute(0, 2, 1, 3).float()
+        sc = torch.einsum("ghrd,ghkd->ghrk", q, k) * s.scale
+        if s.mask is not None:
+            m = torch.as_strided(_flat(s.mask), (G * R // s.mask_rows, s.Nk), (s.mask_ld, 1)).bool()
+            m = m.repeat_interleave(s.mask_rows, dim=0).view(G, 1, R, s.Nk)
+            sc = sc.masked_fill(~m, float("-inf"))
+        p = torch.softmax(sc, dim=-1)
+        o = torch.einsum("ghrk,ghkd->ghrd", p, v)  # [G,H,R,d]
+        o = o.permute(0, 2, 1, 3).reshape(G * R, H * d)
+        outv = torch.as_strided(_flat(s.out), (G * R, H * d), (s.ldo, 1))
+        outv.copy_(o.to(s.out.dtype))
+
+    def temporal_attention(self, qkv, out, B, F, N, heads, d, scale) -> None:
+        self.launches += 1
+        C = heads * d
+        t = qkv.view(B, F, N, 3, heads, d).float()
+        q, k, v = t[:, :, :, 0], t[:, :, :, 1], t[:, :, :, 2]  # [B,F,N,H,d]
+        sc = torch.einsum("bfnhd,bgnhd->bnhfg", q, k) * scale
+        p = torch.softmax(sc, dim=-1)
+        o = torch.einsum("bnhfg,bgnhd->bfnhd", p, v)
+        out.view(B, F, N, C).copy_(o.reshape(B, F, N, C).to(out.dtype))
+
+    # ------------------------------------------------------------------ norms
+    def layernorm(self, x, gamma, beta, pos, out, M, C, eps, N, F) -> None:
+        self.launches += 1
+        v = x.view(M, C).float()
+        if pos is not None:
+            f = (torch.arange(M, device=x.device) // N) % F
+            v = v + pos.view(F, C)[f]
+        o = torch.nn.functional.layer_norm(v, (C,), gamma.float(), beta.float(), eps)
+        out.view(M, C).copy_(o.to(out.dtype))
+
+    def groupnorm_ws_floats(self, n_inst, rows, C) -> int:
+        return 16
+
+    def groupnorm_stats(self, x0, C0, x1, C1, n_inst, rows, groups, eps, stats, ws) -> None:
+        self.launches += 2
+        v = x0.view(n_inst, rows, C0).float()
+        if x1 is not None:
+            v = torch.cat([v, x1.view(n_inst, rows, C1).float()], dim=2)
+        Ct = v.shape[2]
+        g = v.view(n_inst, rows, groups, Ct // groups).permute(0, 2, 1, 3).reshape(n_inst, groups, -1).double()
+        mean = g.mean(dim=2)
+        var = g.var(dim=2, unbiased=False)
+        st = torch.stack([mean, 1.0 / torch.sqrt(var + eps)], dim=2).float()
+        stats.view(n_inst, groups, 2).copy_(st)
+
+    def groupnorm_apply(self, x0, C0, x1, C1, stats, gamma, beta, groups, n_inst, n_img, h, w, silu, upsample,
+                        out) -> None:
+        self.launches += 1
+        v = x0.view(n_img, h, w, C0).float()
+        if x1 is not None:
+            v = torch.cat([v, x1.view(n_img, h, w, C1).float()], dim=3)
+        Ct = v.shape[3]
+        if stats is not None:
+            st = stats.view(n_inst, groups, 2)
+            ipi = n_img // n_inst
+            mean = st[:, :, 0].repeat_interleave(Ct // groups, dim=1).repeat_interleave(ipi, dim=0)
+            rstd = st[:, :, 1].repeat_interleave(Ct // groups, dim=1).repeat_interleave(ipi, dim=0)
+            v = (v - mean.view(n_img, 1, 1, Ct)) * rstd.view(n_img, 1, 1, Ct) * gamma.float().view(1, 1, 1, Ct) + \
+                beta.float().view(1, 1, 1, Ct)
+        if silu:
+            v = torch.nn.functional.silu(v)
+        if upsample:
+            v = v.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+        out.view(v.shape).copy_(v.to(out.dtype))
+
+    # ------------------------------------------------------------------ small kernels
+    def conv_in_im2col(self, lat, out, B, Bs, Cl, F, h, w) -> None:
+        self.launches += 1
+        x = lat.view(Bs, Cl, F, h, w)[torch.arange(B, device=lat.device) % Bs]  # [B,Cl,F,h,w]
+        x = x.permute(0, 2, 1, 3, 4).reshape(B * F, Cl, h, w)
+        xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+        cols = []
+        for ky in range(3):
+            for kx in range(3):
+                cols.append(xp[:, :, ky: ky + h, kx: kx + w])  # [BF, Cl, h, w]
+        t = torch.stack(cols, dim=1)  # [BF, 9, Cl, h, w]
+        t = t.permute(0, 3, 4, 1, 2).reshape(B * F * h * w, 9 * Cl)
+        o = torch.zeros(B * F * h * w, 64, device=lat.device, dtype=torch.float32)
+        o[:, : 9 * Cl] = t
+        out.view(B * F * h * w, 64).copy_(o.to(out.dtype))
+
+    def conv_out_finish(self, y, ldy, wt, bt, out, B, Co, F, h, w) -> None:
+        self.launches += 1
+        hw = h * w
+        v = torch.as_strided(_flat(y), (B, F, hw, Co), (F * hw * ldy, hw * ldy, ldy, 1)).float()
+        prev = torch.cat([v[:, :1], v[:, :-1]], dim=1)
+        head = v[:, :1].expand_as(v)
+        cat = torch.cat([head, prev, v], dim=3)  # [B,F,hw,3Co]
+        o = v + cat @ wt.view(Co, 3 * Co).float().t() + bt.float()
+        out.view(B, Co, F, hw).copy_(o.permute(0, 3, 1, 2))
+
+    def small_linear(self, x, w, bias, out, M, N, K, act_in, act_out) -> None:
+        self.launches += 1
+        v = x.view(M, K).float()
+        if act_in == 1:
+            v = torch.nn.functional.silu(v)
+        o = v @ w.view(N, K).float().t()
+        if bias is not None:
+            o = o + bias.float()
+        if act_out == 1:
+            o = torch.nn.functional.silu(o)
+        out.view(M, N).copy_(o)
+
+    def timestep_features(self, t, out, B, dim, flip) -> None:
+        self.launches += 1
+        half = dim // 2
+        freq = torch.exp(-math.log(10000.0) * torch.arange(half, device=t.device, dtype=torch.float32) / half)
+        arg = t.view(B, 1).float() * freq.view(1, half)
+        s, c = torch.sin(arg), torch.cos(arg)
+        out.view(B, dim).copy_(torch.cat([c, s], dim=1) if flip else torch.cat([s, c], dim=1))
+
+    def _cfg(self, eps, k, coef):
+        e = 0
+        for j in range(k):
+            e = e + coef[j] * eps[j]
+        return e
+
+    def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw) -> None:
+        self.launches += 1
+        e = self._cfg(eps.view(k, C, F, hw), k, coef)
+        lv = lat.view(C, F, hw)
+        lv[:, 1:] = coef[3] * lv[:, 1:] + coef[4] * e[:, 1:]
+
+    def cfg_plms_step(self, eps, k, lat, hist, coef, slots, C, F, hw) -> None:
+        self.launches += 1
+        e = self._cfg(eps.view(k, C, F, hw), k, coef)
+        hv = hist.view(4, C, F, hw)
+        ehat = coef[5] * e
+        for j in range(1, 4):
+            if float(coef[5 + j]) != 0.0:
+                ehat = ehat + coef[5 + j] * hv[int(slots[j])]
+        if int(slots[0]) >= 0:
+            hv[int(slots[0]), :, 1:] = e[:, 1:]
+        lv = lat.view(C, F, hw)
+        lv[:, 1:] = coef[3] * lv[:, 1:] + coef[4] * ehat[:, 1:]
