@@ -1,0 +1,405 @@
+"""avgen.models.unets.AudioUNet3DConditionModel - drop-in for the reference class of the same name
+(/root/reference/avgen/models/unets/audio_cond_unet_3d_condition.py:56-838): same constructor config, same
+state-dict keys (1106 for the SD-1.5 geometry), same forward signature and output object.  The module tree below
+only HOLDS parameters under the reference's names; the arithmetic runs in asva_b200.engine.UNetEngine
+(hand-written sm_100a kernels behind include/asva_b200.h).  There is no CPU or eager-PyTorch fallback: a forward on
+non-CUDA tensors, or without libasva_b200.so, raises."""
+import json
+import os
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from asva_b200 import engine as _engine
+from asva_b200._lib import AsvaError
+
+WEIGHTS_NAME = "diffusion_pytorch_model.bin"
+SAFETENSORS_WEIGHTS_NAME = "diffusion_pytorch_model.safetensors"
+
+
+class _Config(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+@dataclass
+class UNet3DConditionOutput:
+    """Mirrors the reference's BaseOutput subclass (:46-53): `.sample`, `["sample"]`, `[0]`, `.to_tuple()`."""
+    sample: torch.Tensor
+
+    def __getitem__(self, k):
+        return self.sample if k in (0, "sample") else (_ for _ in ()).throw(KeyError(k))
+
+    def to_tuple(self):
+        return (self.sample,)
+
+
+# ------------------------------------------------------------------------------------------------ parameter holders
+class _InflatedConv(nn.Conv2d):
+    """weight/bias of the per-frame 2-D conv + `conv_temp` Linear(3*Cout -> Cout), zero-initialised like the
+    reference constructor (utils.py:22-32)."""
+
+    def __init__(self, cin, cout, k, **kw):
+        super().__init__(cin, cout, k, **kw)
+        self.conv_temp = nn.Linear(3 * cout, cout)
+        nn.init.zeros_(self.conv_temp.weight)
+        nn.init.zeros_(self.conv_temp.bias)
+
+
+class _TimeMLP(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, cout)
+        self.linear_2 = nn.Linear(cout, cout)
+
+
+class _Attn(nn.Module):
+    def __init__(self, dim, ctx_dim=None):
+        super().__init__()
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_v = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+        self.processor = None
+
+    def set_processor(self, processor):
+        self.processor = processor
+
+
+class _GEGLU(nn.Module):
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.proj = nn.Linear(dim, 2 * inner)
+
+
+class _FF(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([_GEGLU(dim, 4 * dim), nn.Dropout(0.0), nn.Linear(4 * dim, dim)])
+
+
+class _TBlock(nn.Module):
+    def __init__(self, dim, text_dim, audio_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = _Attn(dim)
+        self.norm_audio = nn.LayerNorm(dim)
+        self.attn_audio = _Attn(dim, audio_dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = _Attn(dim, text_dim)
+        self.pos_embedding_temp = _TimeMLP(dim, dim)
+        self.attn_temp = _Attn(dim)
+        nn.init.zeros_(self.attn_temp.to_out[0].weight)  # ff_spatio_audio_temp_transformer_3d.py:267
+        self.norm_temp = nn.LayerNorm(dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = _FF(dim)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, dim, groups, text_dim, audio_dim):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
+        self.proj_in = nn.Conv2d(dim, dim, 1)
+        self.transformer_blocks = nn.ModuleList([_TBlock(dim, text_dim, audio_dim)])
+        self.proj_out = nn.Conv2d(dim, dim, 1)
+
+
+class _Res(nn.Module):
+    def __init__(self, cin, cout, temb, groups, eps):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = _InflatedConv(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.conv2 = _InflatedConv(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.conv_shortcut = _InflatedConv(cin, cout, 1)
+
+
+class _Sampler(nn.Module):
+    def __init__(self, c, stride):
+        super().__init__()
+        self.conv = _InflatedConv(c, c, 3, stride=stride, padding=1)
+
+
+class _Block(nn.Module):
+    def __init__(self, res, attn=None, down=None, up=None):
+        super().__init__()
+        self.resnets = nn.ModuleList(res)
+        if attn is not None:
+            self.attentions = nn.ModuleList(attn)
+            self.has_cross_attention = True
+        if down is not None:
+            self.downsamplers = nn.ModuleList([down])
+        if up is not None:
+            self.upsamplers = nn.ModuleList([up])
+
+
+_DEFAULTS = dict(
+    sample_size=None, in_channels=4, out_channels=4, center_input_sample=False, flip_sin_to_cos=True, freq_shift=0,
+    down_block_types=("FFSpatioAudioTempCrossAttnDownBlock3D",) * 3 + ("FFSpatioTempResDownBlock3D",),
+    mid_block_type="FFSpatioAudioTempCrossAttnUNetMidBlock3D",
+    up_block_types=("FFSpatioTempResUpBlock3D",) + ("FFSpatioAudioTempCrossAttnUpBlock3D",) * 3,
+    only_cross_attention=False, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, downsample_padding=1,
+    mid_block_scale_factor=1, act_fn="silu", norm_num_groups=32, norm_eps=1e-5, cross_attention_dim=1280,
+    encoder_hid_dim=None, attention_head_dim=8, dual_cross_attention=False, use_linear_projection=False,
+    class_embed_type=None, addition_embed_type=None, num_class_embeds=None, upcast_attention=False,
+    resnet_time_scale_shift="default", resnet_skip_time_act=False, resnet_out_scale_factor=1.0,
+    time_embedding_type="positional", time_embedding_dim=None, time_embedding_act_fn=None, timestep_post_act=None,
+    time_cond_proj_dim=None, conv_in_kernel=3, conv_out_kernel=3, projection_class_embeddings_input_dim=None,
+    class_embeddings_concat=False, mid_block_only_cross_attention=None, cross_attention_norm=None,
+    addition_embed_type_num_heads=64, audio_cross_attention_dim=768,
+)
+# constructor options of the reference that select code paths the shipped checkpoints never use
+_MUST_BE_DEFAULT = ("center_input_sample", "only_cross_attention", "downsample_padding", "mid_block_scale_factor",
+                    "encoder_hid_dim", "dual_cross_attention", "use_linear_projection", "class_embed_type",
+                    "addition_embed_type", "num_class_embeds", "resnet_time_scale_shift", "resnet_out_scale_factor",
+                    "time_embedding_type", "time_embedding_dim", "time_embedding_act_fn", "timestep_post_act",
+                    "time_cond_proj_dim", "conv_in_kernel", "conv_out_kernel", "class_embeddings_concat")
+
+
+class AudioUNet3DConditionModel(nn.Module):
+    config_name = "config.json"
+    _supports_gradient_checkpointing = False
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        unknown = set(kwargs) - set(_DEFAULTS)
+        if unknown:
+            raise TypeError(f"unexpected config keys {sorted(unknown)}")
+        cfg = dict(_DEFAULTS)
+        cfg.update(kwargs)
+        for k in _MUST_BE_DEFAULT:
+            if cfg[k] != _DEFAULTS[k]:
+                raise NotImplementedError(f"config {k}={cfg[k]!r}: only the reference default {_DEFAULTS[k]!r} is built")
+        if cfg["act_fn"] not in ("silu", "swish"):
+            raise NotImplementedError("act_fn must be silu")
+        for k in ("block_out_channels", "down_block_types", "up_block_types"):
+            cfg[k] = tuple(cfg[k])
+        if not isinstance(cfg["layers_per_block"], int) or not isinstance(cfg["attention_head_dim"], int) \
+                or not isinstance(cfg["cross_attention_dim"], int):
+            raise NotImplementedError("per-level layers_per_block / attention_head_dim / cross_attention_dim")
+        self._internal_dict = _Config(cfg)
+        self.sample_size = cfg["sample_size"]
+        _engine.check_supported(self._engine_cfg())
+        ch, L, g, eps = cfg["block_out_channels"], cfg["layers_per_block"], cfg["norm_num_groups"], cfg["norm_eps"]
+        td, ad, temb = cfg["cross_attention_dim"], cfg["audio_cross_attention_dim"], ch[0] * 4
+        nlev = len(ch)
+        self.conv_in = _InflatedConv(cfg["in_channels"], ch[0], 3, padding=1)
+        self.time_embedding = _TimeMLP(ch[0], temb)
+        downs, cprev = [], ch[0]
+        for i, c in enumerate(ch):
+            attn = "Attn" in cfg["down_block_types"][i]
+            res = [_Res(cprev if j == 0 else c, c, temb, g, eps) for j in range(L)]
+            downs.append(_Block(res, [_Transformer(c, g, td, ad) for _ in range(L)] if attn else None,
+                                down=_Sampler(c, 2) if i < nlev - 1 else None))
+            cprev = c
+        self.down_blocks = nn.ModuleList(downs)
+        self.mid_block = _Block([_Res(ch[-1], ch[-1], temb, g, eps) for _ in range(2)], [_Transformer(ch[-1], g, td, ad)])
+        ups, rev = [], tuple(reversed(ch))
+        cprev = rev[0]
+        for i, c in enumerate(rev):
+            attn = "Attn" in cfg["up_block_types"][i]
+            cin = rev[min(i + 1, nlev - 1)]
+            res = []
+            for j in range(L + 1):
+                skip = cin if j == L else c
+                res.append(_Res((cprev if j == 0 else c) + skip, c, temb, g, eps))
+            ups.append(_Block(res, [_Transformer(c, g, td, ad) for _ in range(L + 1)] if attn else None,
+                              up=_Sampler(c, 1) if i < nlev - 1 else None))
+            cprev = c
+        self.up_blocks = nn.ModuleList(ups)
+        self.num_upsamplers = nlev - 1
+        self.conv_norm_out = nn.GroupNorm(g, ch[0], eps=eps)
+        self.conv_out = _InflatedConv(ch[0], cfg["out_channels"], 3, padding=1)
+        self._eng = None
+        self._runner = None
+        self._ctx_key = None
+        self._ctx_keepalive = None
+        self.eval()
+
+    # ------------------------------------------------------------------------------------------ config / io
+    @property
+    def config(self):
+        return self._internal_dict
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    def _engine_cfg(self) -> dict:
+        c = self._internal_dict
+        return {k: c[k] for k in _engine.DEFAULT_CONFIG if k in c}
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        c = {k: v for k, v in dict(config).items() if k in _DEFAULTS}
+        c.update(kwargs)
+        return cls(**c)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, subfolder=None, torch_dtype=None, **kwargs):
+        """Reads a diffusers-format directory: config.json + diffusion_pytorch_model.{safetensors,bin}
+        (what trainer.save_pretrained writes, audio_cond_animation_trainer.py:152-155; loaded at
+        scripts/animation_demo.py:80)."""
+        path = os.path.join(pretrained_model_path, subfolder) if subfolder else pretrained_model_path
+        with open(os.path.join(path, cls.config_name)) as f:
+            model = cls.from_config(json.load(f), **kwargs)
+        st = os.path.join(path, SAFETENSORS_WEIGHTS_NAME)
+        if os.path.isfile(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(path, WEIGHTS_NAME), map_location="cpu", weights_only=True)
+        model.load_state_dict(sd)
+        if torch_dtype is not None:
+            model.to(torch_dtype)
+        return model
+
+    @classmethod
+    def from_pretrained_2d(cls, config3d, pretrained_model_path, subfolder=None):
+        """Inflates an SD-1.5 2-D UNet checkpoint: keeps every 2-D weight whose name and shape match and leaves the
+        temporal / audio parameters at their constructor values (reference :800-838)."""
+        path = os.path.join(pretrained_model_path, subfolder) if subfolder else pretrained_model_path
+        with open(os.path.join(path, cls.config_name)) as f:
+            c2 = json.load(f)
+        for k in ("down_block_types", "up_block_types", "mid_block_type", "cross_attention_dim",
+                  "audio_cross_attention_dim"):
+            if k in config3d:
+                c2[k] = config3d[k]
+        model = cls.from_config(c2)
+        sd2 = torch.load(os.path.join(path, WEIGHTS_NAME), map_location="cpu", weights_only=True)
+        own = model.state_dict()
+        merged = {k: (sd2[k] if ("_temp" not in k and k in sd2 and sd2[k].shape == v.shape) else v)
+                  for k, v in own.items()}
+        model.load_state_dict(merged)
+        return model
+
+    def save_pretrained(self, save_directory, safe_serialization=True, **kw):
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = dict(self._internal_dict)
+        cfg["_class_name"] = type(self).__name__
+        with open(os.path.join(save_directory, self.config_name), "w") as f:
+            json.dump(cfg, f, indent=2)
+        sd = {k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, SAFETENSORS_WEIGHTS_NAME))
+        else:
+            torch.save(sd, os.path.join(save_directory, WEIGHTS_NAME))
+
+    # ------------------------------------------------------------------------------------------ attention processors
+    @property
+    def attn_processors(self) -> Dict[str, Any]:
+        return {f"{n}.processor": m.processor for n, m in self.named_modules() if isinstance(m, _Attn)}
+
+    def set_attn_processor(self, processor):
+        mods = {f"{n}.processor": m for n, m in self.named_modules() if isinstance(m, _Attn)}
+        if isinstance(processor, dict):
+            if len(processor) != len(mods):
+                raise ValueError(f"A dict of processors was passed, but the number of processors {len(processor)} "
+                                 f"does not match the number of attention layers: {len(mods)}.")
+            for k, m in mods.items():
+                m.set_processor(processor[k])
+        else:
+            for m in mods.values():
+                m.set_processor(processor)
+
+    def set_default_attn_processor(self):
+        self.set_attn_processor(None)
+
+    # ------------------------------------------------------------------------------------------ engine management
+    def _apply(self, fn, *a, **k):
+        self._eng = None  # .to()/.cuda()/.half(): repack on next use
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._eng = None
+        return super().load_state_dict(*a, **k)
+
+    def refresh_weights(self):
+        """Call after editing parameters in place; the engine otherwise keeps its packed bf16 copies."""
+        self._eng = None
+
+    def engine(self) -> "_engine.UNetEngine":
+        if self._eng is None:
+            dev = self.device
+            if dev.type != "cuda":
+                raise AsvaError("AudioUNet3DConditionModel runs on the B200 CUDA engine only: move the model to a "
+                                "CUDA device (no CPU fallback)")
+            if any(p is not None for p in self.attn_processors.values()):
+                raise NotImplementedError("custom attention processors are not supported by the fused CUDA engine")
+            with torch.cuda.device(dev):
+                self._eng = _engine.UNetEngine(self.state_dict(), self._engine_cfg(), device=dev)
+            self._runner, self._ctx_key = None, None
+        return self._eng
+
+    def bind_context(self, text, audio, audio_mask):
+        """(Re)projects the cross-attention keys/values when the conditioning tensors changed."""
+        eng = self.engine()
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride())) if t is not None else None
+                    for t in (text, audio, audio_mask))
+        if key != self._ctx_key or eng.ctx is None:
+            eng.set_context(text, audio, audio_mask)
+            self._ctx_key = key
+            self._ctx_keepalive = (text, audio, audio_mask)  # keeps data_ptr-based keys unambiguous
+
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
+                encoder_hidden_states: torch.Tensor, audio_encoder_hidden_states: Optional[torch.Tensor] = None,
+                class_labels: Optional[torch.Tensor] = None, timestep_cond: Optional[torch.Tensor] = None,
+                attention_mask: Optional[torch.Tensor] = None, audio_attention_mask: Optional[torch.Tensor] = None,
+                cross_attention_kwargs: Optional[Dict[str, Any]] = None,
+                down_block_additional_residuals: Optional[Tuple[torch.Tensor]] = None,
+                mid_block_additional_residual: Optional[torch.Tensor] = None, return_dict: bool = True,
+                first_frame_latent: Optional[torch.Tensor] = None):
+        """sample (B,C,F,h,w); timestep scalar or (B,); encoder_hidden_states = CLIP text (B,F,77,768);
+        audio_encoder_hidden_states (B,F,229,768); audio_attention_mask bool (B,F,229), True = attend.
+        `attention_mask` is accepted and ignored exactly as in the reference (it never reaches an attention,
+        unet_3d_blocks.py:922-928).  `first_frame_latent` (B,C,h,w) is a convenience that overrides frame 0 of a
+        copy of `sample`; the reference carries the conditioning frame inside `sample`."""
+        assert sample.ndim == 5, sample.size()
+        if cross_attention_kwargs is not None:
+            raise AssertionError("cross_attention_kwargs must be None")  # reference: unet_3d_blocks.py:793,1033
+        if class_labels is not None or timestep_cond is not None or down_block_additional_residuals is not None \
+                or mid_block_additional_residual is not None:
+            raise NotImplementedError("class_labels / timestep_cond / additional residuals are not part of this path")
+        if audio_encoder_hidden_states is None:
+            raise ValueError("audio_encoder_hidden_states is required")
+        if not sample.is_cuda:
+            raise AsvaError("AudioUNet3DConditionModel.forward needs CUDA tensors (no CPU fallback)")
+        eng = self.engine()
+        B, C, F, h, w = sample.shape
+        with torch.cuda.device(sample.device):
+            if eng.shape != (B, F, h, w):
+                eng.prepare(B, F, h, w)
+                self._runner, self._ctx_key = None, None
+            self.bind_context(encoder_hidden_states, audio_encoder_hidden_states, audio_attention_mask)
+            if self._runner is None:
+                self._io = (torch.empty(B, C, F, h, w, dtype=torch.float32, device=sample.device),
+                            torch.empty(B, dtype=torch.float32, device=sample.device),
+                            torch.empty(B, self.config.out_channels, F, h, w, dtype=torch.float32, device=sample.device))
+                lat, ts, out = self._io
+                self._runner = _engine.GraphRunner(lambda: eng.forward(lat, ts, out), eng.be)
+            lat, ts, out = self._io
+            lat.copy_(sample)
+            if first_frame_latent is not None:
+                lat[:, :, 0] = first_frame_latent
+            if torch.is_tensor(timestep):
+                ts.copy_(timestep.reshape(-1).expand(B) if timestep.numel() in (1, B) else timestep)
+            else:
+                ts.fill_(float(timestep))
+            self._runner()
+            result = out.to(sample.dtype) if sample.dtype != torch.float32 else out.clone()
+        if not return_dict:
+            return (result,)
+        return UNet3DConditionOutput(sample=result)

@@ -1,0 +1,210 @@
+"""CPU suite: the C-ABI library loads and exports every symbol of include/asva_b200.h; the host logic (weight
+repacking, descriptor construction, launch sequencing) is exact - the engine driven through the torch spec interpreter
+in fp32 reproduces the oracle and the reference-generated goldens; the oracle itself reproduces the goldens (and the
+reference, when /root/reference is present); schedulers; boundary API; no CPU fallback."""
+import glob
+import os
+import re
+
+import pytest
+import torch
+
+from asva_b200 import engine, schedulers, synth
+from oracle import sampler_ref, unet_ref
+from sim_backend import SimBackend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+def _shapes(chans):
+    from avgen.models.unets import AudioUNet3DConditionModel
+    with torch.device("meta"):
+        m = AudioUNet3DConditionModel(sample_size=64, cross_attention_dim=768, attention_head_dim=8,
+                                      block_out_channels=tuple(chans))
+    return [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_header_symbol():
+    from asva_b200 import _lib, build
+    lib_path = build.build()
+    lib = _lib.load(lib_path)
+    header = open(os.path.join(ROOT, "include", "asva_b200.h")).read()
+    declared = set(re.findall(r"\b(asva_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.ABI), (declared ^ set(_lib.ABI))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.asva_version() >= 100
+
+
+def test_product_has_no_cpu_fallback():
+    from asva_b200._lib import AsvaError
+    from avgen.models.unets import AudioUNet3DConditionModel
+    m = AudioUNet3DConditionModel(sample_size=64, cross_attention_dim=768, block_out_channels=(64, 64, 64, 64))
+    x = torch.zeros(1, 4, 2, 8, 8)
+    with pytest.raises(AsvaError):
+        m(x, 1, encoder_hidden_states=torch.zeros(1, 2, 77, 768),
+          audio_encoder_hidden_states=torch.zeros(1, 2, 229, 768))
+
+
+def test_product_never_imports_oracle():
+    for d in ("asva_b200", "avgen"):
+        for f in glob.glob(os.path.join(ROOT, d, "**", "*.py"), recursive=True):
+            src = open(f).read()
+            assert not re.search(r"^\s*(from|import)\s+(oracle|sim_backend)\b", src, re.M), f
+
+
+# ------------------------------------------------------------------------------------------------ oracle pins
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "unet_tiny_*.pt"))), ids=os.path.basename)
+def test_oracle_and_engine_logic_vs_reference_golden(path):
+    g = torch.load(path)
+    chans, k = tuple(g["chans"]), g["k"]
+    sd = synth.synth_state_dict(_shapes(chans), seed=g["seed"])
+    lat, text, audio, mask = synth.synth_inputs(F=g["F"], h=g["h"], w=g["w"], k=k, seed=g["input_seed"])
+    x = lat.expand(k, -1, -1, -1, -1).contiguous()
+    with torch.no_grad():
+        y = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, g["t"], text, audio, mask)
+    assert _rel(y, g["out"]) < 2e-5, "clean-room oracle drifted from the reference-generated golden"
+    eng = engine.UNetEngine(sd, dict(block_out_channels=chans), device="cpu", backend=SimBackend(),
+                            act_dtype=torch.float32)
+    eng.prepare(k, g["F"], g["h"], g["w"])
+    eng.set_context(text, audio, mask)
+    out = torch.empty(k, 4, g["F"], g["h"], g["w"])
+    eng.forward(lat, torch.full((k,), float(g["t"])), out)
+    assert _rel(out, g["out"]) < 2e-5, "engine launch sequence (fp32 interpreter) != reference"
+    # bf16 storage through the interpreter: what the CUDA kernels are expected to land on
+    engb = engine.UNetEngine(sd, dict(block_out_channels=chans), device="cpu", backend=SimBackend())
+    engb.prepare(k, g["F"], g["h"], g["w"])
+    engb.set_context(text, audio, mask)
+    engb.forward(lat, torch.full((k,), float(g["t"])), out)
+    assert _rel(out, g["out"]) < 2.5e-2
+
+
+def test_oracle_vs_reference_live():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box): covered by tests/golden/")
+    chans = (64, 64, 128, 128)
+    m = ref_loader.build_reference_unet(dict(sample_size=64, cross_attention_dim=768, attention_head_dim=8,
+                                             norm_eps=1e-5, block_out_channels=chans))
+    sd = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=3)
+    assert sorted(_shapes(chans)) == sorted((k, tuple(v.shape)) for k, v in m.state_dict().items())
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(11)
+    B, F = 2, 5
+    x, text = torch.randn(B, 4, F, 8, 8, generator=g), torch.randn(B, F, 77, 768, generator=g)
+    audio = torch.randn(B, F, 229, 768, generator=g)  # differs per frame
+    mask = synth.audio_segment_mask(F)[None].expand(B, -1, -1).contiguous()
+    with torch.no_grad():
+        ref = m(x, torch.tensor([3, 900]), encoder_hidden_states=text, audio_encoder_hidden_states=audio,
+                audio_attention_mask=mask).sample
+        got = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, torch.tensor([3, 900]), text, audio, mask)
+    assert _rel(got, ref) < 2e-5
+
+
+def test_state_dict_keys_match_reference_sd15():
+    import json
+    want = json.load(open(os.path.join(GOLD, "state_dict_shapes_sd15.json")))
+    got = {k: list(s) for k, s in _shapes((320, 640, 1280, 1280))}
+    assert len(got) == 1106 and got == want
+
+
+def test_audio_mask_rule():
+    m12, m24, m8 = synth.audio_segment_mask(12), synth.audio_segment_mask(24), synth.audio_segment_mask(8)
+    assert m12.shape == (12, 229) and int(m12[0].sum()) == 25 and int(m24[3].sum()) == 13 and int(m8[7].sum()) == 37
+    assert m12[:, 0].all() and m12[0, 1:1 + 19].tolist()[:3] == [True, True, False]
+    assert m12[11, 1 + 17] and m12[11, 1 + 18] and not m12[11, 1 + 16]
+
+
+# ------------------------------------------------------------------------------------------------ schedulers
+def test_ddim_matches_restatement_and_closed_form():
+    s, r = schedulers.DDIMScheduler(), sampler_ref.DDIMRef(50)
+    s.set_timesteps(50)
+    assert s.timesteps.tolist() == r.timesteps.tolist() == list(range(981, 0, -20))
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(2, 4, 3, 8, 8, generator=g), torch.randn(2, 4, 3, 8, 8, generator=g)
+    for t in (981, 501, 21, 1):
+        assert _rel(s.step(e, t, x, eta=0.0).prev_sample, r.step(e, t, x)) < 1e-6
+    plan = s.step_plan()
+    ac = sampler_ref.alphas_cumprod()
+    # t = 1 steps to "t = -19": set_alpha_to_one=False -> final alpha_bar is alpha_bar[0]
+    assert len(plan) == 50 and abs(plan[-1].c_sample - float((ac[0] / ac[1]) ** 0.5)) < 1e-6
+
+
+def test_pndm_matches_restatement_including_alias_quirk():
+    n = 7
+    g = torch.Generator().manual_seed(1)
+    x0 = torch.randn(1, 4, 5, 4, 4, generator=g)
+    es = [torch.randn(1, 4, 5, 4, 4, generator=g) for _ in range(n + 1)]
+    # (a) protocol step() vs the restated diffusers step, caller keeps separate storage (canonical PLMS)
+    s, r = schedulers.PNDMScheduler(), sampler_ref.PNDMRef(n)
+    s.set_timesteps(n)
+    assert s.timesteps.tolist() == r.timesteps.tolist() and len(s.timesteps) == n + 1
+    xa, xb = x0.clone(), x0.clone()
+    for e, t in zip(es, s.timesteps.tolist()):
+        xa, xb = s.step(e, t, xa).prev_sample, r.step(e, t, xb)
+        assert _rel(xa, xb) < 1e-6
+    # (b) the fused-kernel plan == the reference pipeline's in-place update (F5 alias) driven through the restatement
+    r = sampler_ref.PNDMRef(n)
+    lat = x0.clone()
+    for e, t in zip(es, r.timesteps.tolist()):
+        lat[:, :, 1:] = r.step(e[:, :, 1:], t, lat[:, :, 1:])
+    s.set_timesteps(n)
+    sim, lat2 = SimBackend(), x0.clone().view(4, 5, 16)
+    hist = torch.zeros(4, 4, 5, 16)
+    for e, p in zip(es, s.step_plan()):
+        coef = torch.tensor([1.0, 0.0, 0.0, p.c_sample, p.c_eps, *p.a])
+        sim.cfg_plms_step(e.view(1, 4, 5, 16), 1, lat2, hist, coef, torch.tensor(p.slots, dtype=torch.int32), 4, 5, 16)
+    assert _rel(lat2.view_as(lat), lat) < 1e-5
+    assert torch.equal(lat2.view_as(lat)[:, :, 0], x0[:, :, 0])
+
+
+def test_plan_for_recognises_diffusers_like_objects():
+    class Cfg(dict):
+        __getattr__ = dict.get
+
+    class PNDMScheduler:  # stands in for diffusers.PNDMScheduler (same class name + config keys)
+        def __init__(self):
+            self.config = Cfg(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
+                              beta_schedule="scaled_linear", set_alpha_to_one=False, steps_offset=1,
+                              skip_prk_steps=True, prediction_type="epsilon", timestep_spacing="leading",
+                              trained_betas=None)
+            mine = schedulers.PNDMScheduler()
+            mine.set_timesteps(50)
+            self.timesteps, self.num_inference_steps = mine.timesteps, 50
+
+    plans = schedulers.plan_for(PNDMScheduler())
+    assert plans is not None and len(plans) == 51 and plans[1].a == (0.5, 0.5, 0.0, 0.0)
+    assert schedulers.plan_for(object()) is None
+
+
+# ------------------------------------------------------------------------------------------------ sampler loop logic
+def test_denoise_loop_logic_cpu_vs_golden_trace():
+    """The fused step sequence (engine forward + cfg kernel with plan coefficients), interpreted on CPU in fp32,
+    reproduces the reference-UNet sampler traces."""
+    for name, sched in (("ddim", schedulers.DDIMScheduler()), ("pndm", schedulers.PNDMScheduler())):
+        g = torch.load(os.path.join(GOLD, f"sampler_{name}.pt"))
+        chans = tuple(g["chans"])
+        sd = synth.synth_state_dict(_shapes(chans), seed=0)
+        sim = SimBackend()
+        eng = engine.UNetEngine(sd, dict(block_out_channels=chans), device="cpu", backend=sim,
+                                act_dtype=torch.float32)
+        F, h, w = g["F"], g["h"], g["w"]
+        lat, text, audio, mask = synth.synth_inputs(F=F, h=h, w=w, k=2)
+        eng.prepare(2, F, h, w)
+        eng.set_context(text, audio, mask)
+        sched.set_timesteps(g["steps"])
+        eps, lat = torch.empty(2, 4, F, h, w), lat.clone()
+        hist = torch.zeros(4, 4, F, h, w)
+        s_a = g["audio_scale"]
+        for i, p in enumerate(sched.step_plan()):
+            eng.forward(lat, torch.full((2,), float(p.timestep)), eps)
+            coef = torch.tensor([1.0 - s_a, s_a, 0.0, p.c_sample, p.c_eps, *p.a])
+            sim.cfg_plms_step(eps, 2, lat.view(4, F, h * w), hist, coef, torch.tensor(p.slots, dtype=torch.int32),
+                              4, F, h * w)
+            assert _rel(lat, g["trace"][i]) < 1e-4, (name, i)
