@@ -219,10 +219,42 @@ class CudaBackend:
     def __init__(self) -> None:
         self.lib = _lib.load()
         self.launches = 0
+        self._prof = None
 
     @staticmethod
     def _stream() -> int:
         return torch.cuda.current_stream().cuda_stream
+
+    # -- live per-family timing (bench.py): CUDA events on the launching stream around every C-ABI call
+    def profile_begin(self) -> None:
+        self._prof = []
+
+    def profile_end(self):
+        """-> {family: (calls, total_ms)}; families: gemm, attention, temporal_attention, layernorm, groupnorm, ..."""
+        torch.cuda.synchronize()
+        out = {}
+        for fam, e0, e1 in self._prof or []:
+            c, t = out.get(fam, (0, 0.0))
+            out[fam] = (c + 1, t + e0.elapsed_time(e1))
+        self._prof = None
+        return out
+
+    def _timed(self, fam: str):
+        be = self
+
+        class _T:
+            def __enter__(self):
+                if be._prof is not None:
+                    self.e0 = torch.cuda.Event(enable_timing=True)
+                    self.e0.record()
+
+            def __exit__(self, *a):
+                if be._prof is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    be._prof.append((fam, self.e0, e1))
+
+        return _T()
 
     @staticmethod
     def _chk_dev(*ts: Optional[torch.Tensor]) -> None:
@@ -276,7 +308,8 @@ class CudaBackend:
         d.out = s.out.data_ptr()
         d.row_s1, d.row_s0, d.col_s1 = s.row_s1, s.row_s0, s.col_s1
         d.row_div, d.col_div, d.block_n = s.row_div, s.col_div, s.block_n
-        _lib.check(self.lib.asva_gemm(d, self._stream()), "asva_gemm")
+        with self._timed('gemm'):
+            _lib.check(self.lib.asva_gemm(d, self._stream()), "asva_gemm")
         self.launches += 1
 
     def attention(self, s: AttnSpec) -> None:
@@ -287,18 +320,21 @@ class CudaBackend:
         d.G, d.heads, d.R, d.Nk, d.d, d.dpad = s.G, s.heads, s.R, s.Nk, s.d, s.dpad
         d.kv_rows_per_group, d.k_col0, d.v_col0, d.mask_rows = s.kv_rows_per_group, s.k_col0, s.v_col0, s.mask_rows
         d.scale = s.scale
-        _lib.check(self.lib.asva_attention(d, self._stream()), "asva_attention")
+        with self._timed('attention'):
+            _lib.check(self.lib.asva_attention(d, self._stream()), "asva_attention")
         self.launches += 1
 
     def temporal_attention(self, qkv, out, B, F, N, heads, d, scale) -> None:
         self._chk_dev(qkv, out)
-        _lib.check(self.lib.asva_temporal_attention(qkv.data_ptr(), out.data_ptr(), B, F, N, heads, d, scale,
+        with self._timed('temporal_attention'):
+            _lib.check(self.lib.asva_temporal_attention(qkv.data_ptr(), out.data_ptr(), B, F, N, heads, d, scale,
                                                     self._stream()), "asva_temporal_attention")
         self.launches += 1
 
     def layernorm(self, x, gamma, beta, pos, out, M, C, eps, N, F) -> None:
         self._chk_dev(x, gamma, beta, pos, out)
-        _lib.check(self.lib.asva_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(pos),
+        with self._timed('layernorm'):
+            _lib.check(self.lib.asva_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(pos),
                                            out.data_ptr(), M, C, eps, N, F, self._stream()), "asva_layernorm")
         self.launches += 1
 
@@ -308,7 +344,8 @@ class CudaBackend:
     def groupnorm_stats(self, x0, C0, x1, C1, n_inst, rows, groups, eps, stats, ws) -> None:
         self._chk_dev(x0, x1, stats, ws)
         assert ws.numel() >= self.groupnorm_ws_floats(n_inst, rows, C0 + (C1 if x1 is not None else 0))
-        _lib.check(self.lib.asva_groupnorm_stats(x0.data_ptr(), C0, _ptr(x1), C1, n_inst, rows, groups, eps,
+        with self._timed('groupnorm'):
+            _lib.check(self.lib.asva_groupnorm_stats(x0.data_ptr(), C0, _ptr(x1), C1, n_inst, rows, groups, eps,
                                                  stats.data_ptr(), ws.data_ptr(), self._stream()),
                    "asva_groupnorm_stats")
         self.launches += 2
@@ -316,7 +353,8 @@ class CudaBackend:
     def groupnorm_apply(self, x0, C0, x1, C1, stats, gamma, beta, groups, n_inst, n_img, h, w, silu, upsample,
                         out) -> None:
         self._chk_dev(x0, x1, stats, gamma, beta, out)
-        _lib.check(self.lib.asva_groupnorm_apply(x0.data_ptr(), C0, _ptr(x1), C1, _ptr(stats), _ptr(gamma),
+        with self._timed('groupnorm'):
+            _lib.check(self.lib.asva_groupnorm_apply(x0.data_ptr(), C0, _ptr(x1), C1, _ptr(stats), _ptr(gamma),
                                                  _ptr(beta), groups, n_inst, n_img, h, w, int(silu), int(upsample),
                                                  out.data_ptr(), self._stream()), "asva_groupnorm_apply")
         self.launches += 1
@@ -324,37 +362,43 @@ class CudaBackend:
     def conv_in_im2col(self, lat, out, B, Bs, Cl, F, h, w) -> None:
         self._chk_dev(lat, out)
         assert lat.dtype == torch.float32 and lat.is_contiguous()
-        _lib.check(self.lib.asva_conv_in_im2col(lat.data_ptr(), out.data_ptr(), B, Bs, Cl, F, h, w, self._stream()),
+        with self._timed('misc'):
+            _lib.check(self.lib.asva_conv_in_im2col(lat.data_ptr(), out.data_ptr(), B, Bs, Cl, F, h, w, self._stream()),
                    "asva_conv_in_im2col")
         self.launches += 1
 
     def conv_out_finish(self, y, ldy, wt, bt, out, B, Co, F, h, w) -> None:
         self._chk_dev(y, wt, bt, out)
-        _lib.check(self.lib.asva_conv_out_finish(y.data_ptr(), ldy, wt.data_ptr(), bt.data_ptr(), out.data_ptr(), B,
+        with self._timed('misc'):
+            _lib.check(self.lib.asva_conv_out_finish(y.data_ptr(), ldy, wt.data_ptr(), bt.data_ptr(), out.data_ptr(), B,
                                                  Co, F, h, w, self._stream()), "asva_conv_out_finish")
         self.launches += 1
 
     def small_linear(self, x, w, bias, out, M, N, K, act_in, act_out) -> None:
         self._chk_dev(x, w, bias, out)
-        _lib.check(self.lib.asva_small_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K,
+        with self._timed('small_linear'):
+            _lib.check(self.lib.asva_small_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K,
                                               act_in, act_out, self._stream()), "asva_small_linear")
         self.launches += 1
 
     def timestep_features(self, t, out, B, dim, flip) -> None:
         self._chk_dev(t, out)
-        _lib.check(self.lib.asva_timestep_features(t.data_ptr(), out.data_ptr(), B, dim, int(flip), self._stream()),
+        with self._timed('misc'):
+            _lib.check(self.lib.asva_timestep_features(t.data_ptr(), out.data_ptr(), B, dim, int(flip), self._stream()),
                    "asva_timestep_features")
         self.launches += 1
 
     def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw) -> None:
         self._chk_dev(eps, lat, coef)
-        _lib.check(self.lib.asva_cfg_ddim_step(eps.data_ptr(), k, lat.data_ptr(), coef.data_ptr(), C, F, hw,
+        with self._timed('cfg_step'):
+            _lib.check(self.lib.asva_cfg_ddim_step(eps.data_ptr(), k, lat.data_ptr(), coef.data_ptr(), C, F, hw,
                                                self._stream()), "asva_cfg_ddim_step")
         self.launches += 1
 
     def cfg_plms_step(self, eps, k, lat, hist, coef, slots, C, F, hw) -> None:
         self._chk_dev(eps, lat, hist, coef, slots)
-        _lib.check(self.lib.asva_cfg_plms_step(eps.data_ptr(), k, lat.data_ptr(), hist.data_ptr(), coef.data_ptr(),
+        with self._timed('cfg_step'):
+            _lib.check(self.lib.asva_cfg_plms_step(eps.data_ptr(), k, lat.data_ptr(), hist.data_ptr(), coef.data_ptr(),
                                                slots.data_ptr(), C, F, hw, self._stream()), "asva_cfg_plms_step")
         self.launches += 1
 

@@ -192,6 +192,19 @@ class AudioCondAnimationPipeline(_ProgressMixin):
 
     # ------------------------------------------------------------------------------------------ hot loop
     @torch.no_grad()
+    def open_session(self, text_encodings, audio_encodings, audio_masks, video_length, latent_h, latent_w,
+                     num_inference_steps: int, audio_guidance_scale: float = 4.0,
+                     text_guidance_scale: float = 1.0) -> Optional["DenoiseSession"]:
+        """Binds one clip's conditioning and sampler schedule to the fused denoising step.  Returns None when the
+        scheduler is not one the fused CFG+sampler kernel implements (the caller then uses scheduler.step())."""
+        self.scheduler.set_timesteps(num_inference_steps, device=self.device)
+        plans = _sched.plan_for(self.scheduler)
+        if plans is None:
+            return None
+        return DenoiseSession(self, plans, text_encodings, audio_encodings, audio_masks, video_length, latent_h,
+                              latent_w, audio_guidance_scale, text_guidance_scale)
+
+    @torch.no_grad()
     def denoise(self, video_latents, text_encodings, audio_encodings, audio_masks, num_inference_steps: int,
                 audio_guidance_scale: float = 4.0, text_guidance_scale: float = 1.0, generator=None,
                 callback=None):
@@ -200,69 +213,25 @@ class AudioCondAnimationPipeline(_ProgressMixin):
         Returns the final latents (b,4,F,h,w) fp32 on the device."""
         do_t, do_a = text_guidance_scale > 1.0, audio_guidance_scale > 1.0
         k = 1 + int(do_t) + int(do_a)
-        dev = video_latents.device
         b, C, F, h, w = video_latents.shape
         assert text_encodings.shape[0] == k * b and audio_encodings.shape[0] == k * b, \
             (text_encodings.shape, audio_encodings.shape, k, b)
-        self.scheduler.set_timesteps(num_inference_steps, device=dev)
-        plans = _sched.plan_for(self.scheduler)
-        if plans is None or b != 1:
+        sess = None
+        if b == 1:
+            sess = self.open_session(text_encodings, audio_encodings, audio_masks, F, h, w, num_inference_steps,
+                                     audio_guidance_scale, text_guidance_scale)
+        if sess is None:
+            self.scheduler.set_timesteps(num_inference_steps, device=video_latents.device)
             return self._denoise_generic(video_latents, text_encodings, audio_encodings, audio_masks, k, do_t, do_a,
                                          audio_guidance_scale, text_guidance_scale, generator)
-        s_t, s_a = float(text_guidance_scale), float(audio_guidance_scale)
-        if do_t and do_a:
-            wts = (1.0 - s_t, s_t - s_a, s_a)
-        elif do_t:
-            wts = (1.0 - s_t, s_t, 0.0)
-        elif do_a:
-            wts = (1.0 - s_a, s_a, 0.0)
-        else:
-            wts = (1.0, 0.0, 0.0)
-        plms = any(p.slots[0] >= 0 or p.a != (1.0, 0.0, 0.0, 0.0) for p in plans)
-        unet = self.unet
-        eng = unet.engine()
-        with torch.cuda.device(dev):
-            if eng.shape != (k, F, h, w):
-                eng.prepare(k, F, h, w)
-                unet._runner, unet._ctx_key, self._loop = None, None, None
-            unet.bind_context(text_encodings, audio_encodings, audio_masks)
-            key = (k, C, F, h, w, plms, id(eng))
-            if self._loop is None or self._loop["key"] != key:
-                L = dict(key=key,
-                         lat=torch.empty(1, C, F, h, w, dtype=torch.float32, device=dev),
-                         ts=torch.empty(k, dtype=torch.float32, device=dev),
-                         eps=torch.empty(k, unet.config.out_channels, F, h, w, dtype=torch.float32, device=dev),
-                         coef=torch.empty(9, dtype=torch.float32, device=dev),
-                         slots=torch.zeros(4, dtype=torch.int32, device=dev),
-                         hist=torch.zeros(4, C, F, h, w, dtype=torch.float32, device=dev) if plms else None)
-                be = eng.be
-
-                def step_fn():
-                    eng.forward(L["lat"], L["ts"], L["eps"])
-                    if plms:
-                        be.cfg_plms_step(L["eps"], k, L["lat"], L["hist"], L["coef"], L["slots"], C, F, h * w)
-                    else:
-                        be.cfg_ddim_step(L["eps"], k, L["lat"], L["coef"], C, F, h * w)
-
-                L["runner"] = _engine.GraphRunner(step_fn, be)
-                self._loop = L
-            L = self._loop
-            n = len(plans)
-            coef_all = torch.tensor([[*wts, p.c_sample, p.c_eps, *p.a] for p in plans], dtype=torch.float32).to(dev)
-            slots_all = torch.tensor([list(p.slots) for p in plans], dtype=torch.int32).to(dev)
-            ts_all = torch.tensor([[float(p.timestep)] * k for p in plans], dtype=torch.float32).to(dev)
-            L["lat"].copy_(video_latents)
-            n0 = L["runner"].total_launches
-            for i in self.progress_bar(range(n)):
-                L["ts"].copy_(ts_all[i])
-                L["coef"].copy_(coef_all[i])
-                if plms:
-                    L["slots"].copy_(slots_all[i])
-                L["runner"]()
-                if callback is not None:
-                    callback(i, plans[i].timestep, L["lat"])
-            self.last_launches = L["runner"].total_launches - n0
-            return L["lat"].clone()
+        sess.load_latents(video_latents)
+        n0 = sess.launches
+        for i in self.progress_bar(range(sess.num_steps)):
+            sess.step(i)
+            if callback is not None:
+                callback(i, sess.plans[i].timestep, sess.latents)
+        self.last_launches = sess.launches - n0
+        return sess.latents.clone()
 
     def _denoise_generic(self, video_latents, text, audio, masks, k, do_t, do_a, s_a, s_t, generator):
         """Any other scheduler (or b > 1): the reference's loop verbatim in structure - our UNet module per step,
@@ -311,6 +280,86 @@ class AudioCondAnimationPipeline(_ProgressMixin):
         if not return_dict:
             return videos
         return {"videos": videos}
+
+
+class DenoiseSession:
+    """One clip on one GPU: static fp32 latents (1,C,F,h,w) on the device, the per-step coefficient tables, and a
+    CUDA-graph runner whose body is  UNet forward (k CFG branches) -> fused CFG combine + DDIM/PLMS update of
+    frames 1.. in place.  `step(i)` is one graph replay plus three tiny device-to-device table-row copies."""
+
+    def __init__(self, pipe, plans, text, audio, masks, F, h, w, audio_scale, text_scale):
+        do_t, do_a = text_scale > 1.0, audio_scale > 1.0
+        k = 1 + int(do_t) + int(do_a)
+        s_t, s_a = float(text_scale), float(audio_scale)
+        if do_t and do_a:  # e_u + s_t (e_t - e_u) + s_a (e_ta - e_t)   (reference :349-353)
+            wts = (1.0 - s_t, s_t - s_a, s_a)
+        elif do_t:
+            wts = (1.0 - s_t, s_t, 0.0)
+        elif do_a:
+            wts = (1.0 - s_a, s_a, 0.0)
+        else:
+            wts = (1.0, 0.0, 0.0)
+        unet = pipe.unet
+        eng = unet.engine()
+        dev = unet.device
+        C, Co = unet.config.in_channels, unet.config.out_channels
+        assert text.shape[0] == k and audio.shape[0] == k, "the fused session handles one clip (b = 1) per GPU"
+        self.plans, self.num_steps, self.k, self.dev = plans, len(plans), k, dev
+        self.plms = any(p.slots[0] >= 0 or tuple(p.a) != (1.0, 0.0, 0.0, 0.0) for p in plans)
+        with torch.cuda.device(dev):
+            if eng.shape != (k, F, h, w):
+                eng.prepare(k, F, h, w)
+                unet._runner, unet._ctx_key, pipe._loop = None, None, None
+            unet.bind_context(text, audio, masks)
+            key = (k, C, F, h, w, self.plms, id(eng))
+            if pipe._loop is None or pipe._loop["key"] != key:
+                L = dict(key=key,
+                         lat=torch.empty(1, C, F, h, w, dtype=torch.float32, device=dev),
+                         ts=torch.empty(k, dtype=torch.float32, device=dev),
+                         eps=torch.empty(k, Co, F, h, w, dtype=torch.float32, device=dev),
+                         coef=torch.empty(9, dtype=torch.float32, device=dev),
+                         slots=torch.zeros(4, dtype=torch.int32, device=dev),
+                         hist=torch.zeros(4, C, F, h, w, dtype=torch.float32, device=dev) if self.plms else None)
+                be, plms = eng.be, self.plms
+
+                def step_fn():
+                    eng.forward(L["lat"], L["ts"], L["eps"])
+                    if plms:
+                        be.cfg_plms_step(L["eps"], k, L["lat"], L["hist"], L["coef"], L["slots"], C, F, h * w)
+                    else:
+                        be.cfg_ddim_step(L["eps"], k, L["lat"], L["coef"], C, F, h * w)
+
+                L["runner"] = _engine.GraphRunner(step_fn, be)
+                pipe._loop = L
+            self.L = pipe._loop
+            self.coef_all = torch.tensor([[*wts, p.c_sample, p.c_eps, *p.a] for p in plans],
+                                         dtype=torch.float32).to(dev)
+            self.slots_all = torch.tensor([list(p.slots) for p in plans], dtype=torch.int32).to(dev)
+            self.ts_all = torch.tensor([[float(p.timestep)] * k for p in plans], dtype=torch.float32).to(dev)
+
+    @property
+    def latents(self) -> torch.Tensor:
+        return self.L["lat"]
+
+    @property
+    def launches(self) -> int:
+        return self.L["runner"].total_launches
+
+    def load_latents(self, latents: torch.Tensor) -> None:
+        """Host (pinned) or device tensor (1,C,F,h,w) -> the session's static fp32 latents."""
+        self.L["lat"].copy_(latents, non_blocking=True)
+
+    def read_latents(self, out: torch.Tensor) -> None:
+        out.copy_(self.L["lat"], non_blocking=True)
+
+    def step(self, i: int) -> None:
+        L = self.L
+        with torch.cuda.device(self.dev):
+            L["ts"].copy_(self.ts_all[i])
+            L["coef"].copy_(self.coef_all[i])
+            if self.plms:
+                L["slots"].copy_(self.slots_all[i])
+            L["runner"]()
 
 
 @torch.no_grad()
