@@ -162,26 +162,37 @@ __global__ void __launch_bounds__(256) gn_stats_stage1(const __nv_bfloat16* __re
   }
 }
 
-__global__ void gn_stats_stage2(const float* __restrict__ ws, int n_inst, int splits, int Ctot, int groups,
-                                int64_t rows, float eps, float* __restrict__ stats) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) gn_stats_stage2(const float* __restrict__ ws, int n_inst, int splits, int Ctot,
+                                                         int groups, int64_t rows, float eps,
+                                                         float* __restrict__ stats) {
+  // one warp per (instance, group): lanes stride over splits x channels-in-group, fp64 shuffle reduction
+  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (idx >= n_inst * groups) return;
+  const int lane = threadIdx.x & 31;
   const int inst = idx / groups, g = idx % groups;
   const int cpg = Ctot / groups;
+  const int total = splits * cpg;
   double s = 0.0, q = 0.0;
-  for (int sp = 0; sp < splits; ++sp) {
-    const float* w = ws + ((static_cast<int64_t>(inst) * splits + sp) * Ctot + g * cpg) * 2;
-    for (int c = 0; c < cpg; ++c) {
-      s += static_cast<double>(w[2 * c]);
-      q += static_cast<double>(w[2 * c + 1]);
-    }
+  for (int i = lane; i < total; i += 32) {
+    const int sp = i / cpg, c = i - sp * cpg;
+    const float2 v = *reinterpret_cast<const float2*>(
+        ws + ((static_cast<int64_t>(inst) * splits + sp) * Ctot + g * cpg + c) * 2);
+    s += static_cast<double>(v.x);
+    q += static_cast<double>(v.y);
   }
-  const double cnt = static_cast<double>(rows) * cpg;
-  const double mean = s / cnt;
-  double var = q / cnt - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[idx * 2 + 0] = static_cast<float>(mean);
-  stats[idx * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double cnt = static_cast<double>(rows) * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[idx * 2 + 0] = static_cast<float>(mean);
+    stats[idx * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -278,7 +289,7 @@ extern "C" int asva_groupnorm_stats(const void* x0, int32_t C0, const void* x1, 
                                                pl.cw, pl.rows_per_pass, partial_ws);
   ASVA_CUDA_OK(cudaGetLastError());
   const int total = n_inst * groups;
-  gn_stats_stage2<<<(total + 127) / 128, 128, 0, stream>>>(partial_ws, n_inst, pl.splits, Ctot, groups, rows, eps,
+  gn_stats_stage2<<<(total + 3) / 4, 128, 0, stream>>>(partial_ws, n_inst, pl.splits, Ctot, groups, rows, eps,
                                                             stats);
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
