@@ -76,11 +76,12 @@ ABI = {
     "asva_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                  C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "asva_groupnorm_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
-                                       C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                       C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "asva_groupnorm_ws_floats": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32]),
-    "asva_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                                       C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "asva_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p]),
     "asva_conv_in_im2col": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "asva_conv_out_finish": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -39,6 +39,12 @@ struct AttnCfg {
   static constexpr int kTmemCols = 256;
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2, flush-to-zero; exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // idesc for P(bf16, K-major, from smem) x V(bf16, MN-major): b_major bit 16 set
 __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t M, uint32_t N) {
   return make_idesc_bf16(M, N) | (1u << 16);
@@ -179,30 +185,36 @@ __global__ void __launch_bounds__(192, (DKA <= 2) ? 2 : 1) attn_tc_kernel(const 
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int key0 = j * KV;
-      // pass 1: row maximum
+      // pass 1: row maximum (interior tiles without a mask skip every per-key predicate)
+      const bool plain = (mrow == nullptr) && (key0 + KV <= p.Nk);
       float m_tile = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < KV; c += 32) {
         uint32_t sv[32];
         tmem_ld_x32(tmem_S + lane_base + c, sv);
         tmem_ld_wait();
-        uint32_t mbits = 0xffffffffu;
-        if (mrow != nullptr) {
-          mbits = 0;
+        if (plain) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
-        }
+          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sv[i]));
+        } else {
+          uint32_t mbits = 0xffffffffu;
+          if (mrow != nullptr) {
+            mbits = 0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
-          const float x = keep ? __uint_as_float(sv[i]) * p.scale_log2 : -INFINITY;
-          m_tile = fmaxf(m_tile, x);
+            for (int i = 0; i < 32; ++i)
+              if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
+            m_tile = fmaxf(m_tile, keep ? __uint_as_float(sv[i]) : -INFINITY);
+          }
         }
       }
+      m_tile *= p.scale_log2;  // scale > 0: max commutes with the scaling
       const float m_new = fmaxf(m_run, m_tile);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_safe);  // m_run = -inf -> 0
+      const float alpha = fast_exp2(m_run - m_safe);  // m_run = -inf -> 0
       const bool changed = (m_new > m_run) && (j > 0);
       m_run = m_new;
       l_run *= alpha;
@@ -229,19 +241,23 @@ __global__ void __launch_bounds__(192, (DKA <= 2) ? 2 : 1) attn_tc_kernel(const 
         uint32_t sv[32];
         tmem_ld_x32(tmem_S + lane_base + c, sv);
         tmem_ld_wait();
-        uint32_t mbits = 0xffffffffu;
-        if (mrow != nullptr) {
-          mbits = 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
-        }
         float pv[32];
+        if (plain) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
-          const float e = keep ? exp2f(__uint_as_float(sv[i]) * p.scale_log2 - m_safe) : 0.f;
-          pv[i] = e;
+          for (int i = 0; i < 32; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe));
+        } else {
+          uint32_t mbits = 0xffffffffu;
+          if (mrow != nullptr) {
+            mbits = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
+            pv[i] = keep ? fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe)) : 0.f;
+          }
         }
         // round to bf16 first so that the row sum matches what the tensor core will accumulate
         uint32_t pk[16];
@@ -317,6 +333,7 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
   ASVA_REQUIRE(d->d >= 8 && d->d % 8 == 0 && d->d <= 192, "asva_attention: head dim %d unsupported", d->d);
   ASVA_REQUIRE(d->dpad % 64 == 0 && d->dpad >= d->d && d->dpad <= 192, "asva_attention: dpad %d invalid", d->dpad);
   ASVA_REQUIRE(d->G >= 1 && d->heads >= 1 && d->R >= 1 && d->Nk >= 1, "asva_attention: empty problem");
+  ASVA_REQUIRE(d->scale > 0.f, "asva_attention: scale must be positive");
   ASVA_REQUIRE(d->ldkv % 8 == 0 && d->ldo % 8 == 0 && d->k_col0 % 8 == 0 && d->v_col0 % 8 == 0,
                "asva_attention: ldkv/ldo/k_col0/v_col0 must be multiples of 8");
   ASVA_REQUIRE(d->mask == nullptr || d->mask_rows >= 1, "asva_attention: mask_rows must be >= 1");

@@ -9,6 +9,7 @@ namespace asva {
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnMaxChunks = 8;  // 8 chunks x 8 elements x 32 lanes = 2048 channels
 
+template <int kChunks>  // ceil(C / 256): keeps the register footprint (and so the occupancy) proportional to C
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
@@ -21,10 +22,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   const int nchunk = C >> 3;
   const __nv_bfloat16* xr = x + row * C;
   const float* pr = (pos != nullptr) ? pos + static_cast<int64_t>((row / N) % F) * C : nullptr;
-  float v[kLnMaxChunks][8];
+  float v[kChunks][8];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
+  for (int i = 0; i < kChunks; ++i) {
     const int ch = lane + 32 * i;
     if (ch < nchunk) {
       const uint4 u = *reinterpret_cast<const uint4*>(xr + ch * 8);
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   const float mean = warp_sum(sum) / static_cast<float>(C);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
+  for (int i = 0; i < kChunks; ++i) {
     const int ch = lane + 32 * i;
     if (ch < nchunk) {
 #pragma unroll
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
   __nv_bfloat16* orow = out + row * C;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
+  for (int i = 0; i < kChunks; ++i) {
     const int ch = lane + 32 * i;
     if (ch < nchunk) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
@@ -164,16 +165,18 @@ __global__ void __launch_bounds__(256) gn_stats_stage1(const __nv_bfloat16* __re
 
 __global__ void __launch_bounds__(128) gn_stats_stage2(const float* __restrict__ ws, int n_inst, int splits, int Ctot,
                                                          int groups, int64_t rows, float eps,
-                                                         float* __restrict__ stats) {
-  // one warp per (instance, group): lanes stride over splits x channels-in-group, fp64 shuffle reduction
-  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (idx >= n_inst * groups) return;
-  const int lane = threadIdx.x & 31;
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ stats) {
+  // one CTA per (instance, group): threads stride over splits x channels-in-group, fp64 reduction, then the
+  // per-channel affine  y = x * scale + shift  (scale = rstd * gamma, shift = beta - mean * scale) is written
+  __shared__ double red[2][4];
+  __shared__ float mr[2];
+  const int idx = blockIdx.x;
   const int inst = idx / groups, g = idx % groups;
   const int cpg = Ctot / groups;
   const int total = splits * cpg;
   double s = 0.0, q = 0.0;
-  for (int i = lane; i < total; i += 32) {
+  for (int i = threadIdx.x; i < total; i += 128) {
     const int sp = i / cpg, c = i - sp * cpg;
     const float2 v = *reinterpret_cast<const float2*>(
         ws + ((static_cast<int64_t>(inst) * splits + sp) * Ctot + g * cpg + c) * 2);
@@ -185,13 +188,29 @@ __global__ void __launch_bounds__(128) gn_stats_stage2(const float* __restrict__
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
-  if (lane == 0) {
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    q = red[1][0] + red[1][1] + red[1][2] + red[1][3];
     const double cnt = static_cast<double>(rows) * cpg;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
-    stats[idx * 2 + 0] = static_cast<float>(mean);
-    stats[idx * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    mr[0] = static_cast<float>(mean);
+    mr[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const float mean = mr[0], rstd = mr[1];
+  for (int c = threadIdx.x; c < cpg; c += 128) {
+    const int ch = g * cpg + c;
+    const float sc = rstd * gamma[ch];
+    float* o = stats + (static_cast<int64_t>(inst) * Ctot + ch) * 2;
+    o[0] = sc;
+    o[1] = beta[ch] - mean * sc;
   }
 }
 
@@ -200,37 +219,34 @@ __global__ void __launch_bounds__(128) gn_stats_stage2(const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
                                                        const __nv_bfloat16* __restrict__ x1, int C1,
-                                                       const float* __restrict__ stats,
-                                                       const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, int groups, int img_per_inst,
-                                                       int h, int w, int silu, int up,
-                                                       __nv_bfloat16* __restrict__ out, int64_t total_chunks) {
+                                                       const float* __restrict__ stats, int img_per_inst, int h,
+                                                       int w, int silu, int up, __nv_bfloat16* __restrict__ out,
+                                                       int64_t total_chunks) {
   const int Ctot = C0 + C1;
   const int nchunk = Ctot >> 3;
-  const int cpg = Ctot / groups;
   const int ho = up ? 2 * h : h, wo = up ? 2 * w : w;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_chunks;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(i % nchunk);
     const int64_t pix = i / nchunk;
-    const int xo = static_cast<int>(pix % wo);
-    const int yo = static_cast<int>((pix / wo) % ho);
-    const int64_t img = pix / (static_cast<int64_t>(wo) * ho);
-    const int xs = up ? (xo >> 1) : xo, ys = up ? (yo >> 1) : yo;
-    const int64_t srow = (img * h + ys) * w + xs;
+    int64_t srow = pix, img = pix / (static_cast<int64_t>(wo) * ho);
+    if (up) {
+      const int xo = static_cast<int>(pix % wo);
+      const int yo = static_cast<int>((pix / wo) % ho);
+      srow = (img * h + (yo >> 1)) * w + (xo >> 1);
+    }
     const int c = ch * 8;
     const __nv_bfloat16* src = (c < C0) ? x0 + srow * C0 + c : x1 + srow * C1 + (c - C0);
     const uint4 u = *reinterpret_cast<const uint4*>(src);
     const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cz = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     float f[8] = {a.x, a.y, b.x, b.y, cz.x, cz.y, d.x, d.y};
     if (stats != nullptr) {
-      const int inst = static_cast<int>(img / img_per_inst);
-      const float* st = stats + static_cast<int64_t>(inst) * groups * 2;
+      const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(img / img_per_inst) * Ctot + c) * 2);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = (c + j) / cpg;
-        const float mean = __ldg(st + 2 * g), rstd = __ldg(st + 2 * g + 1);
-        f[j] = (f[j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldg(st + j);  // (scale, shift) of channels c+2j, c+2j+1
+        f[2 * j] = fmaf(f[2 * j], t.x, t.y);
+        f[2 * j + 1] = fmaf(f[2 * j + 1], t.z, t.w);
       }
     }
     if (silu) {
@@ -256,10 +272,17 @@ extern "C" int asva_layernorm(const void* x, const float* gamma, const float* be
   ASVA_REQUIRE(C % 8 == 0 && C >= 8 && C <= 8 * 32 * kLnMaxChunks, "asva_layernorm: C=%d unsupported", C);
   ASVA_REQUIRE(M >= 1, "asva_layernorm: M must be positive");
   ASVA_REQUIRE(pos == nullptr || (N >= 1 && F >= 1), "asva_layernorm: pos needs N, F");
-  const int64_t blocks = (M + 7) / 8;
-  layernorm_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, pos, reinterpret_cast<__nv_bfloat16*>(out), M, C, eps,
-      N > 0 ? N : 1, F > 0 ? F : 1);
+  const unsigned blocks = static_cast<unsigned>((M + 7) / 8);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
+  const int n = N > 0 ? N : 1, f = F > 0 ? F : 1;
+#define ASVA_LN_CASE(K) \
+  case K: layernorm_kernel<K><<<blocks, 256, 0, stream>>>(xp, gamma, beta, pos, op, M, C, eps, n, f); break;
+  switch ((C / 8 + 31) / 32) {
+    ASVA_LN_CASE(1) ASVA_LN_CASE(2) ASVA_LN_CASE(3) ASVA_LN_CASE(4) ASVA_LN_CASE(5) ASVA_LN_CASE(6) ASVA_LN_CASE(7)
+    default: layernorm_kernel<8><<<blocks, 256, 0, stream>>>(xp, gamma, beta, pos, op, M, C, eps, n, f); break;
+  }
+#undef ASVA_LN_CASE
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -271,13 +294,13 @@ extern "C" int64_t asva_groupnorm_ws_floats(int32_t n_inst, int64_t rows, int32_
 }
 
 extern "C" int asva_groupnorm_stats(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t n_inst,
-                                    int64_t rows, int32_t groups, float eps, float* stats, float* partial_ws,
-                                    asva_stream_t stream_) {
+                                    int64_t rows, int32_t groups, float eps, const float* gamma, const float* beta,
+                                    float* stats, float* partial_ws, asva_stream_t stream_) {
   using namespace asva;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (x1 == nullptr) C1 = 0;
   const int Ctot = C0 + C1;
-  ASVA_REQUIRE(x0 && stats && partial_ws, "asva_groupnorm_stats: null operand");
+  ASVA_REQUIRE(x0 && stats && partial_ws && gamma && beta, "asva_groupnorm_stats: null operand");
   ASVA_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && Ctot >= 8, "asva_groupnorm_stats: channels must be multiples of 8");
   ASVA_REQUIRE(groups >= 1 && Ctot % groups == 0, "asva_groupnorm_stats: C=%d not divisible by groups=%d", Ctot, groups);
   ASVA_REQUIRE(n_inst >= 1 && rows >= 1, "asva_groupnorm_stats: empty problem");
@@ -288,34 +311,30 @@ extern "C" int asva_groupnorm_stats(const void* x0, int32_t C0, const void* x1, 
                                                reinterpret_cast<const __nv_bfloat16*>(x1), C1, rows, pl.splits,
                                                pl.cw, pl.rows_per_pass, partial_ws);
   ASVA_CUDA_OK(cudaGetLastError());
-  const int total = n_inst * groups;
-  gn_stats_stage2<<<(total + 3) / 4, 128, 0, stream>>>(partial_ws, n_inst, pl.splits, Ctot, groups, rows, eps,
-                                                            stats);
+  gn_stats_stage2<<<n_inst * groups, 128, 0, stream>>>(partial_ws, n_inst, pl.splits, Ctot, groups, rows, eps, gamma,
+                                                        beta, stats);
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 extern "C" int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* stats,
-                                    const float* gamma, const float* beta, int32_t groups, int32_t n_inst,
-                                    int32_t n_img, int32_t h, int32_t w, int32_t silu, int32_t upsample, void* out,
-                                    asva_stream_t stream_) {
+                                    int32_t n_inst, int32_t n_img, int32_t h, int32_t w, int32_t silu,
+                                    int32_t upsample, void* out, asva_stream_t stream_) {
   using namespace asva;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (x1 == nullptr) C1 = 0;
   const int Ctot = C0 + C1;
   ASVA_REQUIRE(x0 && out, "asva_groupnorm_apply: null operand");
   ASVA_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && Ctot >= 8, "asva_groupnorm_apply: channels must be multiples of 8");
-  ASVA_REQUIRE(stats == nullptr || (gamma && beta && groups >= 1 && Ctot % groups == 0 && n_inst >= 1 &&
-                                    n_img % n_inst == 0),
+  ASVA_REQUIRE(stats == nullptr || (n_inst >= 1 && n_img % n_inst == 0),
                "asva_groupnorm_apply: inconsistent normalisation arguments");
   const int ho = upsample ? 2 * h : h, wo = upsample ? 2 * w : w;
   const int64_t total = static_cast<int64_t>(n_img) * ho * wo * (Ctot / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   gn_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, stats, gamma,
-      beta, groups > 0 ? groups : 1, n_inst > 0 ? n_img / n_inst : 1, h, w, silu, upsample,
-      reinterpret_cast<__nv_bfloat16*>(out), total);
+      reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, stats,
+      n_inst > 0 ? n_img / n_inst : 1, h, w, silu, upsample, reinterpret_cast<__nv_bfloat16*>(out), total);
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -89,7 +89,9 @@ class UNetEngine:
         self.groups = c["norm_num_groups"]
         self.eps = float(c["norm_eps"])
         self.shape = None
+        self.ctx, self.ctx_sig = None, None
         self._bufs: Dict[tuple, torch.Tensor] = {}
+        self._ctx_bufs: Dict[tuple, torch.Tensor] = {}
         self._pack(sd)
 
     # ------------------------------------------------------------------------------------------ weights
@@ -206,6 +208,7 @@ class UNetEngine:
             raise ValueError("1 <= F <= 32 frames supported")
         self._frozen = False
         self._bufs.clear()
+        self._ctx_bufs.clear()
         self.shape = (B, F, h, w)
         be = self.be
         ar = torch.arange(F, dtype=torch.float32, device=self.dev)
@@ -217,37 +220,71 @@ class UNetEngine:
             be.timestep_features(ar, feat, F, C, True)
             be.small_linear(feat, a["pos1_w"], a["pos1_b"], hid, F, C, C, 0, 1)
             be.small_linear(hid, a["pos2_w"], a["pos2_b"], a["pos"], F, C, C, 0, 0)
-        self.ctx = None
+        self.ctx, self.ctx_sig = None, None
+
+    def _ctx_buf(self, tag, shape, dtype):
+        key = (tag, tuple(shape), dtype)
+        t = self._ctx_bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            self._ctx_bufs[key] = t
+        return t
 
     def set_context(self, text: torch.Tensor, audio: torch.Tensor, audio_mask: Optional[torch.Tensor]) -> None:
         """Projects the clip's conditioning to per-block keys/values once (they are constant over the sampler loop).
         text (B,F,n_t,768) / audio (B,F,n_a,768) / audio_mask bool (B,F,n_a) in the reference's wire format
         (pipeline_audio_cond_animation.py:299,304-306).  Frame-invariant contexts (what the pipeline produces with
-        `repeat`, :177) are projected once per batch entry; frame-varying ones once per (b, f)."""
+        `repeat`, :177) are projected once per batch entry, frame-varying ones once per (b, f).  With an audio mask
+        the projected keys/values are then COMPACTED per (b, f) to the keys that frame may attend (25 of 229 at
+        F = 12, segmask_imagebind.py:104-114), so the attention kernel sees short dense key lists and no mask.
+        Results land in persistent buffers (same addresses for every clip of the same geometry) so a captured CUDA
+        graph stays valid; `ctx_sig` changes when the geometry does and owners of graphs must re-capture."""
         B, F, h, w = self.shape
         assert text.shape[:2] == (B, F) and audio.shape[:2] == (B, F), (text.shape, audio.shape, self.shape)
 
         def frame_invariant(t):
             return t.stride(1) == 0 or F == 1 or bool((t[:, :1] == t).all())
 
-        ctx = {}
+        ctx, sig = {}, []
         for name, t in (("attn2", text), ("attn_audio", audio)):
             inv = frame_invariant(t)
             src = t[:, 0] if inv else t.reshape(B * F, t.shape[2], t.shape[3])
             G, nk = src.shape[0], src.shape[1]
             x = src.reshape(G * nk, src.shape[-1]).to(self.dev, self.dt).contiguous()
+            gidx, cmask, nv = None, None, nk
+            if name == "attn_audio" and audio_mask is not None:
+                assert audio_mask.shape == (B, F, nk)
+                m = audio_mask.reshape(B * F, nk).to(self.dev).bool()
+                nv = max(1, int(m.sum(dim=1).max()))
+                # stable order: valid keys first (ascending), padded with key 0 where a row has fewer than nv
+                order = torch.argsort((~m).to(torch.int8), dim=1, stable=True)[:, :nv]
+                valid = torch.gather(m, 1, order)
+                base = (torch.arange(B * F, device=self.dev) // (F if inv else 1)) * nk
+                gidx = (base.view(-1, 1) + torch.where(valid, order, torch.zeros_like(order))).reshape(-1)
+                cmask = None if bool(valid.all()) else valid.to(torch.uint8).contiguous()
             kvs = []
-            for a in self.attns:
-                kv = torch.empty(G * nk, 2 * a["C"], dtype=self.dt, device=self.dev)
-                self.be.gemm(ops.spec_linear(x, a[name + ".kv"], kv))
-                kvs.append(kv)
-            ctx[name] = dict(inv=inv, G=G, nk=nk, kv=kvs)
-        if audio_mask is not None:
-            assert audio_mask.shape == (B, F, audio.shape[2])
-            ctx["mask"] = audio_mask.reshape(B * F, -1).to(self.dev, torch.uint8).contiguous()
-        else:
-            ctx["mask"] = None
+            for i, a in enumerate(self.attns):
+                full = self._ctx_buf(f"{name}.full{i}", (G * nk, 2 * a["C"]), self.dt)
+                self.be.gemm(ops.spec_linear(x, a[name + ".kv"], full))
+                if gidx is not None:
+                    kv = self._ctx_buf(f"{name}.kv{i}", (B * F * nv, 2 * a["C"]), self.dt)
+                    torch.index_select(full, 0, gidx, out=kv)
+                    kvs.append(kv)
+                else:
+                    kvs.append(full)
+            if gidx is not None:
+                ctx[name] = dict(inv=False, G=B * F, nk=nv, kv=kvs)
+                if cmask is not None:
+                    mb = self._ctx_buf("audio.mask", tuple(cmask.shape), torch.uint8)
+                    mb.copy_(cmask)
+                    cmask = mb
+            else:
+                ctx[name] = dict(inv=inv, G=G, nk=nk, kv=kvs)
+            sig.append((ctx[name]["inv"], ctx[name]["G"], ctx[name]["nk"], cmask is not None))
+            if name == "attn_audio":
+                ctx["mask"] = cmask
         self.ctx = ctx
+        self.ctx_sig = tuple(sig)
 
     # ------------------------------------------------------------------------------------------ building blocks
     def _ffconv_tail(self, cv: _Conv, y, out, B, F, N, tproj=None, res1=None):
@@ -257,11 +294,12 @@ class UNetEngine:
         be.gemm(ops.spec_tconv(y, cv.w2, out, B=B, F=F, N=N, head_term=head, tproj=tproj,
                                tproj_ld=self._tproj_total, res1=res1))
 
-    def _gn_stats(self, x0, C0, x1, C1, n_inst, rows, eps):
-        st = self.buf("gn_stats", (n_inst, self.groups, 2), torch.float32)
+    def _gn_stats(self, x0, C0, x1, C1, n_inst, rows, eps, gamma, beta):
+        """-> fp32 [n_inst, C, 2] per-channel (scale, shift) so that GroupNorm(x) = x * scale + shift."""
+        st = self.buf("gn_stats", (n_inst, C0 + C1, 2), torch.float32)
         need = max(16, int(self.be.groupnorm_ws_floats(n_inst, rows, C0 + C1)))
         ws = self.buf("gn_ws", (need,), torch.float32)
-        self.be.groupnorm_stats(x0, C0, x1, C1, n_inst, rows, self.groups, eps, st, ws)
+        self.be.groupnorm_stats(x0, C0, x1, C1, n_inst, rows, self.groups, eps, gamma, beta, st, ws)
         return st
 
     def _conv3(self, cv: _Conv, a, B, F, h, w, stride=1):
@@ -275,16 +313,16 @@ class UNetEngine:
         M = B * F * N
         C0, C1 = x0.shape[1], (x1.shape[1] if x1 is not None else 0)
         cin, cout = C0 + C1, r["conv1"].cout
-        st = self._gn_stats(x0, C0, x1, C1, B, F * N, self.eps)
+        st = self._gn_stats(x0, C0, x1, C1, B, F * N, self.eps, r["g1"], r["b1"])
         a = self.buf("gn_out", (M, cin))
-        be.groupnorm_apply(x0, C0, x1, C1, st, r["g1"], r["b1"], self.groups, B, B * F, h, w, True, False, a)
+        be.groupnorm_apply(x0, C0, x1, C1, st, B, B * F, h, w, True, False, a)
         y, _, _ = self._conv3(r["conv1"], a, B, F, h, w)
         h1 = self.buf("res_h1", (M, cout))
         tp = self.tproj[:, r["tproj_off"]: r["tproj_off"] + cout]
         self._ffconv_tail(r["conv1"], y, h1, B, F, N, tproj=tp)
-        st = self._gn_stats(h1, cout, None, 0, B, F * N, self.eps)
+        st = self._gn_stats(h1, cout, None, 0, B, F * N, self.eps, r["g2"], r["b2"])
         a2 = self.buf("gn_out", (M, cout))
-        be.groupnorm_apply(h1, cout, None, 0, st, r["g2"], r["b2"], self.groups, B, B * F, h, w, True, False, a2)
+        be.groupnorm_apply(h1, cout, None, 0, st, B, B * F, h, w, True, False, a2)
         y2, _, _ = self._conv3(r["conv2"], a2, B, F, h, w)
         if r["short"] is not None:
             sc = r["short"]
@@ -316,9 +354,9 @@ class UNetEngine:
     def _transformer(self, a: dict, x, B, F, h, w, idx: int, out_tag: str):
         be, N, C = self.be, h * w, a["C"]
         M = B * F * N
-        st = self._gn_stats(x, C, None, 0, B * F, N, 1e-6)
+        st = self._gn_stats(x, C, None, 0, B * F, N, 1e-6, a["gn_g"], a["gn_b"])
         g = self.buf("gn_out", (M, C))
-        be.groupnorm_apply(x, C, None, 0, st, a["gn_g"], a["gn_b"], self.groups, B * F, B * F, h, w, False, False, g)
+        be.groupnorm_apply(x, C, None, 0, st, B * F, B * F, h, w, False, False, g)
         t = self.buf("tok", (M, C))
         be.gemm(ops.spec_linear(g, a["pi_w"], t, bias=a["pi_b"]))
         n = self.buf("ln_out", (M, C))
@@ -419,16 +457,16 @@ class UNetEngine:
             if blk["up"] is not None:
                 C = x.shape[1]
                 u = self.buf("gn_out", (B * F * 4 * hh * ww, C))
-                be.groupnorm_apply(x, C, None, 0, None, None, None, self.groups, B, B * F, hh, ww, False, True, u)
+                be.groupnorm_apply(x, C, None, 0, None, B, B * F, hh, ww, False, True, u)
                 hh, ww = 2 * hh, 2 * ww
                 y, _, _ = self._conv3(blk["up"], u, B, F, hh, ww)
                 x = self.buf(up_tag(), (B * F * hh * ww, blk["up"].cout))
                 self._ffconv_tail(blk["up"], y, x, B, F, hh * ww)
         # conv_norm_out -> SiLU -> conv_out (3x3 to 4 channels, fp32) -> its temporal 3-tap in fp32
         C = ch[0]
-        st = self._gn_stats(x, C, None, 0, B, F * N, self.eps)
+        st = self._gn_stats(x, C, None, 0, B, F * N, self.eps, self.out_g, self.out_b)
         a = self.buf("gn_out", (B * F * N, C))
-        be.groupnorm_apply(x, C, None, 0, st, self.out_g, self.out_b, self.groups, B, B * F, h, w, True, False, a)
+        be.groupnorm_apply(x, C, None, 0, st, B, B * F, h, w, True, False, a)
         yo = self.buf("out_y", (B * F * N, 8), torch.float32)
         be.gemm(ops.spec_conv3x3(a, self.conv_out.w, yo, n_img=B * F, h=h, wd=w, bias=self.conv_out.b, out_fp32=True))
         be.conv_out_finish(yo, 8, self.conv_out.wt_full, self.conv_out.bt, out, B, self.cfg["out_channels"], F, h, w)

@@ -341,22 +341,23 @@ class CudaBackend:
     def groupnorm_ws_floats(self, n_inst, rows, C) -> int:
         return int(self.lib.asva_groupnorm_ws_floats(n_inst, rows, C))
 
-    def groupnorm_stats(self, x0, C0, x1, C1, n_inst, rows, groups, eps, stats, ws) -> None:
-        self._chk_dev(x0, x1, stats, ws)
-        assert ws.numel() >= self.groupnorm_ws_floats(n_inst, rows, C0 + (C1 if x1 is not None else 0))
+    def groupnorm_stats(self, x0, C0, x1, C1, n_inst, rows, groups, eps, gamma, beta, stats, ws) -> None:
+        """stats: fp32 [n_inst, C0+C1, 2] <- per-channel (scale, shift)."""
+        self._chk_dev(x0, x1, gamma, beta, stats, ws)
+        Ct = C0 + (C1 if x1 is not None else 0)
+        assert ws.numel() >= self.groupnorm_ws_floats(n_inst, rows, Ct) and stats.numel() >= n_inst * Ct * 2
         with self._timed('groupnorm'):
             _lib.check(self.lib.asva_groupnorm_stats(x0.data_ptr(), C0, _ptr(x1), C1, n_inst, rows, groups, eps,
-                                                 stats.data_ptr(), ws.data_ptr(), self._stream()),
-                   "asva_groupnorm_stats")
+                                                     gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                                                     ws.data_ptr(), self._stream()), "asva_groupnorm_stats")
         self.launches += 2
 
-    def groupnorm_apply(self, x0, C0, x1, C1, stats, gamma, beta, groups, n_inst, n_img, h, w, silu, upsample,
-                        out) -> None:
-        self._chk_dev(x0, x1, stats, gamma, beta, out)
+    def groupnorm_apply(self, x0, C0, x1, C1, stats, n_inst, n_img, h, w, silu, upsample, out) -> None:
+        self._chk_dev(x0, x1, stats, out)
         with self._timed('groupnorm'):
-            _lib.check(self.lib.asva_groupnorm_apply(x0.data_ptr(), C0, _ptr(x1), C1, _ptr(stats), _ptr(gamma),
-                                                 _ptr(beta), groups, n_inst, n_img, h, w, int(silu), int(upsample),
-                                                 out.data_ptr(), self._stream()), "asva_groupnorm_apply")
+            _lib.check(self.lib.asva_groupnorm_apply(x0.data_ptr(), C0, _ptr(x1), C1, _ptr(stats), n_inst, n_img, h,
+                                                     w, int(silu), int(upsample), out.data_ptr(), self._stream()),
+                       "asva_groupnorm_apply")
         self.launches += 1
 
     def conv_in_im2col(self, lat, out, B, Bs, Cl, F, h, w) -> None:

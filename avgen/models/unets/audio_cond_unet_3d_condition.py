@@ -219,6 +219,7 @@ class AudioUNet3DConditionModel(nn.Module):
         self.conv_out = _InflatedConv(ch[0], cfg["out_channels"], 3, padding=1)
         self._eng = None
         self._runner = None
+        self._runner_sig = None
         self._ctx_key = None
         self._ctx_keepalive = None
         self.eval()
@@ -384,7 +385,10 @@ class AudioUNet3DConditionModel(nn.Module):
                 eng.prepare(B, F, h, w)
                 self._runner, self._ctx_key = None, None
             self.bind_context(encoder_hidden_states, audio_encoder_hidden_states, audio_attention_mask)
+            if self._runner is not None and self._runner_sig != eng.ctx_sig:
+                self._runner = None  # context geometry changed: the captured graph addresses other buffers
             if self._runner is None:
+                self._runner_sig = eng.ctx_sig
                 self._io = (torch.empty(B, C, F, h, w, dtype=torch.float32, device=sample.device),
                             torch.empty(B, dtype=torch.float32, device=sample.device),
                             torch.empty(B, self.config.out_channels, F, h, w, dtype=torch.float32, device=sample.device))

@@ -311,7 +311,7 @@ class DenoiseSession:
                 eng.prepare(k, F, h, w)
                 unet._runner, unet._ctx_key, pipe._loop = None, None, None
             unet.bind_context(text, audio, masks)
-            key = (k, C, F, h, w, self.plms, id(eng))
+            key = (k, C, F, h, w, self.plms, id(eng), eng.ctx_sig)
             if pipe._loop is None or pipe._loop["key"] != key:
                 L = dict(key=key,
                          lat=torch.empty(1, C, F, h, w, dtype=torch.float32, device=dev),

@@ -126,22 +126,24 @@ int asva_layernorm(const void* x, const float* gamma, const float* beta, const f
                    int32_t C, float eps, int32_t N, int32_t F, asva_stream_t stream);
 
 /* GroupNorm statistics over channels-last data.  Instance i covers rows [i*rows, (i+1)*rows) of the (virtually
- * concatenated) sources x0[.,C0] | x1[.,C1]; group g covers channels [g*(C0+C1)/groups, ...).  Writes
- * stats[i][g] = (mean, rstd).  Replaces the statistics half of nn.GroupNorm in FFSpatioTempResnetBlock3D
- * (resnets/ff_spatio_temp_resnet_3d.py:164,175; instance = one clip, all frames), the per-frame GroupNorm of
- * the transformer (ff_spatio_audio_temp_transformer_3d.py:117) and conv_norm_out
+ * concatenated) sources x0[.,C0] | x1[.,C1]; group g covers channels [g*(C0+C1)/groups, ...).  Writes the folded
+ * per-channel affine  stats[i][c] = (scale, shift)  with scale = rstd_g * gamma[c], shift = beta[c] - mean_g * scale,
+ * so that GroupNorm(x)[c] = x * scale + shift.  Replaces the statistics half of nn.GroupNorm in
+ * FFSpatioTempResnetBlock3D (resnets/ff_spatio_temp_resnet_3d.py:164,175; instance = one clip, all frames), the
+ * per-frame GroupNorm of the transformer (ff_spatio_audio_temp_transformer_3d.py:117) and conv_norm_out
  * (audio_cond_unet_3d_condition.py:791). */
 int asva_groupnorm_stats(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t n_inst, int64_t rows,
-                         int32_t groups, float eps, float* stats, float* partial_ws, asva_stream_t stream);
+                         int32_t groups, float eps, const float* gamma, const float* beta, float* stats,
+                         float* partial_ws, asva_stream_t stream);
 /* number of floats asva_groupnorm_stats needs in partial_ws */
 int64_t asva_groupnorm_ws_floats(int32_t n_inst, int64_t rows, int32_t C /* C0 + C1 */);
 
 /* GroupNorm apply (+ optional SiLU, + optional nearest 2x spatial upsample, + channel concat of two sources)
- * -> bf16 [n_img][h_out][w_out][C0+C1].  upsample=1 replicates each source pixel 2x2
- * (F.interpolate nearest, ff_spatio_temp_resnet_3d.py:47); stats==NULL skips the normalisation. */
-int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* stats,
-                         const float* gamma, const float* beta, int32_t groups, int32_t n_inst, int32_t n_img,
-                         int32_t h, int32_t w, int32_t silu, int32_t upsample, void* out, asva_stream_t stream);
+ * -> bf16 [n_img][h_out][w_out][C0+C1] with the (scale, shift) table of asva_groupnorm_stats.  upsample=1 replicates
+ * each source pixel 2x2 (F.interpolate nearest, ff_spatio_temp_resnet_3d.py:47); stats==NULL skips the affine. */
+int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* stats, int32_t n_inst,
+                         int32_t n_img, int32_t h, int32_t w, int32_t silu, int32_t upsample, void* out,
+                         asva_stream_t stream);
 
 /* conv_in front end: fp32 latents [Bs][Cl][F][h][w] (Cl<=7) -> bf16 im2col rows [B*F*h*w][64] for the 3x3, pad 1
  * conv (column = tap*Cl + c, zero padded to 64); batch b reads latent b % Bs (CFG duplication,

@@ -134,7 +134,7 @@ class SimBackend:
     def groupnorm_ws_floats(self, n_inst, rows, C) -> int:
         return 16
 
-    def groupnorm_stats(self, x0, C0, x1, C1, n_inst, rows, groups, eps, stats, ws) -> None:
+    def groupnorm_stats(self, x0, C0, x1, C1, n_inst, rows, groups, eps, gamma, beta, stats, ws) -> None:
         self.launches += 2
         v = x0.view(n_inst, rows, C0).float()
         if x1 is not None:
@@ -142,24 +142,21 @@ class SimBackend:
         Ct = v.shape[2]
         g = v.view(n_inst, rows, groups, Ct // groups).permute(0, 2, 1, 3).reshape(n_inst, groups, -1).double()
         mean = g.mean(dim=2)
-        var = g.var(dim=2, unbiased=False)
-        st = torch.stack([mean, 1.0 / torch.sqrt(var + eps)], dim=2).float()
-        stats.view(n_inst, groups, 2).copy_(st)
+        rstd = 1.0 / torch.sqrt(g.var(dim=2, unbiased=False) + eps)
+        mean_c = mean.repeat_interleave(Ct // groups, dim=1)
+        scale = rstd.repeat_interleave(Ct // groups, dim=1) * gamma.double().view(1, Ct)
+        shift = beta.double().view(1, Ct) - mean_c * scale
+        stats.view(n_inst, Ct, 2).copy_(torch.stack([scale, shift], dim=2).float())
 
-    def groupnorm_apply(self, x0, C0, x1, C1, stats, gamma, beta, groups, n_inst, n_img, h, w, silu, upsample,
-                        out) -> None:
+    def groupnorm_apply(self, x0, C0, x1, C1, stats, n_inst, n_img, h, w, silu, upsample, out) -> None:
         self.launches += 1
         v = x0.view(n_img, h, w, C0).float()
         if x1 is not None:
             v = torch.cat([v, x1.view(n_img, h, w, C1).float()], dim=3)
         Ct = v.shape[3]
         if stats is not None:
-            st = stats.view(n_inst, groups, 2)
-            ipi = n_img // n_inst
-            mean = st[:, :, 0].repeat_interleave(Ct // groups, dim=1).repeat_interleave(ipi, dim=0)
-            rstd = st[:, :, 1].repeat_interleave(Ct // groups, dim=1).repeat_interleave(ipi, dim=0)
-            v = (v - mean.view(n_img, 1, 1, Ct)) * rstd.view(n_img, 1, 1, Ct) * gamma.float().view(1, 1, 1, Ct) + \
-                beta.float().view(1, 1, 1, Ct)
+            st = stats.view(n_inst, Ct, 2).repeat_interleave(n_img // n_inst, dim=0)
+            v = v * st[:, :, 0].view(n_img, 1, 1, Ct) + st[:, :, 1].view(n_img, 1, 1, Ct)
         if silu:
             v = torch.nn.functional.silu(v)
         if upsample:

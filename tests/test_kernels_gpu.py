@@ -240,13 +240,18 @@ def test_groupnorm(cuda_backend, n_inst, rows, C0, C1):
     x1 = _rand((n_inst * rows, C1), 71) if C1 else None
     C = C0 + C1
     g, b = _rand((C,), 72, dtype=torch.float32), _rand((C,), 73, dtype=torch.float32)
-    st_ref = torch.zeros(n_inst, 32, 2, dtype=torch.float32, device=DEV)
+    st_ref = torch.zeros(n_inst, C, 2, dtype=torch.float32, device=DEV)
     st_cu = torch.zeros_like(st_ref)
     ws = torch.zeros(max(16, cuda_backend.groupnorm_ws_floats(n_inst, rows, C)), dtype=torch.float32, device=DEV)
-    SimBackend().groupnorm_stats(x0, C0, x1, C1, n_inst, rows, 32, 1e-5, st_ref, ws)
-    cuda_backend.groupnorm_stats(x0, C0, x1, C1, n_inst, rows, 32, 1e-5, st_cu, ws)
+    SimBackend().groupnorm_stats(x0, C0, x1, C1, n_inst, rows, 32, 1e-5, g, b, st_ref, ws)
+    cuda_backend.groupnorm_stats(x0, C0, x1, C1, n_inst, rows, 32, 1e-5, g, b, st_cu, ws)
     torch.cuda.synchronize()
-    _report("gn stats", st_cu.view(-1, 2), st_ref.view(-1, 2), 1e-4)
+    _report("gn scale/shift", st_cu.view(-1, 2), st_ref.view(-1, 2), 1e-4)
+    # against torch's own group_norm on the concatenated NCHW tensor
+    xc = torch.cat([x0.float()] + ([x1.float()] if C1 else []), dim=1).view(n_inst, rows, C).permute(0, 2, 1)
+    want = torch.nn.functional.group_norm(xc, 32, g, b, 1e-5).permute(0, 2, 1)
+    have = xc.permute(0, 2, 1) * st_cu[:, :, 0].view(n_inst, 1, C) + st_cu[:, :, 1].view(n_inst, 1, C)
+    _report("gn vs F.group_norm", have.reshape(-1, C), want.reshape(-1, C), 1e-4)
     # apply: treat every instance as `rows` = h*w pixels of one image; with and without 2x upsample
     h = 1
     for cand in (32, 16, 8, 5, 2, 1):
@@ -258,10 +263,15 @@ def test_groupnorm(cuda_backend, n_inst, rows, C0, C1):
         shp = (n_inst * rows * (4 if up else 1), C)
         o_ref = torch.zeros(shp, dtype=torch.bfloat16, device=DEV)
         o_cu = torch.zeros_like(o_ref)
-        SimBackend().groupnorm_apply(x0, C0, x1, C1, st_ref, g, b, 32, n_inst, n_inst, h, w, 1, up, o_ref)
-        cuda_backend.groupnorm_apply(x0, C0, x1, C1, st_ref, g, b, 32, n_inst, n_inst, h, w, 1, up, o_cu)
+        SimBackend().groupnorm_apply(x0, C0, x1, C1, st_ref, n_inst, n_inst, h, w, 1, up, o_ref)
+        cuda_backend.groupnorm_apply(x0, C0, x1, C1, st_ref, n_inst, n_inst, h, w, 1, up, o_cu)
         torch.cuda.synchronize()
         _report(f"gn apply up{up}", o_cu, o_ref, 4e-3)
+    o_ref.zero_(), o_cu.zero_()
+    SimBackend().groupnorm_apply(x0, C0, x1, C1, None, n_inst, n_inst, h, w, 0, 1, o_ref)
+    cuda_backend.groupnorm_apply(x0, C0, x1, C1, None, n_inst, n_inst, h, w, 0, 1, o_cu)
+    torch.cuda.synchronize()
+    assert torch.equal(o_ref, o_cu)  # pure nearest-upsample copy
 
 
 # ------------------------------------------------------------------------------------------------ small kernels

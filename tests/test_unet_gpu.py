@@ -2,8 +2,9 @@
 (1) tests/golden/ fixtures produced by executing the reference's own UNet files on CPU in fp32
 (oracle/make_goldens.py) and (2) the clean-room CPU oracle on fresh seeds.
 Stated tolerance (reference fp32 vs bf16-storage / fp32-accumulate kernels; SURVEY.md section 8(c) calibrates torch's
-own bf16 eager run of the reference at rel-L2 1.45e-2): one UNet forward rel-L2 <= 2.5e-2 and cosine >= 0.9995;
-N-step sampler latents rel-L2 <= 3e-2."""
+own bf16 eager run of the reference at rel-L2 1.45e-2): one UNet forward at the SD-1.5 geometry rel-L2 <= 2e-2 and
+cosine >= 0.9995; the 64..256-channel toy geometries (fewer channels to average the rounding over) rel-L2 <= 3e-2;
+N-step sampler latents on the toy geometry rel-L2 <= 3.5e-2."""
 import glob
 import os
 
@@ -49,7 +50,7 @@ def test_unet_vs_reference_golden_tiny(cuda_backend, path):
     for rep in range(3):  # eager, graph capture, graph replay must all agree
         y = m(x, g["t"], encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
               audio_attention_mask=mask.cuda()).sample
-        _check(f"{os.path.basename(path)} call {rep}", y, g["out"], 2.5e-2)
+        _check(f"{os.path.basename(path)} call {rep}", y, g["out"], 3e-2)
 
 
 def test_unet_vs_reference_golden_sd15(cuda_backend):
@@ -60,7 +61,7 @@ def test_unet_vs_reference_golden_sd15(cuda_backend):
     for rep in range(3):
         y = m(x, torch.tensor(g["t"]), encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
               audio_attention_mask=mask.cuda()).sample
-        _check(f"sd15 12x32x32 call {rep}", y, g["out"], 2.5e-2)
+        _check(f"sd15 12x32x32 call {rep}", y, g["out"], 2e-2)
 
 
 def test_unet_vs_oracle_fresh_seed_and_frame_varying_context(cuda_backend):
@@ -78,12 +79,12 @@ def test_unet_vs_oracle_fresh_seed_and_frame_varying_context(cuda_backend):
         ref = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, 37, text, audio, mask)
     y = m(x.cuda(), 37, encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
           audio_attention_mask=mask.cuda(), return_dict=False)[0]
-    _check("fresh seed, per-frame contexts", y, ref, 2.5e-2)
+    _check("fresh seed, per-frame contexts", y, ref, 3e-2)
     y2 = m(x.cuda(), 37, encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
            audio_attention_mask=None).sample
     with torch.no_grad():
         ref2 = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, 37, text, audio, None)
-    _check("no audio mask", y2, ref2, 2.5e-2)
+    _check("no audio mask", y2, ref2, 3e-2)
 
 
 @pytest.mark.parametrize("name", ["ddim", "pndm"])
@@ -104,7 +105,7 @@ def test_sampler_trace_vs_golden(cuda_backend, name):
         assert len(trace) == g["trace"].shape[0]
         assert torch.equal(out.cpu()[:, :, 0], lat[:, :, 0]), "conditioning frame must never change"
         for i in (0, 1, 2, len(trace) - 1):
-            _check(f"{name} run {run} after step {i + 1}", trace[i], g["trace"][i], 3e-2)
+            _check(f"{name} run {run} after step {i + 1}", trace[i], g["trace"][i], 3.5e-2)
     assert pipe.last_launches > 0
 
 
@@ -126,3 +127,33 @@ def test_generic_scheduler_path_matches_fused(cuda_backend):
     gen.scheduler.set_timesteps(4)
     b = gen._denoise_generic(args[0], args[1], args[2], args[3], 2, False, True, 4.0, 1.0, None)
     _check("generic vs fused loop", b, a, 2e-2)
+
+
+def test_context_swap_after_graph_capture(cuda_backend):
+    """A captured step graph must see the NEXT clip's conditioning (persistent context buffers), including a
+    change of context geometry (ragged mask -> rule mask) that forces a re-capture."""
+    from oracle import unet_ref
+    chans = (64, 128, 256, 256)
+    m, sd = _model(chans)
+    B, F, h, w = 2, 4, 8, 8
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(B, 4, F, h, w, generator=g)
+
+    def run(text, audio, mask, name, reps):
+        with torch.no_grad():
+            ref = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, 500, text, audio, mask)
+        for r in range(reps):
+            y = m(x.cuda(), 500, encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
+                  audio_attention_mask=mask.cuda()).sample
+            _check(f"{name} rep {r}", y, ref, 3e-2)
+
+    rule = synth.audio_segment_mask(F)[None].expand(B, -1, -1).contiguous()
+    t1 = torch.randn(B, 1, 77, 768, generator=g).expand(B, F, 77, 768)
+    a1 = torch.randn(B, 1, 229, 768, generator=g).expand(B, F, 229, 768)
+    run(t1, a1, rule, "clip 1", 3)                       # eager, capture, replay
+    t2 = torch.randn(B, 1, 77, 768, generator=g).expand(B, F, 77, 768)
+    a2 = torch.randn(B, 1, 229, 768, generator=g).expand(B, F, 229, 768)
+    run(t2, a2, rule, "clip 2 (same geometry, replayed graph)", 2)
+    ragged = torch.rand(B, F, 229, generator=g) < 0.2
+    ragged[:, :, 0] = True
+    run(t2, a2, ragged, "clip 3 (ragged mask)", 3)
