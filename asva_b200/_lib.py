@@ -17,12 +17,12 @@ class AsvaError(RuntimeError):
 
 
 class GemmSeg(C.Structure):
-    _fields_ = [("src", C.c_int32), ("c0", C.c_int32), ("off", C.c_int32 * 3), ("num_kb", C.c_int32)]
+    _fields_ = [("src", C.c_int32), ("c0", C.c_int32), ("off", C.c_int32 * 3), ("num_kb", C.c_int32),
+                ("wk", C.c_int32), ("wk_first", C.c_int32), ("fix2", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RowAdd(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("div_outer", C.c_int32), ("mul_outer", C.c_int32),
-                ("mod_inner", C.c_int32), ("sel_lt", C.c_int32), ("sel_off", C.c_int32)]
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("div", C.c_int32), ("reserved", C.c_int32)]
 
 
 class GemmDesc(C.Structure):
@@ -39,27 +39,27 @@ class GemmDesc(C.Structure):
         ("ldw", C.c_int64),
         ("N", C.c_int32),
         ("K", C.c_int32),
+        ("wcols", C.c_int32),
+        ("reserved0", C.c_int32),
         ("bias", C.c_void_p),
-        ("add", RowAdd * 2),
+        ("add", RowAdd),
         ("res", C.c_void_p * 2),
         ("res_ld", C.c_int64 * 2),
         ("geglu", C.c_int32),
         ("out_fp32", C.c_int32),
         ("out", C.c_void_p),
-        ("row_s1", C.c_int64),
-        ("row_s0", C.c_int64),
-        ("col_s1", C.c_int64),
-        ("row_div", C.c_int32),
-        ("col_div", C.c_int32),
+        ("ldo", C.c_int64),
         ("block_n", C.c_int32),
-        ("reserved", C.c_int32),
+        ("split_k", C.c_int32),
+        ("ws", C.c_void_p),
+        ("ws_bytes", C.c_int64),
     ]
 
 
 class AttnDesc(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("kv", C.c_void_p), ("mask", C.c_void_p), ("out", C.c_void_p),
-        ("ldkv", C.c_int64), ("ldo", C.c_int64), ("mask_ld", C.c_int64),
+        ("ldq", C.c_int64), ("ldkv", C.c_int64), ("ldo", C.c_int64), ("mask_ld", C.c_int64),
         ("G", C.c_int32), ("heads", C.c_int32), ("R", C.c_int32), ("Nk", C.c_int32), ("d", C.c_int32),
         ("dpad", C.c_int32),
         ("kv_rows_per_group", C.c_int32), ("k_col0", C.c_int32), ("v_col0", C.c_int32), ("mask_rows", C.c_int32),

@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(192, (DKA <= 2) ? 2 : 1) attn_tc_kernel(const 
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
 #pragma unroll
-      for (int a = 0; a < DKA; ++a) tma_load_3d(sQ + a * 128 * 128, &p.tmQ, q_full, a * 64, row0, g * p.heads + head);
+      // Q comes straight from the token-major projection output: tensor (d, heads, rows); the 64-wide box reaches
+      // past d and TMA zero-fills the padding
+      for (int a = 0; a < DKA; ++a) tma_load_3d(sQ + a * 128 * 128, &p.tmQ, q_full, a * 64, head, g * p.R + row0);
       const uint32_t tx = static_cast<uint32_t>(DKA + p.nvb) * KV * 128u;
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
@@ -336,6 +338,8 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
   ASVA_REQUIRE(d->scale > 0.f, "asva_attention: scale must be positive");
   ASVA_REQUIRE(d->ldkv % 8 == 0 && d->ldo % 8 == 0 && d->k_col0 % 8 == 0 && d->v_col0 % 8 == 0,
                "asva_attention: ldkv/ldo/k_col0/v_col0 must be multiples of 8");
+  ASVA_REQUIRE(d->ldq % 8 == 0 && d->ldq >= (int64_t)d->heads * d->d, "asva_attention: ldq=%lld invalid",
+               (long long)d->ldq);
   ASVA_REQUIRE(d->mask == nullptr || d->mask_rows >= 1, "asva_attention: mask_rows must be >= 1");
   ASVA_REQUIRE(d->kv_rows_per_group >= d->Nk, "asva_attention: kv_rows_per_group < Nk");
 
@@ -359,9 +363,9 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
   const int dka = d->dpad / 64;
   const int kv = (dka == 1) ? 128 : 64;
   {
-    uint64_t dims[3] = {(uint64_t)d->dpad, (uint64_t)d->R, (uint64_t)d->G * (uint64_t)d->heads};
-    uint64_t strides[2] = {(uint64_t)d->dpad * 2u, (uint64_t)d->R * (uint64_t)d->dpad * 2u};
-    uint32_t box[3] = {64u, 128u, 1u};
+    uint64_t dims[3] = {(uint64_t)d->d, (uint64_t)d->heads, (uint64_t)d->G * (uint64_t)d->R};
+    uint64_t strides[2] = {(uint64_t)d->d * 2u, (uint64_t)d->ldq * 2u};
+    uint32_t box[3] = {64u, 1u, 128u};
     uint32_t el[3] = {1u, 1u, 1u};
     int rc = make_tmap_bf16(&kp.tmQ, d->q, 3, dims, strides, box, el);
     if (rc != 0) return rc;

@@ -1,103 +1,130 @@
 // tcgen05 GEMM for sm_100a:  out[M,N] = epilogue( A[M,K] * W[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
 //
-// Persistent kernel: one CTA per SM walks output tiles (128 x BN) round-robin. Warp roles (192 threads):
-//   warp 0      TMA producer: per 64-wide K block one 4-D box load of A (table-driven: implicit-GEMM conv taps,
-//               temporal taps, concat sources) and one 2-D box load of W into a 128B-swizzled smem ring
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per K block); the accumulator is double
-//               buffered in TMEM (2 x BN columns), so tile t+1's main loop runs under tile t's epilogue
-//   warps 2..5  epilogue, two phases per 64-column panel:
-//                 1. tcgen05.ld (lane = output row) -> fp32 staging tile in smem (odd 16-byte pitch: conflict free)
-//                 2. threads re-map to (row, 8-column chunk) so that consecutive lanes touch consecutive 16 bytes of
-//                    one output row: bias / broadcast adds / residual loads and the bf16|fp32 stores are coalesced
+// Persistent kernel, one CTA per SM walking 128 x BN output tiles round-robin; every global access is a TMA
+// transfer, so no warp ever waits on a global load. Warp roles (384 threads):
+//   warp 0       TMA producer: per 64-wide K block one 4-D box load of A (table driven: implicit-GEMM conv taps,
+//                temporal taps, concat sources) and one 2-D box load of W into a 128B-swizzled smem ring
+//   warp 1       TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per K block); the accumulator is double
+//                buffered in TMEM (2 x BN columns), so tile t+1's main loop runs under tile t's epilogue
+//   warp 2       epilogue loader: streams the residual operands of each 32-column output panel through a second
+//                TMA ring (64B-swizzled [128 rows][32 bf16] slots), ahead of the epilogue warps
+//   warps 4..11  epilogue, two groups of 4 warps (warp % 4 = TMEM lane quadrant, thread = output row); the groups
+//                take alternate 32-column panels: tcgen05.ld -> + bias / per-row-block addend / residual panels
+//                (from smem) [or GEGLU] -> swizzled staging slot -> one elected thread issues the TMA store
+//                (tails are clipped by the tensor map). Staging slots are double buffered per group.
+// Split-K (small-M, long-K problems): tiles are (split, m, n) triples writing fp32 partial tiles to a scratch
+// buffer through the same TMA-store path; splitk_finalize_kernel then reduces them and applies the epilogue.
 #include "common.cuh"
 #include "host_common.h"
+#include <stdlib.h>
 #include <string.h>
 
 namespace asva {
 
+constexpr int kMaxStages = 8;
+constexpr int kResSlots = 3;          // residual-panel slots per epilogue group
+constexpr int kResSlotBytes = 8192;   // 128 rows x 32 bf16
+constexpr int kGemmThreads = 384;
+constexpr int kSmemLimit = 232448;    // 227 KB opt-in maximum per CTA
+constexpr int kBarBytes = 512;
+
 struct SegK {
-  int32_t src, c0, off1, off2, off3, num_kb;
-};
-struct RowAddK {
-  const float* ptr;
-  int64_t ld;
-  int32_t div_outer, mul_outer, mod_inner, sel_lt, sel_off;
+  int32_t src, c0, off1, off2, off3, num_kb, wk, wk_first, fix2;
 };
 
 struct GemmKParams {
-  CUtensorMap tmA0, tmA1, tmW;
+  CUtensorMap tmA0, tmA1, tmW, tmR0, tmR1, tmO;
   SegK seg[ASVA_GEMM_MAX_SEG];
   int32_t box[3], trav[3], out_dims[3], tiles[3];
-  int32_t rows_per_tile, N, num_kb, n_tiles_n, total_tiles;
+  int32_t rows_per_tile, N, n_out, num_kb, n_tiles_n, mn_tiles, total_tiles, split_k, kb_per_split;
+  int32_t n_stages, n_res, out_fp32;
   const float* bias;
-  RowAddK add[2];
-  const __nv_bfloat16* res[2];
-  int64_t res_ld[2];
-  void* out;
-  int64_t row_s1, row_s0, col_s1;
-  int32_t row_div, col_div, out_fp32;
+  const float* add_ptr;
+  int64_t add_ld;
+  int32_t add_div;
 };
 
-struct RowInfo {  // per output row of the current tile, written by the thread that owns the TMEM lane
-  int64_t row;      // global output row, -1 = outside the problem
-  int64_t out_off;  // element offset of the row in `out`
-  int64_t add_off[2];
+struct TileCoord {
+  int n0, o1, o2, o3, split, kb0, kb1;
 };
 
-template <int BN, bool GEGLU>
-struct GemmCfg {
-  static constexpr int kStages = (BN <= 64) ? 6 : 4;
-  static constexpr int kABytes = 128 * 128;
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutCols = GEGLU ? 64 : BN;        // output columns per tile
-  static constexpr int kPanel = 64;                        // columns staged at a time
-  static constexpr int kPitch = kPanel * 4 + 16;           // bytes per staged row (odd multiple of 16)
-  static constexpr int kStagingBytes = 128 * kPitch;
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 128 * (int)sizeof(RowInfo) +
-                                    1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-__device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
+  TileCoord t;
+  t.split = tile / p.mn_tiles;
+  const int rem = tile - t.split * p.mn_tiles;
+  const int nt = rem % p.n_tiles_n;
+  const int mt = rem / p.n_tiles_n;
+  t.n0 = nt * BN;
+  t.o1 = (mt % p.tiles[0]) * p.box[0];
+  t.o2 = ((mt / p.tiles[0]) % p.tiles[1]) * p.box[1];
+  t.o3 = (mt / (p.tiles[0] * p.tiles[1])) * p.box[2];
+  t.kb0 = t.split * p.kb_per_split;
+  t.kb1 = min(p.num_kb, t.kb0 + p.kb_per_split);
+  return t;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, bool GEGLU>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<BN, GEGLU>;
-  constexpr int kStages = Cfg::kStages;
+__device__ __forceinline__ int tile_panels(const GemmKParams& p, int n0) {
+  constexpr int kOutCols = GEGLU ? 64 : BN;
+  const int n0_out = GEGLU ? (n0 >> 1) : n0;
+  const int left = p.n_out - n0_out;
+  return ((left < kOutCols ? left : kOutCols) + 31) >> 5;
+}
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <int BN, bool GEGLU>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
+  constexpr int kABytes = 128 * 128;
+  constexpr int kBBytes = BN * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
-  RowInfo* rowinfo = reinterpret_cast<RowInfo*>(staging + Cfg::kStagingBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(rowinfo + 128);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  const int n_stages = p.n_stages;
+  uint8_t* res_ring = smem + n_stages * kStageBytes;
+  uint8_t* out_ring = res_ring + (p.n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0);
+  const int out_slot_bytes = p.out_fp32 ? 16384 : 8192;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_ring + 4 * out_slot_bytes);
+  uint64_t* full_bar = bars;                     // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2 * kResSlots]
+  uint64_t* res_empty_bar = res_full_bar + 2 * kResSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 2 * kResSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[a], 8);  // one arrival per epilogue warp
+    }
+    for (int s = 0; s < 2 * kResSlots; ++s) {
+      mbar_init(&res_full_bar[s], 1);
+      mbar_init(&res_empty_bar[s], 4);   // one arrival per warp of the owning group
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmW);
+    tma_prefetch_desc(&p.tmO);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -106,27 +133,30 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ---------------- TMA producer (A, W) ----------------
     if (lane == 0) {
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.rows_per_tile) * 128u + Cfg::kBBytes;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.rows_per_tile) * 128u + kBBytes;
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles_n) * BN;
-        const int mt = tile / p.n_tiles_n;
-        const int t1 = mt % p.tiles[0];
-        const int t2 = (mt / p.tiles[0]) % p.tiles[1];
-        const int t3 = mt / (p.tiles[0] * p.tiles[1]);
-        const int i1 = t1 * p.box[0] * p.trav[0], i2 = t2 * p.box[1] * p.trav[1], i3 = t3 * p.box[2] * p.trav[2];
-        int seg = 0, kin = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const uint32_t s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
+        const TileCoord tc = decode_tile<BN>(p, tile);
+        const int i1 = tc.o1 * p.trav[0], i2 = tc.o2 * p.trav[1], i3 = tc.o3 * p.trav[2];
+        int seg = 0, kin = tc.kb0;
+        while (kin >= p.seg[seg].num_kb) {
+          kin -= p.seg[seg].num_kb;
+          ++seg;
+        }
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
+          const uint32_t s = it % n_stages;
+          const uint32_t ph = (it / n_stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          uint8_t* sa = smem + s * kStageBytes;
           const SegK sg = p.seg[seg];
-          tma_load_4d(sa, sg.src ? &p.tmA1 : &p.tmA0, &full_bar[s], sg.c0 + kin * 64, i1 + sg.off1, i2 + sg.off2,
+          const int c2 = sg.fix2 >= 0 ? sg.fix2 : i2 + sg.off2;
+          const int wk = (sg.wk_first >= 0 && tc.o2 == 0) ? sg.wk_first : sg.wk;
+          tma_load_4d(sa, sg.src ? &p.tmA1 : &p.tmA0, &full_bar[s], sg.c0 + kin * 64, i1 + sg.off1, c2,
                       i3 + sg.off3);
-          tma_load_2d(sa + Cfg::kABytes, &p.tmW, &full_bar[s], kb * 64, n0);
+          tma_load_2d(sa + kABytes, &p.tmW, &full_bar[s], wk + kin * 64, tc.n0);
           if (++kin == sg.num_kb) {
             kin = 0;
             ++seg;
@@ -136,229 +166,368 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN);
       uint32_t it = 0, t = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+        const TileCoord tc = decode_tile<BN>(p, tile);
         const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const uint32_t s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
+          const uint32_t s = it % n_stages;
+          const uint32_t ph = (it / n_stages) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sa = smem_u32(smem + s * kStageBytes);
           const uint64_t adesc = make_sdesc_sw128(sa);
-          const uint64_t bdesc = make_sdesc_sw128(sa + Cfg::kABytes);
+          const uint64_t bdesc = make_sdesc_sw128(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > tc.kb0 || k != 0) ? 1u : 0u);
           tc_commit(&empty_bar[s]);
         }
         tc_commit(&tmem_full_bar[acc]);
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == 2) {
+    // ---------------- epilogue loader (residual panels) ----------------
+    if (lane == 0 && p.n_res > 0) {
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.rows_per_tile) * 64u;
+      uint32_t pc = 0, cnt[2] = {0u, 0u};
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile<BN>(p, tile);
+        const int n_panels = tile_panels<BN, GEGLU>(p, tc.n0);
+        for (int q = 0; q < n_panels; ++q) {
+          const uint32_t g = (pc + q) & 1u;
+          for (int i = 0; i < p.n_res; ++i) {
+            const uint32_t slot = g * kResSlots + cnt[g] % kResSlots;
+            const uint32_t ph = (cnt[g] / kResSlots) & 1u;
+            mbar_wait(&res_empty_bar[slot], ph ^ 1u);
+            mbar_arrive_expect_tx(&res_full_bar[slot], tx_bytes);
+            tma_load_4d(res_ring + slot * kResSlotBytes, i ? &p.tmR1 : &p.tmR0, &res_full_bar[slot],
+                        tc.n0 + q * 32, tc.o1, tc.o2, tc.o3);
+            ++cnt[g];
+          }
+        }
+        pc += n_panels;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
     // ---------------- epilogue ----------------
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // TMEM lane == row inside the tile; also the linear thread id of phase 2
+    const uint32_t g = static_cast<uint32_t>(warp - 4) >> 2;
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;  // TMEM lane == row inside the tile
     const int r1 = r % p.box[0];
     const int r2 = (r / p.box[0]) % p.box[1];
     const int r3 = r / (p.box[0] * p.box[1]);
-    uint8_t* my_stage = staging + r * Cfg::kPitch;
-    uint32_t t = 0;
+    const bool leader = (qd == 0) && (lane == 0);
+    uint8_t* my_out = out_ring + g * 2 * out_slot_bytes;
+    uint32_t pc = 0, ocnt = 0, rcnt = 0, t = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+      const TileCoord tc = decode_tile<BN>(p, tile);
       const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
-      const int n0 = (tile % p.n_tiles_n) * BN;
-      const int mt = tile / p.n_tiles_n;
-      const int o1 = (mt % p.tiles[0]) * p.box[0];
-      const int o2 = ((mt / p.tiles[0]) % p.tiles[1]) * p.box[1];
-      const int o3 = (mt / (p.tiles[0] * p.tiles[1])) * p.box[2];
-      {
-        const bool valid = (r < p.rows_per_tile) && (o1 + r1 < p.out_dims[0]) && (o2 + r2 < p.out_dims[1]) &&
-                           (o3 + r3 < p.out_dims[2]);
-        RowInfo ri;
-        ri.row = -1;
-        ri.out_off = 0;
-        ri.add_off[0] = ri.add_off[1] = 0;
-        if (valid) {
-          const int64_t row =
-              (static_cast<int64_t>(o3 + r3) * p.out_dims[1] + (o2 + r2)) * p.out_dims[0] + (o1 + r1);
-          ri.row = row;
-          ri.out_off = (row / p.row_div) * p.row_s1 + (row % p.row_div) * p.row_s0;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (p.add[i].ptr != nullptr) {
-              const RowAddK& a = p.add[i];
-              const int64_t arow = (row / a.div_outer) * a.mul_outer + (row % a.mod_inner);
-              ri.add_off[i] = arow * a.ld + (((row % a.div_outer) < a.sel_lt) ? a.sel_off : 0);
-            }
-          }
-        }
-        rowinfo[r] = ri;  // published by the first epi_bar_sync below
+      const int n_panels = tile_panels<BN, GEGLU>(p, tc.n0);
+      const int n0_out = GEGLU ? (tc.n0 >> 1) : tc.n0;
+      const float* addp = nullptr;
+      if (p.add_ptr != nullptr) {
+        int a1 = tc.o1 + r1, a2 = tc.o2 + r2, a3 = tc.o3 + r3;
+        const bool valid = (r < p.rows_per_tile) && (a1 < p.out_dims[0]) && (a2 < p.out_dims[1]) &&
+                           (a3 < p.out_dims[2]);
+        const int64_t row = valid ? (static_cast<int64_t>(a3) * p.out_dims[1] + a2) * p.out_dims[0] + a1 : 0;
+        addp = p.add_ptr + (row / p.add_div) * p.add_ld;
       }
+      int q_last = n_panels - 1;
+      if (((pc + q_last) & 1u) != g) --q_last;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-
-#pragma unroll 1
-      for (int pc = 0; pc < Cfg::kOutCols; pc += Cfg::kPanel) {
-        const int pw = (Cfg::kOutCols - pc) < Cfg::kPanel ? (Cfg::kOutCols - pc) : Cfg::kPanel;  // 64 or 32
-        // ---- phase 1: accumulator -> fp32 staging (thread = row)
-#pragma unroll 1
-        for (int c = 0; c < pw; c += 32) {
-          uint32_t v[32];
-          if constexpr (!GEGLU) {
-            tmem_ld_x32(taddr + pc + c, v);
-            tmem_ld_wait();
-          } else {
-            // tile columns [0,64) = value h, [64,128) = gate g; staged value = (h + bh) * gelu(g + bg)
-            uint32_t gv[32];
-            tmem_ld_x32(taddr + pc + c, v);
-            tmem_ld_x32(taddr + 64 + pc + c, gv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              float bh[8], bg[8];
-              const int tc = pc + c + g8 * 8;
-              if (p.bias != nullptr && n0 + 64 + tc + 8 <= p.N) {
-                load8_f32(p.bias + n0 + tc, bh);
-                load8_f32(p.bias + n0 + 64 + tc, bg);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) bh[j] = bg[j] = 0.f;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float h = __uint_as_float(v[g8 * 8 + j]) + bh[j];
-                const float gg = __uint_as_float(gv[g8 * 8 + j]) + bg[j];
-                v[g8 * 8 + j] = __float_as_uint(h * gelu_erf_f(gg));
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(my_stage + (c + j * 4) * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (pc + Cfg::kPanel >= Cfg::kOutCols) {  // whole accumulator read: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        epi_bar_sync();
-        // ---- phase 2: (row, 8-column chunk) per thread, coalesced global access
-        const int cpp_shift = (pw == 64) ? 3 : 2;  // chunks per row in this panel: 8 or 4
-        const int nchunks = 128 << cpp_shift;
-        constexpr int U = 4;
-#pragma unroll 1
-        for (int id0 = r; id0 < nchunks; id0 += 128 * U) {
-          float v[U][8];
-          bool live[U];
-          int64_t ooff[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int id = id0 + u * 128;
-            const int row_l = id >> cpp_shift;
-            const int cc = id & ((1 << cpp_shift) - 1);
-            const RowInfo ri = rowinfo[row_l];
-            const int ocol = (GEGLU ? (n0 >> 1) : n0) + pc + cc * 8;  // output column
-            const int ncol = GEGLU ? (n0 + 64 + pc + cc * 8) : ocol;    // last accumulator column this chunk needs
-            live[u] = (id < nchunks) && (ri.row >= 0) && (ncol < p.N);
-            if (!live[u]) continue;
-            const float4* sp = reinterpret_cast<const float4*>(staging + row_l * Cfg::kPitch + cc * 32);
-            const float4 x0 = sp[0], x1 = sp[1];
-            v[u][0] = x0.x; v[u][1] = x0.y; v[u][2] = x0.z; v[u][3] = x0.w;
-            v[u][4] = x1.x; v[u][5] = x1.y; v[u][6] = x1.z; v[u][7] = x1.w;
-            ooff[u] = ri.out_off + static_cast<int64_t>(ocol / p.col_div) * p.col_s1 + (ocol % p.col_div);
-            if constexpr (!GEGLU) {
-              if (p.bias != nullptr) {
-                float b[8];
-                load8_f32(p.bias + ocol, b);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[u][j] += b[j];
-              }
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                if (p.add[i].ptr != nullptr) {
-                  float b[8];
-                  load8_f32(p.add[i].ptr + ri.add_off[i] + ocol, b);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[u][j] += b[j];
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                if (p.res[i] != nullptr) {
-                  const uint4 w = *reinterpret_cast<const uint4*>(p.res[i] + ri.row * p.res_ld[i] + ocol);
-                  const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z),
-                               f3 = unpack_bf16x2(w.w);
-                  v[u][0] += f0.x; v[u][1] += f0.y; v[u][2] += f1.x; v[u][3] += f1.y;
-                  v[u][4] += f2.x; v[u][5] += f2.y; v[u][6] += f3.x; v[u][7] += f3.y;
-                }
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (!live[u]) continue;
-            if (p.out_fp32) {
-              float* o = reinterpret_cast<float*>(p.out) + ooff[u];
-              *reinterpret_cast<float4*>(o) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
-            } else {
-              uint4 w;
-              w.x = pack_bf16x2(v[u][0], v[u][1]);
-              w.y = pack_bf16x2(v[u][2], v[u][3]);
-              w.z = pack_bf16x2(v[u][4], v[u][5]);
-              w.w = pack_bf16x2(v[u][6], v[u][7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[u]) = w;
-            }
-          }
-        }
-        epi_bar_sync();  // staging (and, after the last panel, rowinfo) may be overwritten
+      if (q_last < 0) {  // no panel of this tile is ours: hand the accumulator back right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       }
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(qd * 32) << 16);
+#pragma unroll 1
+      for (int q = 0; q < n_panels; ++q) {
+        if (((pc + q) & 1u) != g) continue;
+        uint32_t v[32];
+        if constexpr (!GEGLU) {
+          tmem_ld_x32(taddr + q * 32, v);
+          tmem_ld_wait();
+          if (q == q_last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          const int acol = tc.n0 + q * 32;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (acol + j * 4 < p.N) {
+                const float4 b = ldg4(p.bias + acol + j * 4);
+                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+              }
+            }
+          }
+          if (addp != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (acol + j * 4 < p.N) {
+                const float4 b = ldg4(addp + acol + j * 4);
+                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+              }
+            }
+          }
+          for (int i = 0; i < p.n_res; ++i) {
+            const uint32_t slot = g * kResSlots + rcnt % kResSlots;
+            const uint32_t ph = (rcnt / kResSlots) & 1u;
+            mbar_wait(&res_full_bar[slot], ph);
+            const uint8_t* rp = res_ring + slot * kResSlotBytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t lin = static_cast<uint32_t>(r) * 64u + j * 16u;
+              const uint4 w = *reinterpret_cast<const uint4*>(rp + (lin ^ (((lin >> 7) & 3u) << 4)));
+              const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z),
+                           f3 = unpack_bf16x2(w.w);
+              v[8 * j + 0] = __float_as_uint(__uint_as_float(v[8 * j + 0]) + f0.x);
+              v[8 * j + 1] = __float_as_uint(__uint_as_float(v[8 * j + 1]) + f0.y);
+              v[8 * j + 2] = __float_as_uint(__uint_as_float(v[8 * j + 2]) + f1.x);
+              v[8 * j + 3] = __float_as_uint(__uint_as_float(v[8 * j + 3]) + f1.y);
+              v[8 * j + 4] = __float_as_uint(__uint_as_float(v[8 * j + 4]) + f2.x);
+              v[8 * j + 5] = __float_as_uint(__uint_as_float(v[8 * j + 5]) + f2.y);
+              v[8 * j + 6] = __float_as_uint(__uint_as_float(v[8 * j + 6]) + f3.x);
+              v[8 * j + 7] = __float_as_uint(__uint_as_float(v[8 * j + 7]) + f3.y);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&res_empty_bar[slot]);
+            ++rcnt;
+          }
+        } else {
+          // tile columns [0,64) = value h, [64,128) = gate g; output = (h + bh) * gelu(g + bg)
+          uint32_t gv[32];
+          tmem_ld_x32(taddr + q * 32, v);
+          tmem_ld_x32(taddr + 64 + q * 32, gv);
+          tmem_ld_wait();
+          if (q == q_last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          const int acol = tc.n0 + q * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+            if (p.bias != nullptr) {
+              bh = ldg4(p.bias + acol + j * 4);
+              bg = ldg4(p.bias + acol + 64 + j * 4);
+            }
+            v[4 * j + 0] = __float_as_uint((__uint_as_float(v[4 * j + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gv[4 * j + 0]) + bg.x));
+            v[4 * j + 1] = __float_as_uint((__uint_as_float(v[4 * j + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gv[4 * j + 1]) + bg.y));
+            v[4 * j + 2] = __float_as_uint((__uint_as_float(v[4 * j + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gv[4 * j + 2]) + bg.z));
+            v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gv[4 * j + 3]) + bg.w));
+          }
+        }
+        // ---- stage the panel (swizzled exactly as the output tensor map expects) and store it with TMA
+        uint8_t* op = my_out + (ocnt & 1u) * out_slot_bytes;
+        if (leader) bulk_wait_read<1>();  // the store that last used this slot has finished reading it
+        named_bar_sync(1 + g, 128);
+        if (!p.out_fp32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+            w.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+            w.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+            w.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            const uint32_t lin = static_cast<uint32_t>(r) * 64u + j * 16u;
+            *reinterpret_cast<uint4*>(op + (lin ^ (((lin >> 7) & 3u) << 4))) = w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t lin = static_cast<uint32_t>(r) * 128u + j * 16u;
+            *reinterpret_cast<uint4*>(op + (lin ^ (((lin >> 7) & 7u) << 4))) =
+                make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + g, 128);
+        if (leader) {
+          tma_store_5d(&p.tmO, op, n0_out + q * 32, tc.o1, tc.o2, tc.o3, tc.split);
+          bulk_commit();
+        }
+        ++ocnt;
+      }
+      pc += n_panels;
     }
+    if (leader) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Split-K second pass: out = sum_s ws[s] + bias + addend + residuals, 8 columns per thread.
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int S, int64_t M, int N,
+                                                              const float* __restrict__ bias,
+                                                              const float* __restrict__ add_ptr, int64_t add_ld,
+                                                              int add_div, const __nv_bfloat16* res0, int64_t ld0,
+                                                              const __nv_bfloat16* res1, int64_t ld1, void* out,
+                                                              int64_t ldo, int out_fp32) {
+  const int nchunk = N >> 3;
+  const int64_t total = M * nchunk;
+  const int64_t plane = M * static_cast<int64_t>(N);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / nchunk;
+    const int col = static_cast<int>(i % nchunk) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    const float* src = ws + row * N + col;
+    for (int s = 0; s < S; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(src + s * plane);
+      const float4 b = *reinterpret_cast<const float4*>(src + s * plane + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (bias != nullptr) {
+      const float4 a = ldg4(bias + col), b = ldg4(bias + col + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (add_ptr != nullptr) {
+      const float* ap = add_ptr + (row / add_div) * add_ld + col;
+      const float4 a = ldg4(ap), b = ldg4(ap + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const __nv_bfloat16* rp = k ? res1 : res0;
+      if (rp == nullptr) continue;
+      const uint4 w = *reinterpret_cast<const uint4*>(rp + row * (k ? ld1 : ld0) + col);
+      const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z), f3 = unpack_bf16x2(w.w);
+      v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y; v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+    }
+    if (out_fp32) {
+      float* o = reinterpret_cast<float*>(out) + row * ldo + col;
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 w;
+      w.x = pack_bf16x2(v[0], v[1]);
+      w.y = pack_bf16x2(v[2], v[3]);
+      w.z = pack_bf16x2(v[4], v[5]);
+      w.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + row * ldo + col) = w;
+    }
+  }
 }
 
 static int g_num_sms = 0;
 
-template <int BN, bool GEGLU>
-static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, GEGLU>;
-  static bool configured = false;
-  if (!configured) {
-    ASVA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::kSmemBytes));
-    configured = true;
-  }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    ASVA_CUDA_OK(cudaGetDevice(&dev));
-    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  const int grid = kp.total_tiles < g_num_sms ? kp.total_tiles : g_num_sms;
-  gemm_tc_kernel<BN, GEGLU><<<grid, 192, Cfg::kSmemBytes, stream>>>(kp);
-  ASVA_CUDA_OK(cudaGetLastError());
-  return 0;
+struct GemmPlan {
+  int bn, split, stages;
+};
+
+static int stages_for(int bn, int n_res, int out_fp32) {
+  const int stage = 16384 + bn * 128;
+  const int fixed = 1024 /*align*/ + kBarBytes + 4 * (out_fp32 ? 16384 : 8192) +
+                    (n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0);
+  int s = (kSmemLimit - fixed) / stage;
+  return s > kMaxStages ? kMaxStages : s;
+}
+static int smem_for(int bn, int stages, int n_res, int out_fp32) {
+  return 1024 + kBarBytes + 4 * (out_fp32 ? 16384 : 8192) + (n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0) +
+         stages * (16384 + bn * 128);
 }
 
-static int pick_block_n(int N, int64_t m_tiles) {
-  // prefer exact tilings; small grids take narrower tiles to put more CTAs in flight
-  if (N % 128 == 0) {
-    if (m_tiles * (N / 128) < 148 && N % 64 == 0) return 64;
-    return 128;
+// Cost model (cycles) behind the automatic tile-width / split-K choice. Per 64-wide K block a CTA needs
+// max(MMA issue time = 2*BN cycles, operand bytes / its share of the L2->SM bandwidth); a launch takes
+// ceil(tiles / SMs) waves of (K blocks * that + fixed per-tile cost); split-K adds the reduce pass.
+static double plan_cost(int bn, int split, int N, int64_t m_tiles, int num_kb, int64_t M, int sms) {
+  const int n_tiles = (N + bn - 1) / bn;
+  const int kbps = (num_kb + split - 1) / split;
+  const int64_t tiles = m_tiles * n_tiles * split;
+  const int64_t ctas = tiles < sms ? tiles : sms;
+  const int64_t waves = (tiles + sms - 1) / sms;
+  double bw = 6500.0 / static_cast<double>(ctas);  // bytes / cycle / SM
+  if (bw > 100.0) bw = 100.0;
+  const double feed = (16384.0 + bn * 128.0) / bw;
+  const double mma = 2.0 * bn;
+  const double per_kb = feed > mma ? feed : mma;
+  const double epi = 300.0 * ((bn + 31) / 32) / 2.0 + 400.0;  // per tile, two groups in parallel
+  double tile = kbps * per_kb;
+  if (tile < epi) tile = epi;
+  double cost = 2500.0 + waves * (tile + 700.0);
+  if (split > 1) cost += 5000.0 + static_cast<double>(M) * N * 4.0 * (split + 1) / 3000.0;
+  return cost;
+}
+
+static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, int num_kb, int n_res, int sms) {
+  static int env_bn = -1, env_split = -1;
+  if (env_bn < 0) {
+    const char* e = getenv("ASVA_GEMM_BN");
+    env_bn = e ? atoi(e) : 0;
+    e = getenv("ASVA_GEMM_SPLIT");
+    env_split = e ? atoi(e) : 0;
   }
-  if (N % 160 == 0) return 160;
-  if (N % 64 == 0) return 64;
-  if (N <= 64) return 64;
-  return 128;
+  GemmPlan best{128, 1, 2};
+  if (d->geglu) {
+    best.stages = stages_for(128, 0, 0);
+    return best;
+  }
+  const int bns[4] = {64, 128, 160, 256};
+  const int splits[10] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+  const int want_bn = d->block_n ? d->block_n : env_bn;
+  const int want_split = d->split_k ? d->split_k : env_split;
+  const int64_t max_split = (d->ws != nullptr) ? d->ws_bytes / (M * static_cast<int64_t>(d->N) * 4) : 1;
+  double best_cost = 1e300;
+  for (int bi = 0; bi < 4; ++bi) {
+    const int bn = bns[bi];
+    if (want_bn && bn != want_bn) continue;
+    if (bn > 64 && bn >= 2 * ((d->N + 31) / 32) * 32) continue;  // more than half the tile would be padding
+    for (int si = 0; si < 10; ++si) {
+      int sp = splits[si];
+      if (want_split && sp != want_split && !(want_split > max_split && sp == 1)) continue;
+      if (sp > max_split || sp > num_kb) continue;
+      const int kbps = (num_kb + sp - 1) / sp;
+      if ((num_kb + kbps - 1) / kbps != sp) continue;  // would leave an empty split
+      const int nr = sp > 1 ? 0 : n_res;
+      if (stages_for(bn, nr, sp > 1 ? 1 : d->out_fp32) < 2) continue;
+      const double c = plan_cost(bn, sp, d->N, m_tiles, num_kb, M, sms);
+      if (c < best_cost) {
+        best_cost = c;
+        best.bn = bn;
+        best.split = sp;
+      }
+    }
+  }
+  const int nr = best.split > 1 ? 0 : n_res;
+  best.stages = stages_for(best.bn, nr, best.split > 1 ? 1 : d->out_fp32);
+  return best;
+}
+
+template <int BN, bool GEGLU>
+static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    ASVA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSmemLimit));
+    configured = kSmemLimit;
+  }
+  const int grid = kp.total_tiles < g_num_sms ? kp.total_tiles : g_num_sms;
+  gemm_tc_kernel<BN, GEGLU><<<grid, kGemmThreads, smem_bytes, stream>>>(kp);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace asva
@@ -371,13 +540,20 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   ASVA_REQUIRE(d->nseg >= 1 && d->nseg <= ASVA_GEMM_MAX_SEG, "asva_gemm: nseg=%d out of range", d->nseg);
   ASVA_REQUIRE(d->N >= 8 && d->N % 8 == 0, "asva_gemm: N=%d must be a positive multiple of 8", d->N);
   ASVA_REQUIRE(d->K > 0 && d->K % 64 == 0, "asva_gemm: K=%d must be a positive multiple of 64", d->K);
-  ASVA_REQUIRE(d->ldw >= d->K && d->ldw % 8 == 0, "asva_gemm: ldw=%lld invalid", (long long)d->ldw);
-  ASVA_REQUIRE(d->row_div > 0 && d->col_div > 0 && d->col_div % 8 == 0, "asva_gemm: bad output addressing");
+  ASVA_REQUIRE(d->wcols >= 64 && d->ldw >= d->wcols && d->ldw % 8 == 0, "asva_gemm: ldw=%lld / wcols=%d invalid",
+               (long long)d->ldw, d->wcols);
+  ASVA_REQUIRE(d->ldo % (d->out_fp32 ? 4 : 8) == 0 && d->ldo >= (d->geglu ? d->N / 2 : d->N),
+               "asva_gemm: ldo=%lld invalid", (long long)d->ldo);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    ASVA_CUDA_OK(cudaGetDevice(&dev));
+    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
 
   GemmKParams kp;
   memset(&kp, 0, sizeof(kp));
   int rows = 1;
-  int64_t m_tiles = 1;
+  int64_t m_tiles = 1, M = 1;
   for (int i = 0; i < 3; ++i) {
     ASVA_REQUIRE(d->box[i] >= 1 && d->out_dims[i] >= 1 && (d->trav[i] == 1 || d->trav[i] == 2),
                  "asva_gemm: bad box/out_dims/trav at dim %d", i);
@@ -387,11 +563,13 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
     kp.tiles[i] = (d->out_dims[i] + d->box[i] - 1) / d->box[i];
     rows *= d->box[i];
     m_tiles *= kp.tiles[i];
+    M *= d->out_dims[i];
   }
   ASVA_REQUIRE(rows <= 128, "asva_gemm: tile of %d rows exceeds 128", rows);
   ASVA_REQUIRE(m_tiles <= (1 << 24), "asva_gemm: %lld M tiles", (long long)m_tiles);
   kp.rows_per_tile = rows;
   kp.N = d->N;
+  kp.n_out = d->geglu ? d->N / 2 : d->N;
 
   int kb_total = 0;
   bool uses_src1 = false;
@@ -401,13 +579,51 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
     ASVA_REQUIRE(g.c0 >= 0 && g.c0 + 64 * (int64_t)g.num_kb <= d->a_dims[g.src][0],
                  "asva_gemm: segment %d channels [%d, %lld) exceed source extent %lld", s, g.c0,
                  (long long)(g.c0 + 64 * (int64_t)g.num_kb), (long long)d->a_dims[g.src][0]);
-    kp.seg[s] = SegK{g.src, g.c0, g.off[0], g.off[1], g.off[2], g.num_kb};
+    ASVA_REQUIRE(g.wk >= 0 && g.wk % 64 == 0 && g.wk + 64 * g.num_kb <= d->wcols,
+                 "asva_gemm: segment %d weight columns [%d, %d) exceed wcols=%d", s, g.wk, g.wk + 64 * g.num_kb,
+                 d->wcols);
+    ASVA_REQUIRE(g.wk_first < 0 || (g.wk_first % 64 == 0 && g.wk_first + 64 * g.num_kb <= d->wcols),
+                 "asva_gemm: segment %d wk_first=%d invalid", s, g.wk_first);
+    ASVA_REQUIRE((g.wk_first < 0 && g.fix2 < 0) || d->box[1] == 1,
+                 "asva_gemm: segment %d uses wk_first/fix2, which need box[1] == 1", s);
+    kp.seg[s] = SegK{g.src, g.c0, g.off[0], g.off[1], g.off[2], g.num_kb, g.wk, g.wk_first, g.fix2};
     kb_total += g.num_kb;
     uses_src1 |= (g.src == 1);
   }
   ASVA_REQUIRE(kb_total * 64 == d->K, "asva_gemm: segments cover K=%d but desc says K=%d", kb_total * 64, d->K);
   ASVA_REQUIRE(!uses_src1 || d->a[1] != nullptr, "asva_gemm: segment references missing source 1");
   kp.num_kb = kb_total;
+
+  int n_res = 0;
+  const void* res[2] = {nullptr, nullptr};
+  int64_t res_ld[2] = {0, 0};
+  for (int i = 0; i < 2; ++i) {
+    if (d->res[i] == nullptr) continue;
+    ASVA_REQUIRE(d->res_ld[i] % 8 == 0 && d->res_ld[i] >= d->N, "asva_gemm: residual ld must be a multiple of 8");
+    res[n_res] = d->res[i];
+    res_ld[n_res] = d->res_ld[i];
+    ++n_res;
+  }
+  ASVA_REQUIRE(!d->geglu || (n_res == 0 && d->add.ptr == nullptr && !d->out_fp32 && d->N % 128 == 0),
+               "asva_gemm: GEGLU takes bias only, writes bf16 and needs N %% 128 == 0 (N=%d)", d->N);
+  ASVA_REQUIRE(d->add.ptr == nullptr || (d->add.ld % 4 == 0 && d->add.div >= 1),
+               "asva_gemm: rowadd ld must be a multiple of 4 and div >= 1");
+
+  const GemmPlan plan = plan_gemm(d, m_tiles, M, kb_total, n_res, g_num_sms);
+  const int bn = plan.bn;
+  const bool split = plan.split > 1;
+  kp.split_k = plan.split;
+  kp.kb_per_split = (kb_total + plan.split - 1) / plan.split;
+  kp.n_res = split ? 0 : n_res;
+  kp.out_fp32 = split ? 1 : d->out_fp32;
+  kp.n_stages = plan.stages;
+  ASVA_REQUIRE(plan.stages >= 2, "asva_gemm: no shared memory left for a pipeline (block_n=%d)", bn);
+  if (!split) {
+    kp.bias = d->bias;
+    kp.add_ptr = d->add.ptr;
+    kp.add_ld = d->add.ld;
+    kp.add_div = d->add.div > 0 ? d->add.div : 1;
+  }
 
   for (int src = 0; src < 2; ++src) {
     if (d->a[src] == nullptr) continue;
@@ -426,55 +642,64 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
     if (rc != 0) return rc;
   }
   if (d->a[1] == nullptr) kp.tmA1 = kp.tmA0;
-
-  int bn = d->block_n;
-  if (d->geglu) {
-    ASVA_REQUIRE(d->N % 128 == 0, "asva_gemm: GEGLU needs N %% 128 == 0 (N=%d)", d->N);
-    ASVA_REQUIRE(!d->out_fp32, "asva_gemm: GEGLU writes bf16");
-    bn = 128;
-  } else if (bn == 0) {
-    bn = pick_block_n(d->N, m_tiles);
-  }
-  ASVA_REQUIRE(bn == 64 || bn == 128 || bn == 160, "asva_gemm: unsupported block_n=%d", bn);
   {
-    uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+    uint64_t dims[2] = {(uint64_t)d->wcols, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)d->ldw * 2u};
     uint32_t box[2] = {64u, (uint32_t)bn};
     uint32_t el[2] = {1u, 1u};
     int rc = make_tmap_bf16(&kp.tmW, d->w, 2, dims, strides, box, el);
     if (rc != 0) return rc;
   }
-
-  kp.bias = d->bias;
-  for (int i = 0; i < 2; ++i) {
-    kp.add[i].ptr = d->add[i].ptr;
-    kp.add[i].ld = d->add[i].ld;
-    kp.add[i].div_outer = d->add[i].div_outer > 0 ? d->add[i].div_outer : 1;
-    kp.add[i].mul_outer = d->add[i].mul_outer;
-    kp.add[i].mod_inner = d->add[i].mod_inner > 0 ? d->add[i].mod_inner : 1;
-    kp.add[i].sel_lt = d->add[i].sel_lt;
-    kp.add[i].sel_off = d->add[i].sel_off;
-    kp.res[i] = reinterpret_cast<const __nv_bfloat16*>(d->res[i]);
-    kp.res_ld[i] = d->res_ld[i];
-    ASVA_REQUIRE(d->res[i] == nullptr || d->res_ld[i] % 8 == 0, "asva_gemm: residual ld must be a multiple of 8");
-    ASVA_REQUIRE(d->add[i].ptr == nullptr || (d->add[i].ld % 4 == 0 && d->add[i].sel_off % 4 == 0),
-                 "asva_gemm: rowadd ld/sel_off must be multiples of 4");
+  // output (or split-K scratch) and residuals: (cols, d1, d2, d3[, split]) boxes of 32 columns x the row box
+  const uint32_t rbox[5] = {32u, (uint32_t)d->box[0], (uint32_t)d->box[1], (uint32_t)d->box[2], 1u};
+  const uint32_t rel[5] = {1u, 1u, 1u, 1u, 1u};
+  {
+    const bool f32 = kp.out_fp32 != 0;
+    const uint64_t es = f32 ? 4u : 2u;
+    const uint64_t ld = split ? (uint64_t)d->N : (uint64_t)d->ldo;
+    void* base = split ? d->ws : d->out;
+    uint64_t dims[5] = {(uint64_t)kp.n_out, (uint64_t)d->out_dims[0], (uint64_t)d->out_dims[1],
+                        (uint64_t)d->out_dims[2], (uint64_t)plan.split};
+    uint64_t strides[4] = {ld * es, ld * es * dims[1], ld * es * dims[1] * dims[2],
+                           ld * es * dims[1] * dims[2] * dims[3]};
+    int rc = make_tmap(&kp.tmO, base, f32 ? TMAP_F32 : TMAP_BF16, f32 ? TMAP_SW128 : TMAP_SW64, 5, dims, strides,
+                       rbox, rel);
+    if (rc != 0) return rc;
   }
-  kp.out = d->out;
-  kp.row_s1 = d->row_s1;
-  kp.row_s0 = d->row_s0;
-  kp.col_s1 = d->col_s1;
-  kp.row_div = d->row_div;
-  kp.col_div = d->col_div;
-  kp.out_fp32 = d->out_fp32;
+  for (int i = 0; i < kp.n_res; ++i) {
+    uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->out_dims[0], (uint64_t)d->out_dims[1], (uint64_t)d->out_dims[2]};
+    const uint64_t ld = (uint64_t)res_ld[i] * 2u;
+    uint64_t strides[3] = {ld, ld * dims[1], ld * dims[1] * dims[2]};
+    int rc = make_tmap(i == 0 ? &kp.tmR0 : &kp.tmR1, res[i], TMAP_BF16, TMAP_SW64, 4, dims, strides, rbox, rel);
+    if (rc != 0) return rc;
+  }
+  if (kp.n_res < 2) kp.tmR1 = kp.tmR0;
+  if (kp.n_res < 1) kp.tmR0 = kp.tmR1 = kp.tmO;
 
   kp.n_tiles_n = (d->N + bn - 1) / bn;
-  ASVA_REQUIRE(m_tiles * kp.n_tiles_n < (1ll << 31), "asva_gemm: too many tiles");
-  kp.total_tiles = (int)(m_tiles * kp.n_tiles_n);
-  if (d->geglu) return launch_gemm<128, true>(kp, stream);
-  switch (bn) {
-    case 64: return launch_gemm<64, false>(kp, stream);
-    case 128: return launch_gemm<128, false>(kp, stream);
-    default: return launch_gemm<160, false>(kp, stream);
+  ASVA_REQUIRE(m_tiles * kp.n_tiles_n * plan.split < (1ll << 31), "asva_gemm: too many tiles");
+  kp.mn_tiles = (int)(m_tiles * kp.n_tiles_n);
+  kp.total_tiles = kp.mn_tiles * plan.split;
+  const int smem = smem_for(bn, plan.stages, kp.n_res, kp.out_fp32);
+  int rc;
+  if (d->geglu) {
+    rc = launch_gemm<128, true>(kp, smem, stream);
+  } else {
+    switch (bn) {
+      case 64: rc = launch_gemm<64, false>(kp, smem, stream); break;
+      case 128: rc = launch_gemm<128, false>(kp, smem, stream); break;
+      case 160: rc = launch_gemm<160, false>(kp, smem, stream); break;
+      default: rc = launch_gemm<256, false>(kp, smem, stream); break;
+    }
   }
+  if (rc != 0 || !split) return rc;
+  const int64_t chunks = M * (d->N / 8);
+  int64_t blocks = (chunks + 255) / 256;
+  if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
+  splitk_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+      reinterpret_cast<const float*>(d->ws), plan.split, M, d->N, d->bias, d->add.ptr, d->add.ld,
+      d->add.div > 0 ? d->add.div : 1, reinterpret_cast<const __nv_bfloat16*>(res[0]), res_ld[0],
+      reinterpret_cast<const __nv_bfloat16*>(res[1]), res_ld[1], d->out, d->ldo, d->out_fp32);
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
 }

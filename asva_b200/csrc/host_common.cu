@@ -40,6 +40,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return make_tmap(out, base, TMAP_BF16, TMAP_SW128, rank, dims, strides_bytes, box, elem_strides);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int dtype, int swizzle, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(ASVA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0)
@@ -59,9 +64,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
       return fail(ASVA_ERR_INVALID, "TMA stride[%d]=%llu bytes must be a non-zero multiple of 16", i,
                   (unsigned long long)strides_bytes[i]);
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
-                  gbox, gel, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = (dtype == TMAP_F32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = (swizzle == TMAP_SW128)  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle == TMAP_SW64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                         : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, gel,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(ASVA_ERR_CUDA,
                 "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r,

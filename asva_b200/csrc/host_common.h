@@ -19,6 +19,13 @@ int fail(int code, const char* fmt, ...);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 
+// General form: dtype TMAP_BF16 / TMAP_F32, swizzle TMAP_SW_NONE / TMAP_SW64 / TMAP_SW128 (the box's innermost
+// extent in bytes must not exceed the swizzle span).
+enum { TMAP_BF16 = 0, TMAP_F32 = 1 };
+enum { TMAP_SW_NONE = 0, TMAP_SW64 = 1, TMAP_SW128 = 2 };
+int make_tmap(CUtensorMap* out, const void* base, int dtype, int swizzle, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+
 #define ASVA_CUDA_OK(expr)                                                                         \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \

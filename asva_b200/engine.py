@@ -54,8 +54,9 @@ def check_supported(cfg: dict) -> None:
 
 
 class _Conv:
-    """Packed FFInflatedConv3d: spatial weight [Cout, k*k*Cin] (K index = (ky*3+kx)*Cin + c), temporal weights
-    W2 = [Wc | Wp] and the frame-0 term W_head = [Wh ; Wh + Wp]."""
+    """Packed FFInflatedConv3d: spatial weight [Cout, k*k*Cin] (K index = (ky*3+kx)*Cin + c) and the temporal
+    weights W4 = [Wc | Wp | Wh | Wh + Wp] (current / previous / first frame; the last block serves frame 0, whose
+    "previous frame" is itself - see ops.spec_tconv)."""
 
     def __init__(self, sd: SD, p: str, dev, dt=torch.bfloat16):
         w = sd[p + ".weight"].float()
@@ -67,10 +68,8 @@ class _Conv:
         wh, wp, wc = wt[:, :co], wt[:, co:2 * co], wt[:, 2 * co:]
         self.wt_full = wt.to(dev).contiguous()
         self.bt = sd[p + ".conv_temp.bias"].float().to(dev).contiguous()
-        if co % 32 == 0:
-            self.w2 = torch.cat([wc, wp], dim=1).to(dev, dt).contiguous()
-            self.w_head = torch.cat([wh, wh + wp], dim=0).to(dev, dt).contiguous()
-            self.b_head = torch.cat([self.bt, self.bt]).contiguous()
+        if co % 64 == 0:
+            self.w4 = torch.cat([wc, wp, wh, wh + wp], dim=1).to(dev, dt).contiguous()
 
 
 class UNetEngine:
@@ -288,11 +287,8 @@ class UNetEngine:
 
     # ------------------------------------------------------------------------------------------ building blocks
     def _ffconv_tail(self, cv: _Conv, y, out, B, F, N, tproj=None, res1=None):
-        be = self.be
-        head = self.buf("tc_head", (B * N, 2 * cv.cout), torch.float32)
-        be.gemm(ops.spec_tconv_head(y, cv.w_head, cv.b_head, head, B=B, F=F, N=N))
-        be.gemm(ops.spec_tconv(y, cv.w2, out, B=B, F=F, N=N, head_term=head, tproj=tproj,
-                               tproj_ld=self._tproj_total, res1=res1))
+        self.be.gemm(ops.spec_tconv(y, cv.w4, out, B=B, F=F, N=N, bias=cv.bt, tproj=tproj,
+                                    tproj_ld=self._tproj_total, res1=res1))
 
     def _gn_stats(self, x0, C0, x1, C1, n_inst, rows, eps, gamma, beta):
         """-> fp32 [n_inst, C, 2] per-channel (scale, shift) so that GroupNorm(x) = x * scale + shift."""
@@ -341,12 +337,10 @@ class UNetEngine:
     def _attention(self, a: dict, name: str, t, n, B, F, N, kv, G, R, nk, mask=None, mask_rows=1):
         """t <- t + Wo softmax(Q K^T / sqrt(d)) V + bo   with Q = Wq n (head-split epilogue)."""
         be, C, d, dpad, H = self.be, a["C"], a["d"], a["dpad"], self.heads
-        q = self.buf("attn_q", (G, H, R, dpad), zero=True)  # pad columns stay zero: never written
-        sp = ops.spec_linear(n, a[name + ".q"], q)
-        ops.set_headsplit_out(sp, rows_per_group=R, heads=H, d=d, dpad=dpad)
-        be.gemm(sp)
+        q = self.buf("attn_q", (B * F * N, C))
+        be.gemm(ops.spec_linear(n, a[name + ".q"], q))
         o = self.buf("attn_o", (B * F * N, C))
-        be.attention(ops.AttnSpec(q=q, kv=kv, out=o, G=G, heads=H, R=R, Nk=nk, d=d, dpad=dpad, ldkv=2 * C, ldo=C,
+        be.attention(ops.AttnSpec(q=q, kv=kv, out=o, G=G, heads=H, R=R, Nk=nk, d=d, dpad=dpad, ldq=C, ldkv=2 * C, ldo=C,
                                   kv_rows_per_group=nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d), mask=mask,
                                   mask_ld=(mask.shape[1] if mask is not None else 0), mask_rows=mask_rows))
         be.gemm(ops.spec_linear(o, a[name + ".o_w"], t, bias=a[name + ".o_b"], res0=t))

@@ -22,17 +22,16 @@ class Seg:
     c0: int
     off: Tuple[int, int, int]
     num_kb: int
+    wk: int = -1        # first column of W this segment multiplies; -1 = consecutive (filled in by GemmSpec)
+    wk_first: int = -1  # >= 0: column of W used instead by tiles whose d2 origin is 0 (box[1] must be 1)
+    fix2: int = -1      # >= 0: absolute d2 coordinate of the rows read (box[1] must be 1)
 
 
 @dataclass
 class RowAdd:
-    t: torch.Tensor  # fp32; element [arow * ld + col (+ sel_off)]
+    t: torch.Tensor  # fp32; element [(row // div) * ld + col]
     ld: int
-    div_outer: int
-    mul_outer: int
-    mod_inner: int
-    sel_lt: int = 0
-    sel_off: int = 0
+    div: int
 
 
 @dataclass
@@ -54,19 +53,28 @@ class GemmSpec:
     ldw: int
     N: int
     K: int
-    out: torch.Tensor
+    out: torch.Tensor  # [M, ldo] row-major (bf16, or fp32 with out_fp32)
+    ldo: int = 0
+    wcols: int = 0
     bias: Optional[torch.Tensor] = None
-    add: List[Optional[RowAdd]] = field(default_factory=lambda: [None, None])
+    add: Optional[RowAdd] = None
     res: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
     res_ld: List[int] = field(default_factory=lambda: [0, 0])
     geglu: bool = False
     out_fp32: bool = False
-    row_div: int = 1
-    row_s1: int = 0
-    row_s0: int = 0
-    col_div: int = BIG
-    col_s1: int = 0
     block_n: int = 0
+    split_k: int = 0
+
+    def __post_init__(self):
+        k = 0
+        for sg in self.segs:
+            if sg.wk < 0:
+                sg.wk = k
+            k += 64 * sg.num_kb
+        if self.wcols == 0:
+            self.wcols = max([self.K] + [max(sg.wk, sg.wk_first) + 64 * sg.num_kb for sg in self.segs])
+        if self.ldo == 0:
+            self.ldo = self.out.stride(0)
 
     @property
     def M(self) -> int:
@@ -75,7 +83,7 @@ class GemmSpec:
 
 @dataclass
 class AttnSpec:
-    q: torch.Tensor  # bf16 [G, heads, R, dpad]
+    q: torch.Tensor  # bf16 [G*R, ldq] token-major, head h at columns h*d..
     kv: torch.Tensor  # bf16 rows of ldkv
     out: torch.Tensor  # bf16 [G*R, ldo]
     G: int
@@ -84,6 +92,7 @@ class AttnSpec:
     Nk: int
     d: int
     dpad: int
+    ldq: int
     ldkv: int
     ldo: int
     kv_rows_per_group: int
@@ -104,11 +113,6 @@ def pick_box(dims: Sequence[int], limit: int = 128) -> Tuple[int, int, int]:
     b2 = min(dims[1], max(1, limit // b1))
     b3 = min(dims[2], max(1, limit // (b1 * b2)))
     return (b1, b2, b3)
-
-
-def _plain_out(spec: GemmSpec, ldo: int) -> None:
-    spec.row_div, spec.row_s1, spec.row_s0 = 1, ldo, 0
-    spec.col_div, spec.col_s1 = BIG, 0
 
 
 def _rows_view(x: torch.Tensor) -> AView:
@@ -135,7 +139,6 @@ def spec_linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, x2: Opti
                     ldw=w.stride(0), N=N, K=K, out=out, bias=bias, geglu=geglu, out_fp32=out_fp32)
     spec.res = [res0, res1]
     spec.res_ld = [r.stride(0) if r is not None else 0 for r in spec.res]
-    _plain_out(spec, out.stride(0))
     return spec
 
 
@@ -144,11 +147,9 @@ def spec_rows3(x: AView, box_dims: Tuple[int, int, int], w: torch.Tensor, out: t
     """Plain GEMM over a strided 3-level row set (e.g. the frame-0 rows of every clip)."""
     N, K = w.shape
     assert K == x.dims[0]
-    spec = GemmSpec(a=[x, None], box=pick_box(box_dims), trav=(1, 1, 1), out_dims=tuple(box_dims),
+    return GemmSpec(a=[x, None], box=pick_box(box_dims), trav=(1, 1, 1), out_dims=tuple(box_dims),
                     segs=[Seg(0, 0, (0, 0, 0), K // 64)], w=w, ldw=w.stride(0), N=N, K=K, out=out, bias=bias,
                     out_fp32=out_fp32)
-    _plain_out(spec, out.stride(0))
-    return spec
 
 
 def spec_conv3x3(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n_img: int, h: int, wd: int,
@@ -161,47 +162,35 @@ def spec_conv3x3(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n_img: 
     ho, wo = (h + 2 - 3) // stride + 1, (wd + 2 - 3) // stride + 1
     segs = [Seg(0, 0, (kx - 1, ky - 1, 0), Cin // 64) for ky in range(3) for kx in range(3)]
     av = AView(x, (Cin, wd, h, n_img), (Cin, wd * Cin, h * wd * Cin))
-    spec = GemmSpec(a=[av, None], box=pick_box((wo, ho, n_img)), trav=(stride, stride, 1),
+    return GemmSpec(a=[av, None], box=pick_box((wo, ho, n_img)), trav=(stride, stride, 1),
                     out_dims=(wo, ho, n_img), segs=segs, w=w, ldw=w.stride(0), N=N, K=K, out=out, bias=bias,
                     out_fp32=out_fp32)
-    _plain_out(spec, out.stride(0))
-    return spec
 
 
-def spec_tconv(y: torch.Tensor, w2: torch.Tensor, out: torch.Tensor, *, B: int, F: int, N: int,
-               head_term: torch.Tensor, tproj: Optional[torch.Tensor] = None, tproj_ld: int = 0,
+def spec_tconv(y: torch.Tensor, w4: torch.Tensor, out: torch.Tensor, *, B: int, F: int, N: int,
+               bias: Optional[torch.Tensor] = None, tproj: Optional[torch.Tensor] = None, tproj_ld: int = 0,
                res1: Optional[torch.Tensor] = None) -> GemmSpec:
-    """conv_temp main GEMM (utils.py:43-53 restated):  out_f = y_f + Wc y_f + Wp y_{f-1} + H   where the frame-0
-    term H = Wh y_0 + bt (+ Wp y_0 for f = 0, whose "previous frame" is itself) comes from `head_term`
-    (fp32 [B*N, 2C]: columns [0,C) for f >= 1, [C,2C) for f = 0).  y, out: [B*F*N, C]; w2: [C, 2C] = [Wc | Wp].
-    The previous-frame segment reads frame f-1 through a -1 coordinate offset; f = 0 hits TMA zero fill."""
+    """conv_temp as ONE GEMM (utils.py:43-53 restated):
+        out_f = y_f + Wc y_f + Wp y_{max(f-1,0)} + Wh y_0 + bt (+ tproj[b]) (+ res1)
+    y, out: [B*F*N, C]; w4: [C, 4C] = [Wc | Wp | Wh | Wh + Wp].  Every tile holds rows of ONE frame (box (n, 1, b)),
+    so the three K segments are: the tile's own rows, the same rows one frame earlier (coordinate offset -1; frame 0
+    reads TMA zero fill) and the same rows of frame 0 (fix2 = 0), whose weight block is Wh - or Wh + Wp for the
+    tiles of frame 0 itself (wk_first), which puts back the previous-frame term the zero fill dropped."""
     Cc = y.shape[1]
-    assert w2.shape == (Cc, 2 * Cc) and y.stride(0) == Cc
+    assert w4.shape == (Cc, 4 * Cc) and y.stride(0) == Cc
     av = AView(y, (Cc, N, F, B), (Cc, N * Cc, F * N * Cc))
-    segs = [Seg(0, 0, (0, 0, 0), Cc // 64), Seg(0, 0, (0, -1, 0), Cc // 64)]
-    spec = GemmSpec(a=[av, None], box=pick_box((N, F, B)), trav=(1, 1, 1), out_dims=(N, F, B), segs=segs, w=w2,
-                    ldw=w2.stride(0), N=Cc, K=2 * Cc, out=out)
-    spec.add[0] = RowAdd(head_term, 2 * Cc, div_outer=F * N, mul_outer=N, mod_inner=N, sel_lt=N, sel_off=Cc)
+    kb = Cc // 64
+    segs = [Seg(0, 0, (0, 0, 0), kb, wk=0), Seg(0, 0, (0, -1, 0), kb, wk=Cc),
+            Seg(0, 0, (0, 0, 0), kb, wk=2 * Cc, wk_first=3 * Cc, fix2=0)]
+    b1 = min(N, 128)
+    box = (b1, 1, min(B, max(1, 128 // b1)))
+    spec = GemmSpec(a=[av, None], box=box, trav=(1, 1, 1), out_dims=(N, F, B), segs=segs, w=w4,
+                    ldw=w4.stride(0), N=Cc, K=3 * Cc, out=out, bias=bias)
     if tproj is not None:
-        spec.add[1] = RowAdd(tproj, tproj_ld, div_outer=F * N, mul_outer=1, mod_inner=1)
+        spec.add = RowAdd(tproj, tproj_ld, div=F * N)
     spec.res = [y, res1]
     spec.res_ld = [Cc, res1.stride(0) if res1 is not None else 0]
-    _plain_out(spec, out.stride(0))
     return spec
-
-
-def spec_tconv_head(y: torch.Tensor, w_head: torch.Tensor, bias2: torch.Tensor, out: torch.Tensor, *, B: int,
-                    F: int, N: int) -> GemmSpec:
-    """Frame-0 term of conv_temp: out[b*N + n, :] = [Wh ; Wh + Wp] y[b, 0, n] + [bt ; bt]  (fp32 [B*N, 2C])."""
-    Cc = y.shape[1]
-    av = AView(y, (Cc, N, B, 1), (Cc, F * N * Cc, B * F * N * Cc))
-    return spec_rows3(av, (N, B, 1), w_head, out, bias=bias2, out_fp32=True)
-
-
-def set_headsplit_out(spec: GemmSpec, *, rows_per_group: int, heads: int, d: int, dpad: int) -> None:
-    """Route the GEMM output into the attention kernel's Q layout [G][heads][rows_per_group][dpad]."""
-    spec.row_div, spec.row_s1, spec.row_s0 = rows_per_group, heads * rows_per_group * dpad, dpad
-    spec.col_div, spec.col_s1 = d, rows_per_group * dpad
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -216,10 +205,23 @@ class CudaBackend:
 
     name = "cuda"
 
+    SPLITK_WS_BYTES = 96 << 20
+
     def __init__(self) -> None:
         self.lib = _lib.load()
         self.launches = 0
         self._prof = None
+        self._ws = {}
+
+    def splitk_ws(self) -> torch.Tensor:
+        """fp32 scratch for split-K partial tiles, one per device, allocated on first use (before any graph
+        capture: the engine's first eager step touches it)."""
+        dev = torch.cuda.current_device()
+        t = self._ws.get(dev)
+        if t is None:
+            t = torch.empty(self.SPLITK_WS_BYTES // 4, dtype=torch.float32, device=f"cuda:{dev}")
+            self._ws[dev] = t
+        return t
 
     @staticmethod
     def _stream() -> int:
@@ -281,22 +283,20 @@ class CudaBackend:
         d.nseg = len(s.segs)
         for i, sg in enumerate(s.segs):
             d.seg[i].src, d.seg[i].c0, d.seg[i].num_kb = sg.src, sg.c0, sg.num_kb
+            d.seg[i].wk, d.seg[i].wk_first, d.seg[i].fix2 = sg.wk, sg.wk_first, sg.fix2
             for j in range(3):
                 d.seg[i].off[j] = sg.off[j]
         self._chk_dev(s.w, s.out, s.bias)
         assert s.w.dtype == torch.bfloat16
-        d.w, d.ldw, d.N, d.K = s.w.data_ptr(), s.ldw, s.N, s.K
+        d.w, d.ldw, d.N, d.K, d.wcols = s.w.data_ptr(), s.ldw, s.N, s.K, s.wcols
         if s.bias is not None:
             assert s.bias.dtype == torch.float32 and s.bias.numel() >= s.N
         d.bias = _ptr(s.bias)
+        if s.add is not None:
+            self._chk_dev(s.add.t)
+            assert s.add.t.dtype == torch.float32
+            d.add.ptr, d.add.ld, d.add.div = s.add.t.data_ptr(), s.add.ld, s.add.div
         for i in range(2):
-            ra = s.add[i]
-            if ra is not None:
-                self._chk_dev(ra.t)
-                assert ra.t.dtype == torch.float32
-                d.add[i].ptr, d.add[i].ld = ra.t.data_ptr(), ra.ld
-                d.add[i].div_outer, d.add[i].mul_outer, d.add[i].mod_inner = ra.div_outer, ra.mul_outer, ra.mod_inner
-                d.add[i].sel_lt, d.add[i].sel_off = ra.sel_lt, ra.sel_off
             r = s.res[i]
             if r is not None:
                 self._chk_dev(r)
@@ -305,9 +305,10 @@ class CudaBackend:
             d.res_ld[i] = s.res_ld[i]
         d.geglu, d.out_fp32 = int(s.geglu), int(s.out_fp32)
         assert s.out.dtype == (torch.float32 if s.out_fp32 else torch.bfloat16)
-        d.out = s.out.data_ptr()
-        d.row_s1, d.row_s0, d.col_s1 = s.row_s1, s.row_s0, s.col_s1
-        d.row_div, d.col_div, d.block_n = s.row_div, s.col_div, s.block_n
+        d.out, d.ldo = s.out.data_ptr(), s.ldo
+        d.block_n, d.split_k = s.block_n, s.split_k
+        ws = self.splitk_ws()
+        d.ws, d.ws_bytes = ws.data_ptr(), ws.numel() * 4
         with self._timed('gemm'):
             _lib.check(self.lib.asva_gemm(d, self._stream()), "asva_gemm")
         self.launches += 1
@@ -316,7 +317,7 @@ class CudaBackend:
         self._chk_dev(s.q, s.kv, s.out, s.mask)
         d = _lib.AttnDesc()
         d.q, d.kv, d.mask, d.out = s.q.data_ptr(), s.kv.data_ptr(), _ptr(s.mask), s.out.data_ptr()
-        d.ldkv, d.ldo, d.mask_ld = s.ldkv, s.ldo, s.mask_ld
+        d.ldq, d.ldkv, d.ldo, d.mask_ld = s.ldq, s.ldkv, s.ldo, s.mask_ld
         d.G, d.heads, d.R, d.Nk, d.d, d.dpad = s.G, s.heads, s.R, s.Nk, s.d, s.dpad
         d.kv_rows_per_group, d.k_col0, d.v_col0, d.mask_rows = s.kv_rows_per_group, s.k_col0, s.v_col0, s.mask_rows
         d.scale = s.scale

@@ -40,17 +40,21 @@ enum asva_status {
  * Attention projections and FeedForward/GEGLU linears (ff_spatio_audio_temp_transformer_3d.py:199-276).
  * ------------------------------------------------------------------------------------------------------------ */
 typedef struct asva_gemm_seg {
-  int32_t src;    /* 0 -> a[0], 1 -> a[1] */
-  int32_t c0;     /* first channel inside the source */
-  int32_t off[3]; /* input-space coordinate offsets along d1..d3 (may be negative: zero fill) */
-  int32_t num_kb; /* number of 64-wide K blocks in this segment */
+  int32_t src;      /* 0 -> a[0], 1 -> a[1] */
+  int32_t c0;       /* first channel inside the source */
+  int32_t off[3];   /* input-space coordinate offsets along d1..d3 (may be negative: zero fill) */
+  int32_t num_kb;   /* number of 64-wide K blocks in this segment */
+  int32_t wk;       /* first column of W this segment multiplies (multiple of 64) */
+  int32_t wk_first; /* >= 0: column of W used instead of wk by tiles whose d2 origin is 0 (needs box[1] == 1) */
+  int32_t fix2;     /* >= 0: absolute d2 coordinate of the rows read, whatever the tile's d2 position (box[1] == 1) */
+  int32_t reserved;
 } asva_gemm_seg;
 
-typedef struct asva_rowadd { /* fp32 addend broadcast over part of the output-row index */
+typedef struct asva_rowadd { /* fp32 addend  ptr[(row / div) * ld + col]  (one addend row per block of div rows) */
   const float* ptr;          /* NULL = disabled */
   int64_t ld;
-  int32_t div_outer, mul_outer, mod_inner; /* arow = (row / div_outer) * mul_outer + (row % mod_inner) */
-  int32_t sel_lt, sel_off;                 /* if ((row % div_outer) < sel_lt) column += sel_off */
+  int32_t div;
+  int32_t reserved;
 } asva_rowadd;
 
 #define ASVA_GEMM_MAX_SEG 10
@@ -65,24 +69,27 @@ typedef struct asva_gemm_desc {
   int32_t out_dims[3];     /* output-space extents along d1..d3; M = product; row = (o3*D2 + o2)*D1 + o1 */
   int32_t nseg;
   asva_gemm_seg seg[ASVA_GEMM_MAX_SEG];
-  /* W operand: [N, K] row-major bf16 */
+  /* W operand: [N, wcols] row-major bf16 (leading dimension ldw) */
   const void* w;
   int64_t ldw;
   int32_t N;
-  int32_t K; /* = 64 * sum(seg.num_kb) */
-  /* epilogue */
+  int32_t K;     /* contraction length = 64 * sum(seg.num_kb) */
+  int32_t wcols; /* columns of W that exist (>= every seg.wk + 64*num_kb) */
+  int32_t reserved0;
+  /* epilogue: out = acc + bias[col] + add + res[0] + res[1]   (GEGLU: (h + bias_h) * gelu_erf(g + bias_g)) */
   const float* bias; /* [N] fp32 or NULL */
-  asva_rowadd add[2];
-  const void* res[2]; /* bf16 residuals addressed res[i][row * res_ld[i] + col]; NULL = disabled */
+  asva_rowadd add;
+  const void* res[2]; /* bf16 residuals res[i][row * res_ld[i] + col]; NULL = disabled; may alias out */
   int64_t res_ld[2];
   int32_t geglu; /* 1: each 128-column tile holds [64 value | 64 gate] columns; writes N/2 columns */
   int32_t out_fp32;
-  /* output addressing: off = (row/row_div)*row_s1 + (row%row_div)*row_s0 + (col/col_div)*col_s1 + (col%col_div) */
-  void* out;
-  int64_t row_s1, row_s0, col_s1;
-  int32_t row_div, col_div;
-  int32_t block_n; /* 0 = auto; 64 / 128 / 160 */
-  int32_t reserved;
+  void* out; /* [M][ldo] bf16 (or fp32), row-major; written by TMA stores (tails clipped) */
+  int64_t ldo;
+  int32_t block_n; /* 0 = auto; 64 / 128 / 160 / 256 */
+  int32_t split_k; /* 0 = auto, 1 = off, n = split the K loop n ways (fp32 partials in ws, then a reduce+epilogue
+                      kernel); ignored (off) when ws is too small or for GEGLU */
+  void* ws;        /* device scratch for split-K partial sums, or NULL */
+  int64_t ws_bytes;
 } asva_gemm_desc;
 
 int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream);
@@ -92,7 +99,8 @@ int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream);
  * Replaces F.scaled_dot_product_attention in FFAttnProcessor (utils.py:151-153: first-frame spatial attention,
  * all frames of a clip share the keys/values of frame 0) and in diffusers AttnProcessor2_0 for attn_audio /
  * attn2 (ff_spatio_audio_temp_transformer_3d.py:315-341; bool mask, True = attend).
- *   q   : bf16 [G][heads][R][dpad]   head-split, columns >= d are zero (written by asva_gemm's addressing)
+ *   q   : bf16 [G*R][ldq]  token-major projection output, head h at columns h*d .. h*d+d-1 (the kernel's TMA box
+ *         zero-fills the padding up to dpad, so no head-split copy exists)
  *   kv  : bf16 rows of ldkv elements; key j of group g is row g*kv_rows_per_group + j; K at column
  *         k_col0 + head*d, V at column v_col0 + head*d
  *   mask: uint8 [G*R / mask_rows][mask_ld] (1 = attend) or NULL; query row r of group g uses mask row
@@ -104,7 +112,7 @@ typedef struct asva_attn_desc {
   const void* kv;
   const uint8_t* mask;
   void* out;
-  int64_t ldkv, ldo, mask_ld;
+  int64_t ldq, ldkv, ldo, mask_ld;
   int32_t G, heads, R, Nk, d, dpad;
   int32_t kv_rows_per_group, k_col0, v_col0, mask_rows;
   float scale;

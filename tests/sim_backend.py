@@ -26,37 +26,41 @@ class SimBackend:
         self.launches = 0
 
     # ------------------------------------------------------------------ gemm
-    def _gather_a(self, s: GemmSpec) -> torch.Tensor:
+    def _accumulate(self, s: GemmSpec) -> torch.Tensor:
+        """fp32 [M, N] = sum over K segments of A_seg @ W[:, wk : wk + len]^T  (rows of frame 0 use wk_first)."""
         D1, D2, D3 = s.out_dims
         dev = s.out.device
         o1 = torch.arange(D1, device=dev).view(1, 1, D1).expand(D3, D2, D1).reshape(-1)
         o2 = torch.arange(D2, device=dev).view(1, D2, 1).expand(D3, D2, D1).reshape(-1)
         o3 = torch.arange(D3, device=dev).view(D3, 1, 1).expand(D3, D2, D1).reshape(-1)
-        cols = []
+        Wf = torch.as_strided(s.w, (s.N, s.wcols), (s.ldw, 1)).float()
+        acc = torch.zeros(o1.numel(), s.N, dtype=torch.float32, device=dev)
         for sg in s.segs:
             av = s.a[sg.src]
             flat = _flat(av.t)
             c_ext, e1, e2, e3 = av.dims
             i1 = o1 * s.trav[0] + sg.off[0]
-            i2 = o2 * s.trav[1] + sg.off[1]
+            i2 = o2 * s.trav[1] + sg.off[1] if sg.fix2 < 0 else torch.full_like(o2, sg.fix2)
             i3 = o3 * s.trav[2] + sg.off[2]
             ok = (i1 >= 0) & (i1 < e1) & (i2 >= 0) & (i2 < e2) & (i3 >= 0) & (i3 < e3)
             base = i1.clamp(0, e1 - 1) * av.strides[0] + i2.clamp(0, e2 - 1) * av.strides[1] + \
                 i3.clamp(0, e3 - 1) * av.strides[2]
-            kk = torch.arange(sg.num_kb * 64, device=dev) + sg.c0
+            n = sg.num_kb * 64
+            kk = torch.arange(n, device=dev) + sg.c0
             okc = kk < c_ext
             idx = base.view(-1, 1) + kk.clamp(max=c_ext - 1).view(1, -1)
-            vals = flat[idx].float()
-            vals = vals * (ok.view(-1, 1) & okc.view(1, -1)).float()
-            cols.append(vals)
-        return torch.cat(cols, dim=1)
+            vals = flat[idx].float() * (ok.view(-1, 1) & okc.view(1, -1)).float()
+            part = vals @ Wf[:, sg.wk: sg.wk + n].t()
+            if sg.wk_first >= 0:
+                alt = vals @ Wf[:, sg.wk_first: sg.wk_first + n].t()
+                part = torch.where((o2 == 0).view(-1, 1), alt, part)
+            acc = acc + part
+        return acc
 
     def gemm(self, s: GemmSpec) -> None:
         self.launches += 1
-        A = self._gather_a(s)  # [M, K] fp32 (bf16 values)
-        M = A.shape[0]
-        W = torch.as_strided(s.w, (s.N, s.K), (s.ldw, 1)).float()
-        acc = A @ W.t()
+        acc = self._accumulate(s)
+        M = acc.shape[0]
         dev = acc.device
         rows = torch.arange(M, device=dev)
         if s.geglu:
@@ -72,13 +76,9 @@ class SimBackend:
             if s.bias is not None:
                 val = val + s.bias[: s.N].float().view(1, -1)
             colsN = torch.arange(s.N, device=dev)
-            for ra in s.add:
-                if ra is None:
-                    continue
-                arow = (rows // ra.div_outer) * ra.mul_outer + (rows % ra.mod_inner)
-                sel = ((rows % ra.div_outer) < ra.sel_lt).long() * ra.sel_off
-                idx = (arow * ra.ld + sel).view(-1, 1) + colsN.view(1, -1)
-                val = val + _flat(ra.t)[idx].float()
+            if s.add is not None:
+                idx = ((rows // s.add.div) * s.add.ld).view(-1, 1) + colsN.view(1, -1)
+                val = val + _flat(s.add.t)[idx].float()
             for r, ld in zip(s.res, s.res_ld):
                 if r is None:
                     continue
@@ -86,8 +86,7 @@ class SimBackend:
                 val = val + _flat(r)[idx].float()
             n_out = s.N
         cols = torch.arange(n_out, device=dev)
-        off = ((rows // s.row_div) * s.row_s1 + (rows % s.row_div) * s.row_s0).view(-1, 1) + \
-            ((cols // s.col_div) * s.col_s1 + (cols % s.col_div)).view(1, -1)
+        off = (rows * s.ldo).view(-1, 1) + cols.view(1, -1)
         outf = _flat(s.out)
         outf[off.reshape(-1)] = val.reshape(-1).to(s.out.dtype)
 
@@ -95,7 +94,7 @@ class SimBackend:
     def attention(self, s: AttnSpec) -> None:
         self.launches += 1
         G, H, R, d = s.G, s.heads, s.R, s.d
-        q = s.q.view(G, H, R, s.dpad)[..., :d].float()
+        q = torch.as_strided(_flat(s.q), (G, R, H, d), (R * s.ldq, s.ldq, d, 1)).permute(0, 2, 1, 3).float()
         kvf = _flat(s.kv)
         kv = torch.as_strided(kvf, (G, s.Nk, s.ldkv), (s.kv_rows_per_group * s.ldkv, s.ldkv, 1))
         k = kv[:, :, s.k_col0: s.k_col0 + H * d].reshape(G, s.Nk, H, d).permute(0, 2, 1, 3).float()

@@ -109,7 +109,8 @@ def test_gemm_conv3x3(cuda_backend, n_img, h, w, Cin, Cout, stride):
     _report("conv3x3 vs F.conv2d", got, y, 6e-3)
 
 
-@pytest.mark.parametrize("B,F,N,C", [(2, 12, 64, 320), (1, 8, 16, 1280), (2, 5, 100, 640)])
+@pytest.mark.parametrize("B,F,N,C", [(2, 12, 64, 320), (1, 8, 16, 1280), (2, 5, 100, 640), (2, 3, 256, 320),
+                                     (3, 4, 16, 640)])
 def test_gemm_tconv(cuda_backend, B, F, N, C):
     y = _rand((B * F * N, C), 16)
     w3 = _rand((C, 3 * C), 17, 0.02)
@@ -117,18 +118,9 @@ def test_gemm_tconv(cuda_backend, B, F, N, C):
     tproj = _rand((B, C), 19, dtype=torch.float32)
     res1 = _rand((B * F * N, C), 20)
     wh, wp, wc = w3[:, :C], w3[:, C:2 * C], w3[:, 2 * C:]
-    w_head = torch.cat([wh, (wh.float() + wp.float()).to(torch.bfloat16)], dim=0).contiguous()
-    bias2 = torch.cat([bt, bt]).contiguous()
-    w2 = torch.cat([wc, wp], dim=1).contiguous()
-    head_ref = torch.zeros(B * N, 2 * C, dtype=torch.float32, device=DEV)
-    head_cu = torch.zeros_like(head_ref)
-    sim = SimBackend()
-    sim.gemm(ops.spec_tconv_head(y, w_head, bias2, head_ref, B=B, F=F, N=N))
-    cuda_backend.gemm(ops.spec_tconv_head(y, w_head, bias2, head_cu, B=B, F=F, N=N))
-    torch.cuda.synchronize()
-    _report("tconv head", head_cu, head_ref, 1e-5)
-    spec = ops.spec_tconv(y, w2, torch.empty(B * F * N, C, dtype=torch.bfloat16, device=DEV), B=B, F=F, N=N,
-                          head_term=head_ref, tproj=tproj, tproj_ld=C, res1=res1)
+    w4 = torch.cat([wc, wp, wh, (wh.float() + wp.float()).to(torch.bfloat16)], dim=1).contiguous()
+    spec = ops.spec_tconv(y, w4, torch.empty(B * F * N, C, dtype=torch.bfloat16, device=DEV), B=B, F=F, N=N,
+                          bias=bt, tproj=tproj, tproj_ld=C, res1=res1)
     got, ref = _run_gemm_pair(cuda_backend, spec, (B * F * N, C), torch.bfloat16)
     _report(f"tconv {B}x{F}x{N}x{C}", got, ref, 4e-3)
     # direct restatement of FFInflatedConv3d's temporal part (utils.py:43-53) + tproj + extra residual
@@ -139,25 +131,62 @@ def test_gemm_tconv(cuda_backend, B, F, N, C):
     _report("tconv vs restatement", got, want.reshape(B * F * N, C), 8e-3)
 
 
-@pytest.mark.parametrize("d,dpad", [(40, 64), (80, 128), (160, 192)])
-def test_gemm_headsplit_out(cuda_backend, d, dpad):
-    G, R, heads = 2, 192, 8
-    C = heads * d
-    x = _rand((G * R, C), 21)
-    w = _rand((C, C), 22, 1.0 / math.sqrt(C))
-    spec = ops.spec_linear(x, w, torch.empty(G, heads, R, dpad, dtype=torch.bfloat16, device=DEV))
-    ops.set_headsplit_out(spec, rows_per_group=R, heads=heads, d=d, dpad=dpad)
-    got, ref = _run_gemm_pair(cuda_backend, spec, (G, heads, R, dpad), torch.bfloat16)
-    _report("headsplit", got.view(-1, dpad), ref.view(-1, dpad), 4e-3)
-    assert (got[..., d:] == 0).all()
+@pytest.mark.parametrize("M,K,N,split,bn", [(384, 11520, 1280, 5, 128), (1536, 5760, 1280, 2, 128), (384, 2560, 1280, 4, 64),
+                                            (200, 1280, 640, 3, 0), (130, 640, 320, 2, 160), (384, 2304, 1280, 0, 0)])
+def test_gemm_split_k(cuda_backend, M, K, N, split, bn):
+    x = _rand((M, K), 51)
+    w = _rand((N, K), 52, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 53, dtype=torch.float32)
+    res = _rand((M, N), 54)
+    spec = ops.spec_linear(x, w, torch.empty(M, N, dtype=torch.bfloat16, device=DEV), bias=bias, res0=res)
+    spec.block_n, spec.split_k = bn, split
+    got, ref = _run_gemm_pair(cuda_backend, spec, (M, N), torch.bfloat16)
+    _report(f"split-k {M}x{K}x{N} /{split}", got, ref, 4e-3)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 160, 256])
+def test_gemm_block_n_and_inplace_residual(cuda_backend, bn):
+    # every tile width, N not a multiple of it, two residuals one of which aliases the output (t = t + ...)
+    M, K, N = 1000, 640, 960
+    x = _rand((M, K), 55)
+    w = _rand((N, K), 56, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 57, dtype=torch.float32)
+    t0 = _rand((M, N), 58)
+    r1 = _rand((M, N), 59)
+    t_ref, t_cu = t0.clone(), t0.clone()
+    s_ref = ops.spec_linear(x, w, t_ref, bias=bias, res0=t_ref, res1=r1)
+    s_cu = ops.spec_linear(x, w, t_cu, bias=bias, res0=t_cu, res1=r1)
+    s_cu.block_n, s_cu.split_k = bn, 1
+    SimBackend().gemm(s_ref)
+    cuda_backend.gemm(s_cu)
+    torch.cuda.synchronize()
+    _report(f"in-place residual bn={bn}", t_cu, t_ref, 4e-3)
+
+
+def test_gemm_strided_out_and_narrow(cuda_backend):
+    # output written into a column slice of a wider buffer; N = 8 (conv_out-like) in fp32
+    M, K = 300, 320
+    x = _rand((M, K), 60)
+    w = _rand((320, K), 61, 1.0 / math.sqrt(K))
+    wide_ref = torch.zeros(M, 1024, dtype=torch.bfloat16, device=DEV)
+    wide_cu = torch.zeros_like(wide_ref)
+    SimBackend().gemm(ops.spec_linear(x, w, wide_ref[:, 320:640]))
+    cuda_backend.gemm(ops.spec_linear(x, w, wide_cu[:, 320:640]))
+    torch.cuda.synchronize()
+    _report("strided out", wide_cu, wide_ref, 4e-3)
+    assert (wide_cu[:, :320] == 0).all() and (wide_cu[:, 640:] == 0).all()
+    w8 = _rand((8, K), 62, 1.0 / math.sqrt(K))
+    b8 = _rand((8,), 63, dtype=torch.float32)
+    spec = ops.spec_linear(x, w8, torch.empty(M, 8, dtype=torch.float32, device=DEV), bias=b8, out_fp32=True)
+    got, ref = _run_gemm_pair(cuda_backend, spec, (M, 8), torch.float32)
+    _report("narrow fp32", got, ref, 1e-5)
 
 
 # ------------------------------------------------------------------------------------------------ attention
 def _attn_case(be, G, heads, R, Nk, d, masked, seed):
     dpad = ((d + 63) // 64) * 64
     C = heads * d
-    q = torch.zeros(G, heads, R, dpad, dtype=torch.bfloat16, device=DEV)
-    q[..., :d] = _rand((G, heads, R, d), seed)
+    q = _rand((G * R, C), seed)
     kv = _rand((G * Nk, 2 * C), seed + 1)
     mask = None
     mask_rows = 1
@@ -172,7 +201,7 @@ def _attn_case(be, G, heads, R, Nk, d, masked, seed):
             mask[i, a:a + 5] = 1
     out_ref = torch.zeros(G * R, C, dtype=torch.bfloat16, device=DEV)
     out_cu = torch.zeros_like(out_ref)
-    spec = ops.AttnSpec(q=q, kv=kv, out=out_ref, G=G, heads=heads, R=R, Nk=Nk, d=d, dpad=dpad, ldkv=2 * C, ldo=C,
+    spec = ops.AttnSpec(q=q, kv=kv, out=out_ref, G=G, heads=heads, R=R, Nk=Nk, d=d, dpad=dpad, ldq=C, ldkv=2 * C, ldo=C,
                         kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d), mask=mask,
                         mask_ld=Nk, mask_rows=mask_rows)
     SimBackend().attention(spec)
@@ -192,13 +221,12 @@ def test_attention_large_scores(cuda_backend):
     # online-softmax rescale path: later key tiles carry the maxima
     G, heads, R, Nk, d = 1, 2, 128, 512, 40
     dpad, C = 64, heads * d
-    q = torch.zeros(G, heads, R, dpad, dtype=torch.bfloat16, device=DEV)
-    q[..., :d] = _rand((G, heads, R, d), 40, 2.0)
+    q = _rand((G * R, C), 40, 2.0)
     kv = _rand((G * Nk, 2 * C), 41)
     kv[:, :C] *= torch.linspace(0.2, 3.0, Nk, device=DEV).view(-1, 1).to(torch.bfloat16)
     out_ref = torch.zeros(G * R, C, dtype=torch.bfloat16, device=DEV)
     out_cu = torch.zeros_like(out_ref)
-    spec = ops.AttnSpec(q=q, kv=kv, out=out_ref, G=G, heads=heads, R=R, Nk=Nk, d=d, dpad=dpad, ldkv=2 * C, ldo=C,
+    spec = ops.AttnSpec(q=q, kv=kv, out=out_ref, G=G, heads=heads, R=R, Nk=Nk, d=d, dpad=dpad, ldq=C, ldkv=2 * C, ldo=C,
                         kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d))
     SimBackend().attention(spec)
     cuda_backend.attention(dataclasses.replace(spec, out=out_cu))
