@@ -40,7 +40,7 @@ class GemmDesc(C.Structure):
         ("N", C.c_int32),
         ("K", C.c_int32),
         ("wcols", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("cta_group", C.c_int32),
         ("bias", C.c_void_p),
         ("add", RowAdd),
         ("res", C.c_void_p * 2),

@@ -2,10 +2,14 @@
 //
 // Persistent kernel, one CTA per SM walking 128 x BN output tiles round-robin; every global access is a TMA
 // transfer, so no warp ever waits on a global load. Warp roles (384 threads):
-//   warp 0       TMA producer: per 64-wide K block one 4-D box load of A (table driven: implicit-GEMM conv taps,
-//                temporal taps, concat sources) and one 2-D box load of W into a 128B-swizzled smem ring
-//   warp 1       TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per K block); the accumulator is double
-//                buffered in TMEM (2 x BN columns), so tile t+1's main loop runs under tile t's epilogue
+//   warps 0, 3   TMA producers (one thread each). The smem ring holds stages of TWO 64-wide K blocks; producer j fills
+//                block j of every stage: one 4-D box load of A (table driven: implicit-GEMM conv taps, temporal
+//                taps, concat sources) and one 2-D box load of W, 128B-swizzled. Two threads and two K blocks per
+//                barrier round trip because a single thread's wait -> arm -> issue chain costs ~520 cycles per K
+//                block (measured, tools/ubench) - more than the MMA time of a 128 x 160 x 64 block (320 cycles)
+//   warp 1       TMEM allocator + single-thread tcgen05.mma issuer (8 x K=16 per stage, one barrier wait and one
+//                commit per stage, the next stage's barrier probed before the MMAs are issued); the accumulator is
+//                double buffered in TMEM (2 x BN columns), so tile t+1's main loop runs under tile t's epilogue
 //   warp 2       epilogue loader: streams the residual operands of each 32-column output panel through a second
 //                TMA ring (64B-swizzled [128 rows][32 bf16] slots), ahead of the epilogue warps
 //   warps 4..11  epilogue, two groups of 4 warps (warp % 4 = TMEM lane quadrant, thread = output row); the groups
@@ -22,7 +26,7 @@
 namespace asva {
 
 constexpr int kMaxStages = 8;
-constexpr int kResSlots = 3;          // residual-panel slots per epilogue group
+constexpr int kResSlots = 2;          // residual-panel slots per epilogue group
 constexpr int kResSlotBytes = 8192;   // 128 rows x 32 bf16
 constexpr int kGemmThreads = 384;
 constexpr int kSmemLimit = 232448;    // 227 KB opt-in maximum per CTA
@@ -37,7 +41,7 @@ struct GemmKParams {
   SegK seg[ASVA_GEMM_MAX_SEG];
   int32_t box[3], trav[3], out_dims[3], tiles[3];
   int32_t rows_per_tile, N, n_out, num_kb, n_tiles_n, mn_tiles, total_tiles, split_k, kb_per_split;
-  int32_t n_stages, n_res, out_fp32;
+  int32_t n_stages, n_res, out_fp32, dbg;  // dbg (ASVA_GEMM_DBG): 1 = skip TMA loads, 2 = skip MMAs (timing only)
   const float* bias;
   const float* add_ptr;
   int64_t add_ld;
@@ -48,13 +52,15 @@ struct TileCoord {
   int n0, o1, o2, o3, split, kb0, kb1;
 };
 
-template <int BN>
-__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
+// CG = 1: `tile` indexes (split, m tile, n tile). CG = 2 (CTA pair): it indexes (split, PAIR of adjacent m tiles,
+// n tile) and the CTA of rank r takes m tile 2*pair + r (an m tile past the end reads zero fill / stores nothing).
+template <int BN, int CG>
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int rank) {
   TileCoord t;
   t.split = tile / p.mn_tiles;
   const int rem = tile - t.split * p.mn_tiles;
   const int nt = rem % p.n_tiles_n;
-  const int mt = rem / p.n_tiles_n;
+  const int mt = (rem / p.n_tiles_n) * CG + rank;
   t.n0 = nt * BN;
   t.o1 = (mt % p.tiles[0]) * p.box[0];
   t.o2 = ((mt / p.tiles[0]) % p.tiles[1]) * p.box[1];
@@ -81,16 +87,17 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
   constexpr int kABytes = 128 * 128;
-  constexpr int kBBytes = BN * 128;
-  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kBBytes = (BN / CG) * 128;  // a CTA of a pair holds half of the W tile's rows
+  constexpr int kStageBytes = kABytes + kBBytes;   // one 64-wide K block
+  constexpr int kSuperBytes = 2 * kStageBytes;     // a ring stage = two K blocks
   constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_stages = p.n_stages;
-  uint8_t* res_ring = smem + n_stages * kStageBytes;
+  uint8_t* res_ring = smem + n_stages * kSuperBytes;
   uint8_t* out_ring = res_ring + (p.n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0);
   const int out_slot_bytes = p.out_fp32 ? 16384 : 8192;
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_ring + 4 * out_slot_bytes);
@@ -104,15 +111,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);  // one arrival per producer thread (of the pair's even CTA)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 8);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[a], 8 * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int s = 0; s < 2 * kResSlots; ++s) {
       mbar_init(&res_full_bar[s], 1);
@@ -124,72 +133,152 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     tma_prefetch_desc(&p.tmO);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ---------------- TMA producer (A, W) ----------------
-    if (lane == 0) {
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.rows_per_tile) * 128u + kBBytes;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile<BN>(p, tile);
+  // The producer and MMA loops run in one thread each and are paced by their own instruction and mbarrier latency,
+  // so they are written for a minimal dependent-instruction count: ring position kept as (stage, phase) counters,
+  // shared addresses and descriptors advanced by adds, segment parameters reloaded only when a segment ends, and the
+  // NEXT stage's barrier probed (non-blocking test_wait) before the current stage's work is issued.
+  const uint32_t smem_a0 = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  if (warp == 0 || warp == 3) {
+    // ---------------- TMA producers (A, W): warp j loads K block j of every stage ----------------
+    // (all 32 lanes run the loop with identical values; `el` predicates the TMA / arrive instructions on one lane)
+    {
+      const uint32_t el = elect_one();
+      const int j = (warp == 3) ? 1 : 0;
+      const uint32_t tx_bytes = (static_cast<uint32_t>(p.rows_per_tile) * 128u + kBBytes) * CG;
+      const uint32_t full0_l = (CG == 2) ? (full0 & kPeerBitMask) : full0;  // pair: the even CTA's barriers
+      const uint32_t el_arm = (rank == 0) ? el : 0u;  // only the even CTA's producers arrive on its barriers
+      const uint32_t n_st = static_cast<uint32_t>(n_stages);
+      uint32_t s = 0, ph = 1;  // ph = parity to wait for on the empty barrier
+      bool ready = true;       // fresh barriers: the "previous phase" of every empty barrier counts as complete
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+        const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
         const int i1 = tc.o1 * p.trav[0], i2 = tc.o2 * p.trav[1], i3 = tc.o3 * p.trav[2];
-        int seg = 0, kin = tc.kb0;
-        while (kin >= p.seg[seg].num_kb) {
-          kin -= p.seg[seg].num_kb;
-          ++seg;
-        }
-        for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
-          const uint32_t s = it % n_stages;
-          const uint32_t ph = (it / n_stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-          uint8_t* sa = smem + s * kStageBytes;
-          const SegK sg = p.seg[seg];
-          const int c2 = sg.fix2 >= 0 ? sg.fix2 : i2 + sg.off2;
-          const int wk = (sg.wk_first >= 0 && tc.o2 == 0) ? sg.wk_first : sg.wk;
-          tma_load_4d(sa, sg.src ? &p.tmA1 : &p.tmA0, &full_bar[s], sg.c0 + kin * 64, i1 + sg.off1, c2,
-                      i3 + sg.off3);
-          tma_load_2d(sa + kABytes, &p.tmW, &full_bar[s], wk + kin * 64, tc.n0);
-          if (++kin == sg.num_kb) {
-            kin = 0;
-            ++seg;
+        const int wn0 = tc.n0 + rank * (BN / CG);
+        const bool first2 = (tc.o2 == 0);
+        int kb = tc.kb0 + j, seg = 0, kin = kb;
+        SegK sg = p.seg[0];
+        const CUtensorMap* tmA = &p.tmA0;
+        int c1 = 0, c2 = 0, c3 = 0, wbase = 0;
+        auto derive = [&]() {
+          tmA = sg.src ? &p.tmA1 : &p.tmA0;
+          c1 = i1 + sg.off1;
+          c3 = i3 + sg.off3;
+          c2 = sg.fix2 >= 0 ? sg.fix2 : i2 + sg.off2;
+          wbase = (sg.wk_first >= 0 && first2) ? sg.wk_first : sg.wk;
+        };
+        if (kb < tc.kb1) {
+          while (kin >= sg.num_kb) {
+            kin -= sg.num_kb;
+            sg = p.seg[++seg];
           }
+          derive();
+        }
+        for (int i = (tc.kb1 - tc.kb0 + 1) >> 1; i > 0; --i) {
+          if (!ready) mbar_wait_a(empty0 + 8u * s, ph);
+          uint32_t s2 = s + 1, ph2 = ph;
+          if (s2 == n_st) {
+            s2 = 0;
+            ph2 ^= 1u;
+          }
+          ready = mbar_test_wait_a(empty0 + 8u * s2, ph2);
+          const uint32_t sa = smem_a0 + s * kSuperBytes + j * kStageBytes;
+          const uint32_t fb = full0_l + 8u * s;
+          if (kb < tc.kb1 && !(p.dbg & 1)) {
+            const int ccol = sg.c0 + kin * 64, wcol = wbase + kin * 64;
+            // pair: both CTAs load their half; all bytes are credited to the even CTA's barrier, armed by its producers
+            mbar_arrive_expect_tx_p(el_arm, fb, tx_bytes);
+            if constexpr (CG == 2) {
+              tma_load_4d_pair_p(el, sa, tmA, fb, ccol, c1, c2, c3);
+              tma_load_2d_pair_p(el, sa + kABytes, &p.tmW, fb, wcol, wn0);
+            } else {
+              tma_load_4d_p(el, sa, tmA, fb, ccol, c1, c2, c3);
+              tma_load_2d_p(el, sa + kABytes, &p.tmW, fb, wcol, wn0);
+            }
+          } else {
+            mbar_arrive_p(el_arm, fb);  // odd K-block count: the last stage of the tile has no second block
+          }
+          kb += 2;
+          kin += 2;
+          if (kb < tc.kb1 && kin >= sg.num_kb) {
+            do {
+              kin -= sg.num_kb;
+              sg = p.seg[++seg];
+            } while (kin >= sg.num_kb);
+            derive();
+          }
+          s = s2;
+          ph = ph2;
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
-      uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-        const TileCoord tc = decode_tile<BN>(p, tile);
+    // ---------------- MMA issuer (warp-uniform loop, instructions predicated on one elected lane) ----------------
+    if (rank == 0) {
+      const uint32_t el = elect_one();
+      constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN);
+      // smem descriptor (K-major, 128B swizzle): low word = (addr >> 4) | LBO(1) << 16, high word constant
+      constexpr uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t a_lo0 = ((smem_a0 & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t n_st = static_cast<uint32_t>(n_stages);
+      const uint32_t tfull0 = smem_u32(tmem_full_bar);
+      // a value the compiler can prove warp-uniform (shared-memory loads are not), so the MMAs take it straight from
+      // a uniform register instead of an elect-and-broadcast loop per instruction
+      const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem_base);
+      uint32_t s = 0, ph = 0, t = 0;
+      bool ready = false;
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
+        const TileCoord tc = decode_tile<BN, CG>(p, tile, 0);
         const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
-          const uint32_t s = it % n_stages;
-          const uint32_t ph = (it / n_stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
+        const uint32_t tmem_d = tmem_u + acc * BN;
+        uint32_t accumulate = 0;
+        for (int n = tc.kb1 - tc.kb0; n > 0; n -= 2) {
+          if (!ready) mbar_wait_a(full0 + 8u * s, ph);
+          uint32_t s2 = s + 1, ph2 = ph;
+          if (s2 == n_st) {
+            s2 = 0;
+            ph2 ^= 1u;
+          }
+          ready = mbar_test_wait_a(full0 + 8u * s2, ph2);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * kStageBytes);
-          const uint64_t adesc = make_sdesc_sw128(sa);
-          const uint64_t bdesc = make_sdesc_sw128(sa + kABytes);
+          const uint32_t a_lo = a_lo0 + s * (kSuperBytes >> 4);
+          const uint32_t el_mma = (p.dbg & 2) ? 0u : el;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > tc.kb0 || k != 0) ? 1u : 0u);
-          tc_commit(&empty_bar[s]);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t el_h = (h == 1 && n < 2) ? 0u : el_mma;
+            const uint64_t adesc = desc_hi | (a_lo + h * (kStageBytes >> 4));
+            const uint64_t bdesc = desc_hi | (a_lo + h * (kStageBytes >> 4) + (kABytes >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t accf = (h == 0 && k == 0) ? accumulate : 1u;
+              if constexpr (CG == 2)
+                umma_bf16_ss_pair_p(el_h, tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+              else
+                umma_bf16_ss_p(el_h, tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+            }
+          }
+          accumulate = 1u;
+          if constexpr (CG == 2) tc_commit_pair_p(el, empty0 + 8u * s, 3); else tc_commit_p(el, empty0 + 8u * s);
+          s = s2;
+          ph = ph2;
         }
-        tc_commit(&tmem_full_bar[acc]);
+        if constexpr (CG == 2) tc_commit_pair_p(el, tfull0 + 8u * acc, 3); else tc_commit_p(el, tfull0 + 8u * acc);
       }
     }
     __syncwarp();
@@ -198,8 +287,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0 && p.n_res > 0) {
       const uint32_t tx_bytes = static_cast<uint32_t>(p.rows_per_tile) * 64u;
       uint32_t pc = 0, cnt[2] = {0u, 0u};
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile<BN>(p, tile);
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+        const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
         const int n_panels = tile_panels<BN, GEGLU>(p, tc.n0);
         for (int q = 0; q < n_panels; ++q) {
           const uint32_t g = (pc + q) & 1u;
@@ -226,10 +315,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int r2 = (r / p.box[0]) % p.box[1];
     const int r3 = r / (p.box[0] * p.box[1]);
     const bool leader = (qd == 0) && (lane == 0);
+    auto release_acc = [](uint64_t* bar) {  // the accumulator-free barrier lives in the pair's even CTA
+      if constexpr (CG == 2) mbar_arrive_pair_leader(bar); else mbar_arrive(bar);
+    };
     uint8_t* my_out = out_ring + g * 2 * out_slot_bytes;
     uint32_t pc = 0, ocnt = 0, rcnt = 0, t = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-      const TileCoord tc = decode_tile<BN>(p, tile);
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
+      const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
       const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
       const int n_panels = tile_panels<BN, GEGLU>(p, tc.n0);
       const int n0_out = GEGLU ? (tc.n0 >> 1) : tc.n0;
@@ -248,7 +340,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if (q_last < 0) {  // no panel of this tile is ours: hand the accumulator back right away
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (lane == 0) release_acc(&tmem_empty_bar[acc]);
       }
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(qd * 32) << 16);
 #pragma unroll 1
@@ -261,7 +353,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (q == q_last) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) release_acc(&tmem_empty_bar[acc]);
           }
           const int acol = tc.n0 + q * 32;
           if (p.bias != nullptr) {
@@ -321,7 +413,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (q == q_last) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) release_acc(&tmem_empty_bar[acc]);
           }
           const int acol = tc.n0 + q * 32;
 #pragma unroll
@@ -374,7 +466,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA of a pair may leave while the other still uses it
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // Split-K second pass: out = sum_s ws[s] + bias + addend + residuals, 8 columns per thread.
@@ -435,99 +530,162 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
 static int g_num_sms = 0;
 
 struct GemmPlan {
-  int bn, split, stages;
+  int bn, split, stages, cg;
 };
 
-static int stages_for(int bn, int n_res, int out_fp32) {
-  const int stage = 16384 + bn * 128;
-  const int fixed = 1024 /*align*/ + kBarBytes + 4 * (out_fp32 ? 16384 : 8192) +
-                    (n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0);
-  int s = (kSmemLimit - fixed) / stage;
+static int fixed_smem(int n_res, int out_fp32) {
+  return 1024 /*align*/ + kBarBytes + 4 * (out_fp32 ? 16384 : 8192) + (n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0);
+}
+// ring stages of two 64-wide K blocks each
+static int stages_for(int bn, int cg, int n_res, int out_fp32) {
+  const int s = (kSmemLimit - fixed_smem(n_res, out_fp32)) / (2 * (16384 + (bn / cg) * 128));
   return s > kMaxStages ? kMaxStages : s;
 }
-static int smem_for(int bn, int stages, int n_res, int out_fp32) {
-  return 1024 + kBarBytes + 4 * (out_fp32 ? 16384 : 8192) + (n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0) +
-         stages * (16384 + bn * 128);
+static int smem_for(int bn, int cg, int stages, int n_res, int out_fp32) {
+  return fixed_smem(n_res, out_fp32) + stages * 2 * (16384 + (bn / cg) * 128);
 }
 
-// Cost model (cycles) behind the automatic tile-width / split-K choice. Per 64-wide K block a CTA needs
+// Cost model (cycles) behind the automatic tile-width / CTA-pair / split-K choice. Per 64-wide K block a CTA needs
 // max(MMA issue time = 2*BN cycles, operand bytes / its share of the L2->SM bandwidth); a launch takes
-// ceil(tiles / SMs) waves of (K blocks * that + fixed per-tile cost); split-K adds the reduce pass.
-static double plan_cost(int bn, int split, int N, int64_t m_tiles, int num_kb, int64_t M, int sms) {
+// ceil(tiles / SMs) waves of (K blocks * that + fixed per-tile cost); split-K adds the reduce pass. Callers that
+// can measure (the engine's tuner) pass block_n / cta_group / split_k explicitly instead.
+static double plan_cost(int bn, int cg, int split, int N, int64_t m_tiles, int num_kb, int64_t M, int sms) {
   const int n_tiles = (N + bn - 1) / bn;
   const int kbps = (num_kb + split - 1) / split;
-  const int64_t tiles = m_tiles * n_tiles * split;
+  const int64_t tiles = ((m_tiles + cg - 1) / cg) * cg * n_tiles * split;  // in CTAs
   const int64_t ctas = tiles < sms ? tiles : sms;
   const int64_t waves = (tiles + sms - 1) / sms;
   double bw = 6500.0 / static_cast<double>(ctas);  // bytes / cycle / SM
-  if (bw > 100.0) bw = 100.0;
-  const double feed = (16384.0 + bn * 128.0) / bw;
+  if (bw > 80.0) bw = 80.0;
+  const double feed = (16384.0 + (bn / cg) * 128.0) / bw;
   const double mma = 2.0 * bn;
   const double per_kb = feed > mma ? feed : mma;
   const double epi = 300.0 * ((bn + 31) / 32) / 2.0 + 400.0;  // per tile, two groups in parallel
   double tile = kbps * per_kb;
   if (tile < epi) tile = epi;
-  double cost = 2500.0 + waves * (tile + 700.0);
+  double cost = 2500.0 + waves * (tile + 700.0) + (cg == 2 ? 600.0 : 0.0);
   if (split > 1) cost += 5000.0 + static_cast<double>(M) * N * 4.0 * (split + 1) / 3000.0;
   return cost;
 }
 
+static int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+
 static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, int num_kb, int n_res, int sms) {
-  static int env_bn = -1, env_split = -1;
+  static int env_bn = -1, env_split = -1, env_cg = -1;
   if (env_bn < 0) {
-    const char* e = getenv("ASVA_GEMM_BN");
-    env_bn = e ? atoi(e) : 0;
-    e = getenv("ASVA_GEMM_SPLIT");
-    env_split = e ? atoi(e) : 0;
+    env_bn = env_int("ASVA_GEMM_BN");
+    env_split = env_int("ASVA_GEMM_SPLIT");
+    env_cg = env_int("ASVA_GEMM_CG");
   }
-  GemmPlan best{128, 1, 2};
-  if (d->geglu) {
-    best.stages = stages_for(128, 0, 0);
-    return best;
-  }
+  GemmPlan best{128, 1, 2, 1};
   const int bns[4] = {64, 128, 160, 256};
   const int splits[10] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
-  const int want_bn = d->block_n ? d->block_n : env_bn;
-  const int want_split = d->split_k ? d->split_k : env_split;
+  const int want_bn = d->geglu ? 128 : (d->block_n ? d->block_n : env_bn);
+  const int want_split = d->geglu ? 1 : (d->split_k ? d->split_k : env_split);
+  const int want_cg = d->cta_group ? d->cta_group : env_cg;
   const int64_t max_split = (d->ws != nullptr) ? d->ws_bytes / (M * static_cast<int64_t>(d->N) * 4) : 1;
   double best_cost = 1e300;
-  for (int bi = 0; bi < 4; ++bi) {
-    const int bn = bns[bi];
-    if (want_bn && bn != want_bn) continue;
-    if (bn > 64 && bn >= 2 * ((d->N + 31) / 32) * 32) continue;  // more than half the tile would be padding
-    for (int si = 0; si < 10; ++si) {
-      int sp = splits[si];
-      if (want_split && sp != want_split && !(want_split > max_split && sp == 1)) continue;
-      if (sp > max_split || sp > num_kb) continue;
-      const int kbps = (num_kb + sp - 1) / sp;
-      if ((num_kb + kbps - 1) / kbps != sp) continue;  // would leave an empty split
-      const int nr = sp > 1 ? 0 : n_res;
-      if (stages_for(bn, nr, sp > 1 ? 1 : d->out_fp32) < 2) continue;
-      const double c = plan_cost(bn, sp, d->N, m_tiles, num_kb, M, sms);
-      if (c < best_cost) {
-        best_cost = c;
-        best.bn = bn;
-        best.split = sp;
+  bool pair_ok = true;  // a pair shares ONE W tile: both m tiles must agree on wk vs wk_first (same d2 origin)
+  for (int s = 0; s < d->nseg; ++s)
+    if (d->seg[s].wk_first >= 0 && ((d->out_dims[0] + d->box[0] - 1) / d->box[0]) % 2 != 0) pair_ok = false;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (want_cg && cg != want_cg && !(cg == 1 && !pair_ok)) continue;
+    if (cg == 2 && !pair_ok) continue;
+    for (int bi = 0; bi < 4; ++bi) {
+      const int bn = bns[bi];
+      if (want_bn && bn != want_bn) continue;
+      if (bn > 64 && bn >= 2 * ((d->N + 31) / 32) * 32) continue;  // more than half the tile would be padding
+      for (int si = 0; si < 10; ++si) {
+        const int sp = splits[si];
+        if (want_split && sp != want_split && !(want_split > max_split && sp == 1)) continue;
+        if (sp > max_split || sp > num_kb) continue;
+        const int kbps = (num_kb + sp - 1) / sp;
+        if ((num_kb + kbps - 1) / kbps != sp) continue;  // would leave an empty split
+        const int nr = sp > 1 ? 0 : n_res;
+        if (stages_for(bn, cg, nr, sp > 1 ? 1 : d->out_fp32) < 2) continue;
+        const double c = plan_cost(bn, cg, sp, d->N, m_tiles, num_kb, M, sms);
+        if (c < best_cost) {
+          best_cost = c;
+          best.bn = bn;
+          best.split = sp;
+          best.cg = cg;
+        }
       }
     }
   }
   const int nr = best.split > 1 ? 0 : n_res;
-  best.stages = stages_for(best.bn, nr, best.split > 1 ? 1 : d->out_fp32);
+  best.stages = stages_for(best.bn, best.cg, nr, best.split > 1 ? 1 : d->out_fp32);
+  const int cap = env_int("ASVA_GEMM_STAGES");
+  if (cap >= 2 && best.stages > cap) best.stages = cap;
   return best;
 }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int CG>
 static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t stream) {
-  static int configured = 0;
-  if (configured < smem_bytes) {
-    ASVA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static bool configured = false;
+  static int max_ctas = 0;
+  if (!configured) {
+    ASVA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kSmemLimit));
-    configured = kSmemLimit;
+    max_ctas = g_num_sms;
+    if (CG == 2) {  // how many CTA pairs the GPU can hold at once (GPCs with an odd SM count lose one)
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(g_num_sms / 2 * 2, 1, 1);
+      q.blockDim = dim3(kGemmThreads, 1, 1);
+      q.dynamicSmemBytes = kSmemLimit;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 2;
+      at.val.clusterDim.y = 1;
+      at.val.clusterDim.z = 1;
+      q.attrs = &at;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, GEGLU, CG>, &q) == cudaSuccess && n > 0)
+        max_ctas = 2 * n;
+      else
+        max_ctas = g_num_sms / 2 * 2;
+      (void)cudaGetLastError();
+    }
+    configured = true;
   }
-  const int grid = kp.total_tiles < g_num_sms ? kp.total_tiles : g_num_sms;
-  gemm_tc_kernel<BN, GEGLU><<<grid, kGemmThreads, smem_bytes, stream>>>(kp);
+  const int want = kp.total_tiles * CG;
+  const int grid = want < max_ctas ? want : max_ctas;
+  if (CG == 1) {
+    gemm_tc_kernel<BN, GEGLU, CG><<<grid, kGemmThreads, smem_bytes, stream>>>(kp);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    ASVA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, GEGLU, CG>, kp));
+  }
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+template <int CG>
+static int dispatch_gemm(const GemmKParams& kp, int bn, bool geglu, int smem, cudaStream_t stream) {
+  if (geglu) return launch_gemm<128, true, CG>(kp, smem, stream);
+  switch (bn) {
+    case 64: return launch_gemm<64, false, CG>(kp, smem, stream);
+    case 128: return launch_gemm<128, false, CG>(kp, smem, stream);
+    case 160: return launch_gemm<160, false, CG>(kp, smem, stream);
+    default: return launch_gemm<256, false, CG>(kp, smem, stream);
+  }
 }
 
 }  // namespace asva
@@ -617,7 +775,10 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   kp.n_res = split ? 0 : n_res;
   kp.out_fp32 = split ? 1 : d->out_fp32;
   kp.n_stages = plan.stages;
+  kp.dbg = env_int("ASVA_GEMM_DBG");
   ASVA_REQUIRE(plan.stages >= 2, "asva_gemm: no shared memory left for a pipeline (block_n=%d)", bn);
+  ASVA_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "asva_gemm: unsupported block_n=%d", bn);
+  ASVA_REQUIRE(plan.cg == 1 || plan.cg == 2, "asva_gemm: cta_group must be 0 (auto), 1 or 2");
   if (!split) {
     kp.bias = d->bias;
     kp.add_ptr = d->add.ptr;
@@ -645,7 +806,7 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   {
     uint64_t dims[2] = {(uint64_t)d->wcols, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)d->ldw * 2u};
-    uint32_t box[2] = {64u, (uint32_t)bn};
+    uint32_t box[2] = {64u, (uint32_t)(bn / plan.cg)};
     uint32_t el[2] = {1u, 1u};
     int rc = make_tmap_bf16(&kp.tmW, d->w, 2, dims, strides, box, el);
     if (rc != 0) return rc;
@@ -678,20 +839,11 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
 
   kp.n_tiles_n = (d->N + bn - 1) / bn;
   ASVA_REQUIRE(m_tiles * kp.n_tiles_n * plan.split < (1ll << 31), "asva_gemm: too many tiles");
-  kp.mn_tiles = (int)(m_tiles * kp.n_tiles_n);
+  kp.mn_tiles = (int)(((m_tiles + plan.cg - 1) / plan.cg) * kp.n_tiles_n);  // pairs of m tiles when cg == 2
   kp.total_tiles = kp.mn_tiles * plan.split;
-  const int smem = smem_for(bn, plan.stages, kp.n_res, kp.out_fp32);
-  int rc;
-  if (d->geglu) {
-    rc = launch_gemm<128, true>(kp, smem, stream);
-  } else {
-    switch (bn) {
-      case 64: rc = launch_gemm<64, false>(kp, smem, stream); break;
-      case 128: rc = launch_gemm<128, false>(kp, smem, stream); break;
-      case 160: rc = launch_gemm<160, false>(kp, smem, stream); break;
-      default: rc = launch_gemm<256, false>(kp, smem, stream); break;
-    }
-  }
+  const int smem = smem_for(bn, plan.cg, plan.stages, kp.n_res, kp.out_fp32);
+  const int rc = plan.cg == 2 ? dispatch_gemm<2>(kp, bn, d->geglu != 0, smem, stream)
+                              : dispatch_gemm<1>(kp, bn, d->geglu != 0, smem, stream);
   if (rc != 0 || !split) return rc;
   const int64_t chunks = M * (d->N / 8);
   int64_t blocks = (chunks + 255) / 256;

@@ -62,8 +62,9 @@ class GemmSpec:
     res_ld: List[int] = field(default_factory=lambda: [0, 0])
     geglu: bool = False
     out_fp32: bool = False
-    block_n: int = 0
+    block_n: int = 0    # 0 = let the library choose (cost model); the engine's tuner sets measured choices
     split_k: int = 0
+    cta_group: int = 0
 
     def __post_init__(self):
         k = 0
@@ -306,7 +307,7 @@ class CudaBackend:
         d.geglu, d.out_fp32 = int(s.geglu), int(s.out_fp32)
         assert s.out.dtype == (torch.float32 if s.out_fp32 else torch.bfloat16)
         d.out, d.ldo = s.out.data_ptr(), s.ldo
-        d.block_n, d.split_k = s.block_n, s.split_k
+        d.block_n, d.split_k, d.cta_group = s.block_n, s.split_k, s.cta_group
         ws = self.splitk_ws()
         d.ws, d.ws_bytes = ws.data_ptr(), ws.numel() * 4
         with self._timed('gemm'):

@@ -75,7 +75,8 @@ typedef struct asva_gemm_desc {
   int32_t N;
   int32_t K;     /* contraction length = 64 * sum(seg.num_kb) */
   int32_t wcols; /* columns of W that exist (>= every seg.wk + 64*num_kb) */
-  int32_t reserved0;
+  int32_t cta_group; /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pairs (tcgen05 cta_group::2: 256-row tiles,
+                        each CTA of the pair loads half of the W tile) */
   /* epilogue: out = acc + bias[col] + add + res[0] + res[1]   (GEGLU: (h + bias_h) * gelu_erf(g + bias_g)) */
   const float* bias; /* [N] fp32 or NULL */
   asva_rowadd add;
