@@ -70,6 +70,10 @@ class AttnDesc(C.Structure):
 # name -> (restype, argtypes); must list every symbol include/asva_b200.h declares
 ABI = {
     "asva_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "asva_gemm_plan": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "asva_gemm_tune": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "asva_attention": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p]),
     "asva_temporal_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_float, C.c_void_p]),

@@ -690,6 +690,97 @@ static int dispatch_gemm(const GemmKParams& kp, int bn, bool geglu, int smem, cu
 
 }  // namespace asva
 
+// The plan asva_gemm would run for this descriptor (explicit block_n / split_k / cta_group requests that are not
+// feasible fall back to the cost model's choice, so callers compare the result with what they asked for).
+static int compute_plan(const asva_gemm_desc* d, asva::GemmPlan* out) {
+  using namespace asva;
+  if (d == nullptr || d->nseg < 1 || d->nseg > ASVA_GEMM_MAX_SEG) return fail(ASVA_ERR_INVALID, "bad descriptor");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    ASVA_CUDA_OK(cudaGetDevice(&dev));
+    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int64_t m_tiles = 1, M = 1;
+  for (int i = 0; i < 3; ++i) {
+    if (d->box[i] < 1 || d->out_dims[i] < 1) return fail(ASVA_ERR_INVALID, "bad box/out_dims");
+    m_tiles *= (d->out_dims[i] + d->box[i] - 1) / d->box[i];
+    M *= d->out_dims[i];
+  }
+  int kb_total = 0, n_res = 0;
+  for (int s = 0; s < d->nseg; ++s) kb_total += d->seg[s].num_kb;
+  for (int i = 0; i < 2; ++i) n_res += d->res[i] != nullptr;
+  *out = plan_gemm(d, m_tiles, M, kb_total, n_res, g_num_sms);
+  return 0;
+}
+
+extern "C" int asva_gemm_plan(const asva_gemm_desc* d, int32_t* block_n, int32_t* split_k, int32_t* cta_group,
+                              int32_t* stages) {
+  asva::GemmPlan pl;
+  const int rc = compute_plan(d, &pl);
+  if (rc != 0) return rc;
+  if (block_n) *block_n = pl.bn;
+  if (split_k) *split_k = pl.split;
+  if (cta_group) *cta_group = pl.cg;
+  if (stages) *stages = pl.stages;
+  return 0;
+}
+
+extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, int32_t reps, int32_t* block_n,
+                              int32_t* split_k, int32_t* cta_group, float* best_us) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(d != nullptr && block_n && split_k && cta_group, "asva_gemm_tune: null argument");
+  if (reps < 1) reps = 3;
+  cudaEvent_t e0, e1;
+  ASVA_CUDA_OK(cudaEventCreate(&e0));
+  ASVA_CUDA_OK(cudaEventCreate(&e1));
+  const int bns[4] = {64, 128, 160, 256};
+  const int splits[6] = {1, 2, 3, 4, 6, 8};
+  float best = 1e30f;
+  int rc = 0, bb = 0, bs = 0, bc = 0;
+  for (int cg = 1; cg <= 2 && rc == 0; ++cg) {
+    for (int bi = 0; bi < 4 && rc == 0; ++bi) {
+      for (int si = 0; si < 6 && rc == 0; ++si) {
+        asva_gemm_desc c = *d;
+        c.block_n = d->geglu ? 128 : bns[bi];
+        c.split_k = splits[si];
+        c.cta_group = cg;
+        if (d->geglu && (bi != 1 || si != 0)) continue;
+        GemmPlan pl;
+        if (compute_plan(&c, &pl) != 0) continue;
+        if (pl.bn != c.block_n || pl.split != c.split_k || pl.cg != c.cta_group) continue;  // not feasible
+        if ((rc = asva_gemm(&c, stream_)) != 0) break;  // warm-up (also first-use kernel attribute setup)
+        cudaEventRecord(e0, stream);
+        for (int r = 0; r < reps && rc == 0; ++r) rc = asva_gemm(&c, stream_);
+        cudaEventRecord(e1, stream);
+        if (rc != 0) break;
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+          rc = fail(ASVA_ERR_CUDA, "asva_gemm_tune: %s", cudaGetErrorString(cudaGetLastError()));
+          break;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const float us = ms * 1e3f / reps;
+        if (us < best) {
+          best = us;
+          bb = c.block_n;
+          bs = c.split_k;
+          bc = cg;
+        }
+      }
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc != 0) return rc;
+  ASVA_REQUIRE(bb != 0, "asva_gemm_tune: no feasible plan");
+  *block_n = bb;
+  *split_k = bs;
+  *cta_group = bc;
+  if (best_us) *best_us = best;
+  return 0;
+}
+
 extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   using namespace asva;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

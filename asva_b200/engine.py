@@ -196,6 +196,7 @@ class UNetEngine:
         return t
 
     _frozen = False
+    _tuned = False
 
     def prepare(self, B: int, F: int, h: int, w: int) -> None:
         """Fixes the problem shape, builds the per-block temporal position embeddings and (by a dry run of the
@@ -220,6 +221,7 @@ class UNetEngine:
             be.small_linear(feat, a["pos1_w"], a["pos1_b"], hid, F, C, C, 0, 1)
             be.small_linear(hid, a["pos2_w"], a["pos2_b"], a["pos"], F, C, C, 0, 0)
         self.ctx, self.ctx_sig = None, None
+        self._tuned = False
 
     def _ctx_buf(self, tag, shape, dtype):
         key = (tag, tuple(shape), dtype)
@@ -245,6 +247,9 @@ class UNetEngine:
             return t.stride(1) == 0 or F == 1 or bool((t[:, :1] == t).all())
 
         ctx, sig = {}, []
+        tune = getattr(self.be, "name", "") == "cuda" and not torch.cuda.is_current_stream_capturing()
+        if tune:
+            self.be.tuning = True  # new K/V projection shapes get their tile plan measured once (cached per shape)
         for name, t in (("attn2", text), ("attn_audio", audio)):
             inv = frame_invariant(t)
             src = t[:, 0] if inv else t.reshape(B * F, t.shape[2], t.shape[3])
@@ -282,6 +287,8 @@ class UNetEngine:
             sig.append((ctx[name]["inv"], ctx[name]["G"], ctx[name]["nk"], cmask is not None))
             if name == "attn_audio":
                 ctx["mask"] = cmask
+        if tune:
+            self.be.tuning = False
         self.ctx = ctx
         self.ctx_sig = tuple(sig)
 
@@ -391,6 +398,15 @@ class UNetEngine:
         device; out fp32 (B,Co,F,h,w)."""
         if self.ctx is None:
             raise RuntimeError("set_context() must be called before forward()")
+        if not self._tuned and getattr(self.be, "name", "") == "cuda" and not torch.cuda.is_current_stream_capturing():
+            # one throw-away pass of the launch sequence in which every new GEMM shape has its tile plan measured on
+            # the device (CudaBackend.gemm / asva_gemm_tune); it only scribbles on the engine's own buffers and `out`
+            self._tuned = True
+            self.be.tuning = True
+            try:
+                self.forward(latents, timesteps, out)
+            finally:
+                self.be.tuning = False
         B, F, h, w = self.shape
         be, ch, L = self.be, self.chans, self.cfg["layers_per_block"]
         nlev = len(ch)

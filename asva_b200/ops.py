@@ -6,6 +6,7 @@ reference operator maps onto the generic kernels; the backend object executes a 
 is `CudaBackend` (ctypes -> libasva_b200.so).  tests/sim_backend.py interprets the same specs with torch on the
 CPU so the descriptor logic can be checked against the oracle without a GPU - it is test infrastructure and is
 never importable from this package."""
+import ctypes as C
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -213,6 +214,8 @@ class CudaBackend:
         self.launches = 0
         self._prof = None
         self._ws = {}
+        self.tuning = False
+        self.plan_cache = {}
 
     def splitk_ws(self) -> torch.Tensor:
         """fp32 scratch for split-K partial tiles, one per device, allocated on first use (before any graph
@@ -265,7 +268,40 @@ class CudaBackend:
             if t is not None and not t.is_cuda:
                 raise _lib.AsvaError("asva_b200 operators need CUDA tensors (no CPU fallback)")
 
+    # -- measured tile plans: while `tuning` is on, the first launch of every new problem shape sweeps the feasible
+    #    (block_n, split_k, cta_group) plans on the device (asva_gemm_tune) and the winner is cached per shape
+    @staticmethod
+    def gemm_signature(s: GemmSpec) -> tuple:
+        return (s.box, s.trav, s.out_dims, tuple((g.src, g.num_kb, g.off, g.wk_first >= 0, g.fix2) for g in s.segs),
+                s.N, s.K, s.bias is not None, s.add is not None, sum(r is not None for r in s.res), s.geglu,
+                s.out_fp32, tuple(None if a is None else a.dims for a in s.a))
+
     def gemm(self, s: GemmSpec) -> None:
+        if s.block_n == 0 and s.split_k == 0 and s.cta_group == 0:
+            sig = self.gemm_signature(s)
+            plan = self.plan_cache.get(sig)
+            if plan is None and self.tuning:
+                d = self._gemm_desc(s)
+                bn, sp, cg, us = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_float(0.0)
+                _lib.check(self.lib.asva_gemm_tune(d, self._stream(), 3, C.byref(bn), C.byref(sp), C.byref(cg),
+                                                   C.byref(us)), "asva_gemm_tune")
+                plan = (bn.value, sp.value, cg.value)
+                self.plan_cache[sig] = plan
+            if plan is not None:
+                s.block_n, s.split_k, s.cta_group = plan
+        d = self._gemm_desc(s)
+        with self._timed('gemm'):
+            _lib.check(self.lib.asva_gemm(d, self._stream()), "asva_gemm")
+        self.launches += 2 if (s.split_k or self.gemm_plan(s, d)[1]) > 1 else 1  # split-K adds the reduce kernel
+
+    def gemm_plan(self, s: GemmSpec, d=None) -> tuple:
+        """(block_n, split_k, cta_group, stages) the library will use for this spec."""
+        d = self._gemm_desc(s) if d is None else d
+        v = [C.c_int32(0) for _ in range(4)]
+        _lib.check(self.lib.asva_gemm_plan(d, *[C.byref(x) for x in v]), "asva_gemm_plan")
+        return tuple(x.value for x in v)
+
+    def _gemm_desc(self, s: GemmSpec) -> "_lib.GemmDesc":
         d = _lib.GemmDesc()
         for i in range(2):
             av = s.a[i]
@@ -310,9 +346,7 @@ class CudaBackend:
         d.block_n, d.split_k, d.cta_group = s.block_n, s.split_k, s.cta_group
         ws = self.splitk_ws()
         d.ws, d.ws_bytes = ws.data_ptr(), ws.numel() * 4
-        with self._timed('gemm'):
-            _lib.check(self.lib.asva_gemm(d, self._stream()), "asva_gemm")
-        self.launches += 1
+        return d
 
     def attention(self, s: AttnSpec) -> None:
         self._chk_dev(s.q, s.kv, s.out, s.mask)

@@ -95,6 +95,16 @@ typedef struct asva_gemm_desc {
 
 int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream);
 
+/* The tile plan asva_gemm would use for `d` (its cost model's choice where block_n / split_k / cta_group are 0). */
+int asva_gemm_plan(const asva_gemm_desc* d, int32_t* block_n, int32_t* split_k, int32_t* cta_group, int32_t* stages);
+
+/* Measures every feasible (block_n, split_k, cta_group) plan of `d` on the device (CUDA events on `stream`, `reps`
+ * launches each after one warm-up) and returns the fastest.  Runs the GEMM repeatedly - the output (and anything that
+ * aliases it) is scratch afterwards - and synchronises with the stream, so it must not be called during graph
+ * capture.  Callers cache the result per problem shape and pass it in block_n / split_k / cta_group. */
+int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream, int32_t reps, int32_t* block_n, int32_t* split_k,
+                   int32_t* cta_group, float* best_us);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Fused softmax(Q K^T * scale [+ mask]) V on tcgen05 (flash-style online softmax, S and O in TMEM).
  * Replaces F.scaled_dot_product_attention in FFAttnProcessor (utils.py:151-153: first-frame spatial attention,

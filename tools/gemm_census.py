@@ -116,16 +116,16 @@ def main():
         torch.cuda.synchronize()
         lib_us = e0.elapsed_time(e1) * 1e3 / n2
         del a_, ws_, o_, g2
-        rows.append((sig, len(specs), us, fl / us / 1e6, len(specs) * us, lib_us))
+        rows.append((sig, len(specs), us, fl / us / 1e6, len(specs) * us, lib_us, be.gemm_plan(specs[0])))
     tot = sum(r[4] for r in rows)
     totfl = sum(2.0 * r[0][0] * r[0][1] * r[0][2] * r[1] for r in rows)
     lines = [f"# asva_gemm census, workload {args.workload}: {len(recorded)} launches/step, summed {tot / 1e3:.3f} ms, "
              f"{totfl / 1e9:.1f} GFLOP executed -> {totfl / tot / 1e6:.1f} TFLOP/s average (back-to-back launches replayed "
              f"from a CUDA graph, CUDA events)", "",
-             "| M | N | K | taps | trav | box | epilogue | launches | us/launch | TFLOP/s | step us | share | cuBLAS us |",
-             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
-    for sig, cnt, us, tf, tt, lib in sorted(rows, key=lambda r: -r[4]):
-        lines.append(f"| {sig[0]} | {sig[1]} | {sig[2]} | {sig[3]} | {sig[4]} | {sig[5]} | {sig[6]} | {cnt} | {us:.1f} | "
+             "| M | N | K | taps | trav | box | epilogue | plan bn/split/cg/stages | launches | us/launch | TFLOP/s | step us | share | cuBLAS us |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    for sig, cnt, us, tf, tt, lib, plan in sorted(rows, key=lambda r: -r[4]):
+        lines.append(f"| {sig[0]} | {sig[1]} | {sig[2]} | {sig[3]} | {sig[4]} | {sig[5]} | {sig[6]} | {'/'.join(str(x) for x in plan)} | {cnt} | {us:.1f} | "
                      f"{tf:.0f} | {tt:.0f} | {100 * tt / tot:.1f}% | {lib:.1f} |")
     lines.append(f"\ncuBLAS yardstick total for the same shapes: {sum(r[5] * r[1] for r in rows) / 1e3:.3f} ms")
     txt = "\n".join(lines)
