@@ -1,14 +1,19 @@
 // Fused attention  O = softmax(Q K^T * scale [+ mask]) V  on tcgen05 for sm_100a.
 //
-// One CTA owns 128 query rows of one (group, head) and streams the keys/values of that group in tiles of KV keys:
-//   warp 0      TMA producer: Q tile once, then per key tile the K box(es) (K-major) and V box(es) (MN-major,
-//               read straight from the token-major [rows][channels] projection output - no transposed copy)
-//   warp 1      TMEM allocator + single-thread MMA issuer:  S = Q K^T  (TMEM cols [0,KV)),  O += P V (cols [KV,..))
-//   warps 2..5  softmax: thread = query row (TMEM lane). Pass 1 reads S for the row maximum, pass 2 re-reads S,
-//               exponentiates (exp2, log2e folded into the scale), writes P as bf16 into a 128B-swizzled smem
-//               tile (the A operand of the second MMA) and rescales O in TMEM when the running maximum moved.
-// K/V tiles are double buffered; S/P are single buffered, so MMA/softmax overlap comes from co-resident CTAs
-// (2 per SM for head_dim <= 80).
+// Persistent kernel, one CTA per SM. A work item is one tile of 128 query rows of one (group, head); the CTA keeps
+// NWG (1 or 2) items in flight, one per softmax warpgroup, so the tensor core works for one warpgroup while the other
+// is in its softmax ("ping-pong"), and loads of the next item overlap the tail of the current one.
+//   warp 0          TMA producer: the Q tile of each warpgroup's next item, then the key tiles of both in-flight items
+//                   interleaved through one shared ring: K box(es) (K-major) and V box(es) (MN-major, read straight
+//                   from the token-major [rows][channels] projection output - no transposed copy). Q comes from the
+//                   token-major projection too: the tensor map is (d, heads, rows) and the 64-wide box zero-fills
+//                   the padding past d.
+//   warp 1, last    TMEM allocator (warp 1) + one single-thread MMA issuer per warpgroup:  S_w = Q_w K^T  (TMEM cols
+//                   [w*KV, ..)),  O_w += P_w V
+//   warps 2..5/6..9 softmax warpgroups (thread = query row = TMEM lane). Pass 1 reads S for the row maximum, pass 2
+//                   re-reads S, exponentiates (exp2, log2e folded into the scale), writes P as bf16 into a
+//                   128B-swizzled smem tile (the A operand of the second MMA) and rescales O in TMEM when the running
+//                   maximum moved; after the last key tile it normalises O and stores the rows.
 // Reference semantics: F.scaled_dot_product_attention with an optional boolean keep-mask
 // (avgen/models/unets/utils.py:151-153 and diffusers AttnProcessor2_0).
 #include "common.cuh"
@@ -25,18 +30,23 @@ struct AttnKParams {
   int32_t R, Nk, d, dN, heads, k_col0, v_col0, mask_rows;
   int32_t ksteps_qk;  // ceil(d/16)
   int32_t nvb;        // number of 64-wide V column blocks = ceil(dN/64)
+  int32_t n_qt;       // query tiles per (group, head)
+  int32_t total_items;
   float scale_log2;   // scale * log2(e)
 };
 
-template <int DKA, int KV>
+template <int DKA, int KV, int NWG, int STAGES>
 struct AttnCfg {
   static constexpr int kQBytes = DKA * 128 * 128;
   static constexpr int kKBytes = DKA * KV * 128;
   static constexpr int kVBytes = DKA * KV * 128;  // nvb <= DKA
   static constexpr int kStageBytes = kKBytes + kVBytes;
   static constexpr int kPBytes = (KV / 64) * 128 * 128;
-  static constexpr int kSmemBytes = kQBytes + 2 * kStageBytes + kPBytes + 1024 + 128;
-  static constexpr int kTmemCols = 256;
+  static constexpr int kONCols = DKA == 1 ? 64 : (DKA == 2 ? 128 : 192);  // TMEM columns reserved per O accumulator
+  static constexpr int kTmemNeed = NWG * (KV + kONCols);
+  static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = NWG * (kQBytes + kPBytes) + STAGES * kStageBytes + 1024 + 256;
+  static constexpr int kThreads = 64 + 128 * NWG + (NWG > 1 ? 32 : 0);  // + the second MMA-issuing warp
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2, flush-to-zero; exp2(-inf) = 0
@@ -56,41 +66,43 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128_mn(uint32_t saddr, uint32_t
          (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int DKA, int KV>
-__global__ void __launch_bounds__(192, (DKA <= 2) ? 2 : 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = AttnCfg<DKA, KV>;
+template <int DKA, int KV, int NWG, int STAGES>
+__global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<DKA, KV, NWG, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + Cfg::kQBytes;
-  uint8_t* sP = sKV + 2 * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sQ = smem;                                // [NWG][kQBytes]
+  uint8_t* sKV = sQ + NWG * Cfg::kQBytes;            // [STAGES][K | V]
+  uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;     // [NWG][kPBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NWG * Cfg::kPBytes);
+  uint64_t* q_full = bars;              // [2]  Q tile of the warpgroup's item landed
+  uint64_t* q_free = bars + 2;          // [2]  every S = Q K^T of the item has been issued and completed
+  uint64_t* s_full = bars + 4;          // [2]
+  uint64_t* p_full = bars + 6;          // [2]  P tile written (and S consumed)
+  uint64_t* pv_done = bars + 8;         // [2]
+  uint64_t* o_free = bars + 10;         // [2]  the warpgroup has read the item's O out of TMEM
+  uint64_t* kv_full = bars + 12;        // [STAGES]
+  uint64_t* kv_empty = kv_full + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * 128;
-  const int head = blockIdx.y;
-  const int g = blockIdx.z;
   const int n_tiles = (p.Nk + KV - 1) / KV;
+  const int item_stride = gridDim.x * NWG;
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(&q_full[w], 1);
+      mbar_init(&q_free[w], 1);
+      mbar_init(&s_full[w], 1);
+      mbar_init(&p_full[w], 128);
+      mbar_init(&pv_done[w], 1);
+      mbar_init(&o_free[w], 128);
+    }
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmKV);
@@ -103,208 +115,265 @@ __global__ void __launch_bounds__(192, (DKA <= 2) ? 2 : 1) attn_tc_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + KV;
 
   if (warp == 0) {
+    // ---------------- TMA producer ----------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+      const uint32_t kv_tx = static_cast<uint32_t>(DKA + p.nvb) * KV * 128u;
+      uint32_t pos = 0;
+      for (int round = 0;; ++round) {
+        const int item0 = round * item_stride + static_cast<int>(blockIdx.x) * NWG;
+        if (item0 >= p.total_items) break;
+        int gh[NWG];
 #pragma unroll
-      // Q comes straight from the token-major projection output: tensor (d, heads, rows); the 64-wide box reaches
-      // past d and TMA zero-fills the padding
-      for (int a = 0; a < DKA; ++a) tma_load_3d(sQ + a * 128 * 128, &p.tmQ, q_full, a * 64, head, g * p.R + row0);
-      const uint32_t tx = static_cast<uint32_t>(DKA + p.nvb) * KV * 128u;
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[s], tx);
-        uint8_t* sk = sKV + s * Cfg::kStageBytes;
-        uint8_t* sv = sk + Cfg::kKBytes;
+        for (int w = 0; w < NWG; ++w) {
+          const int item = item0 + w;
+          gh[w] = -1;
+          if (item >= p.total_items) continue;
+          const int qt = item % p.n_qt;
+          gh[w] = item / p.n_qt;  // g * heads + head
+          const int g = gh[w] / p.heads, head = gh[w] % p.heads;
+          mbar_wait(&q_free[w], (round & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[w], Cfg::kQBytes);
 #pragma unroll
-        for (int a = 0; a < DKA; ++a)
-          tma_load_3d(sk + a * KV * 128, &p.tmKV, &kv_full[s], p.k_col0 + head * p.d + a * 64, j * KV, g);
-        for (int a = 0; a < p.nvb; ++a)
-          tma_load_3d(sv + a * KV * 128, &p.tmKV, &kv_full[s], p.v_col0 + head * p.d + a * 64, j * KV, g);
+          for (int a = 0; a < DKA; ++a)
+            tma_load_3d(sQ + w * Cfg::kQBytes + a * 128 * 128, &p.tmQ, &q_full[w], a * 64, head, g * p.R + qt * 128);
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+#pragma unroll
+          for (int w = 0; w < NWG; ++w) {
+            if (gh[w] < 0) continue;
+            const int g = gh[w] / p.heads, head = gh[w] % p.heads;
+            const uint32_t s = pos % STAGES, ph = (pos / STAGES) & 1u;
+            mbar_wait(&kv_empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&kv_full[s], kv_tx);
+            uint8_t* sk = sKV + s * Cfg::kStageBytes;
+            uint8_t* sv = sk + Cfg::kKBytes;
+#pragma unroll
+            for (int a = 0; a < DKA; ++a)
+              tma_load_3d(sk + a * KV * 128, &p.tmKV, &kv_full[s], p.k_col0 + head * p.d + a * 64, j * KV, g);
+            for (int a = 0; a < p.nvb; ++a)
+              tma_load_3d(sv + a * KV * 128, &p.tmKV, &kv_full[s], p.v_col0 + head * p.d + a * 64, j * KV, g);
+            ++pos;
+          }
+        }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2 + 4 * NWG) {
+    // ---------------- MMA issuers: one thread per warpgroup (warp 1 -> warpgroup 0, the last warp -> warpgroup 1), so a
+    // warpgroup's S = Q K^T never queues behind the other warpgroup's barrier waits ----------------
+    const int w = (warp == 1) ? 0 : 1;
+    if (lane == 0 && w < NWG) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, KV);
       const uint32_t idesc_o = make_idesc_bf16_bmn(128, static_cast<uint32_t>(p.dN));
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
-      auto issue_s = [&](int j) {
-        const uint32_t k_addr = smem_u32(sKV + (j & 1) * Cfg::kStageBytes);
+      const uint32_t q_addr = smem_u32(sQ + w * Cfg::kQBytes);
+      const uint32_t p_addr = smem_u32(sP + w * Cfg::kPBytes);
+      const uint32_t kv_addr0 = smem_u32(sKV);
+      const uint32_t tmem_s = tmem_base + w * KV;
+      const uint32_t tmem_o = tmem_base + NWG * KV + w * Cfg::kONCols;
+      uint32_t cnt = 0;  // key tiles finished (phase of p_full / pv_done)
+      auto issue_s = [&](uint32_t pos) {
+        const uint32_t s = pos % STAGES, ph = (pos / STAGES) & 1u;
+        mbar_wait(&kv_full[s], ph);
+        tc_fence_after();
+        const uint32_t k_addr = kv_addr0 + s * Cfg::kStageBytes;
         for (int ks = 0; ks < p.ksteps_qk; ++ks) {
           const uint32_t a = ks >> 2, o = (ks & 3) * 32u;
-          umma_bf16_ss(tmem_S, make_sdesc_sw128(q_addr + a * 128u * 128u + o),
+          umma_bf16_ss(tmem_s, make_sdesc_sw128(q_addr + a * 128u * 128u + o),
                        make_sdesc_sw128(k_addr + a * KV * 128u + o), idesc_s, ks != 0 ? 1u : 0u);
         }
-        tc_commit(s_full);
+        tc_commit(&s_full[w]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) {
-          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          mbar_wait(s_empty, j & 1);
+      for (int round = 0;; ++round) {
+        const int item0 = round * item_stride + static_cast<int>(blockIdx.x) * NWG;
+        if (item0 + w >= p.total_items) break;
+        // ring positions follow the producer's order: rounds, then key tiles, then the active warpgroups
+        const uint32_t nact = (item0 + NWG - 1 < p.total_items) ? NWG : 1;
+        const uint32_t pos0 = static_cast<uint32_t>(round) * n_tiles * NWG + w;
+        mbar_wait(&q_full[w], round & 1);
+        issue_s(pos0);
+        if (n_tiles == 1) tc_commit(&q_free[w]);
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(&p_full[w], cnt & 1u);
+          // P(j) is ready and S is free: start S(j+1) first (the warpgroup is idle until it lands), then the longer
+          // P V product of tile j
+          if (j + 1 < n_tiles) {
+            issue_s(pos0 + (j + 1) * nact);
+            if (j + 2 == n_tiles) tc_commit(&q_free[w]);
+          }
+          if (j == 0) mbar_wait(&o_free[w], (round & 1) ^ 1);  // the previous item's O has been read out
           tc_fence_after();
-          issue_s(j + 1);
+          const uint32_t s = (pos0 + j * nact) % STAGES;
+          const uint32_t v_addr = kv_addr0 + s * Cfg::kStageBytes + Cfg::kKBytes;
+          const int kvalid = p.Nk - j * KV;  // keys of this tile that exist; P is zero beyond them
+          const int ksteps = kvalid >= KV ? KV / 16 : (kvalid + 15) >> 4;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t adesc = make_sdesc_sw128(p_addr + (ks >> 2) * 128u * 128u + (ks & 3) * 32u);
+            const uint64_t bdesc = make_sdesc_sw128_mn(v_addr + ks * 16u * 128u, KV * 128u);
+            umma_bf16_ss(tmem_o, adesc, bdesc, idesc_o, (j | ks) != 0 ? 1u : 0u);
+          }
+          tc_commit(&kv_empty[s]);
+          tc_commit(&pv_done[w]);
+          ++cnt;
         }
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + (j & 1) * Cfg::kStageBytes + Cfg::kKBytes);
-#pragma unroll
-        for (int ks = 0; ks < KV / 16; ++ks) {
-          const uint64_t adesc = make_sdesc_sw128(p_addr + (ks >> 2) * 128u * 128u + (ks & 3) * 32u);
-          const uint64_t bdesc = make_sdesc_sw128_mn(v_addr + ks * 16u * 128u, KV * 128u);
-          umma_bf16_ss(tmem_O, adesc, bdesc, idesc_o, (j | ks) != 0 ? 1u : 0u);
-        }
-        tc_commit(&kv_empty[j & 1]);
-        tc_commit(pv_done);
       }
     }
     __syncwarp();
   } else {
-    // ---------------- softmax + output ----------------
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int row = row0 + r;
-    const bool valid = row < p.R;
-    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const uint8_t* mrow = nullptr;
-    if (p.mask != nullptr && valid)
-      mrow = p.mask + ((static_cast<int64_t>(g) * p.R + row) / p.mask_rows) * p.mask_ld;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = sP + r * 128;
+    // ---------------- softmax + output (warpgroup w) ----------------
+    const int w = (warp - 2) >> 2;  // warps 2..5 -> warpgroup 0, 6..9 -> warpgroup 1
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tmem_S = tmem_base + w * KV;
+    const uint32_t tmem_O = tmem_base + NWG * KV + w * Cfg::kONCols;
+    uint8_t* prow = sP + w * Cfg::kPBytes + r * 128;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
+    uint32_t cnt = 0;
+    for (int round = 0;; ++round) {
+      const int item = round * item_stride + static_cast<int>(blockIdx.x) * NWG + w;
+      if (item >= p.total_items) break;
+      const int qt = item % p.n_qt;
+      const int ghh = item / p.n_qt;
+      const int g = ghh / p.heads, head = ghh % p.heads;
+      const int row = qt * 128 + r;
+      const bool valid = row < p.R;
+      const uint8_t* mrow = nullptr;
+      if (p.mask != nullptr && valid)
+        mrow = p.mask + ((static_cast<int64_t>(g) * p.R + row) / p.mask_rows) * p.mask_ld;
+      float m_run = -INFINITY, l_run = 0.f;
 
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const int key0 = j * KV;
-      // pass 1: row maximum (interior tiles without a mask skip every per-key predicate)
-      const bool plain = (mrow == nullptr) && (key0 + KV <= p.Nk);
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < KV; c += 32) {
-        uint32_t sv[32];
-        tmem_ld_x32(tmem_S + lane_base + c, sv);
-        tmem_ld_wait();
-        if (plain) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sv[i]));
-        } else {
-          uint32_t mbits = 0xffffffffu;
-          if (mrow != nullptr) {
-            mbits = 0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
-            m_tile = fmaxf(m_tile, keep ? __uint_as_float(sv[i]) : -INFINITY);
-          }
-        }
-      }
-      m_tile *= p.scale_log2;  // scale > 0: max commutes with the scaling
-      const float m_new = fmaxf(m_run, m_tile);
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = fast_exp2(m_run - m_safe);  // m_run = -inf -> 0
-      const bool changed = (m_new > m_run) && (j > 0);
-      m_run = m_new;
-      l_run *= alpha;
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // PV of the previous tile finished: O is stable, P smem is free
+      for (int j = 0; j < n_tiles; ++j, ++cnt) {
+        mbar_wait(&s_full[w], cnt & 1u);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, changed)) {
+        const int key0 = j * KV;
+        // pass 1: row maximum (interior tiles without a mask skip every per-key predicate)
+        const bool plain = (mrow == nullptr) && (key0 + KV <= p.Nk);
+        // columns of this tile that can hold keys, rounded up to the 16-key granularity of the P V product and to
+        // the 32-column chunks processed here (everything past Nk is written as zero probability)
+        const int cols = (p.Nk - key0 >= KV) ? KV : (((p.Nk - key0 + 15) >> 4) << 4);
+        float m_tile = -INFINITY;
 #pragma unroll 1
-          for (int c = 0; c < p.dN; c += 16) {
-            uint32_t ov[16];
-            tmem_ld_x16(tmem_O + lane_base + c, ov);
-            tmem_ld_wait();
+        for (int c = 0; c < cols; c += 32) {
+          uint32_t sv[32];
+          tmem_ld_x32(tmem_S + lane_base + c, sv);
+          tmem_ld_wait();
+          if (plain) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st_x16(tmem_O + lane_base + c, ov);
+            for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sv[i]));
+          } else {
+            uint32_t mbits = 0xffffffffu;
+            if (mrow != nullptr) {
+              mbits = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
+              m_tile = fmaxf(m_tile, keep ? __uint_as_float(sv[i]) : -INFINITY);
+            }
           }
-          tmem_st_wait();
         }
-      }
-      // pass 2: probabilities -> bf16 P tile in smem (K-major, 128B swizzle), row sum
-      float l_tile = 0.f;
+        m_tile *= p.scale_log2;  // scale > 0: max commutes with the scaling
+        const float m_new = fmaxf(m_run, m_tile);
+        const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = fast_exp2(m_run - m_safe);  // m_run = -inf -> 0
+        const bool changed = (m_new > m_run) && (j > 0);
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+          mbar_wait(&pv_done[w], (cnt - 1) & 1u);  // P V of the previous tile finished: O is stable, P smem is free
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, changed)) {
 #pragma unroll 1
-      for (int c = 0; c < KV; c += 32) {
-        uint32_t sv[32];
-        tmem_ld_x32(tmem_S + lane_base + c, sv);
+            for (int c = 0; c < p.dN; c += 16) {
+              uint32_t ov[16];
+              tmem_ld_x16(tmem_O + lane_base + c, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st_x16(tmem_O + lane_base + c, ov);
+            }
+            tmem_st_wait();
+          }
+        }
+        // pass 2: probabilities -> bf16 P tile in smem (K-major, 128B swizzle), row sum
+        float l_tile = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < cols; c += 32) {
+          uint32_t sv[32];
+          tmem_ld_x32(tmem_S + lane_base + c, sv);
+          tmem_ld_wait();
+          float pv[32];
+          if (plain) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe));
+          } else {
+            uint32_t mbits = 0xffffffffu;
+            if (mrow != nullptr) {
+              mbits = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
+              pv[i] = keep ? fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe)) : 0.f;
+            }
+          }
+          // the row sum is taken in fp32 before the bf16 rounding of P (the rounding errors average out over the
+          // row; bf16 keeps 8 bits, the sum of >= 16 terms is good to ~1e-3 relative either way)
+          uint32_t pk[16];
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+            l0 += pv[2 * i];
+            l1 += pv[2 * i + 1];
+          }
+          l_tile += l0 + l1;
+          uint8_t* patom = prow + (c >> 6) * (128 * 128);
+          const uint32_t chunk0 = static_cast<uint32_t>((c & 63) >> 3);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint32_t phys = (chunk0 + v) ^ sw;
+            *reinterpret_cast<uint4*>(patom + phys * 16) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+          }
+        }
+        l_run += l_tile;
+        tc_fence_before();
+        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+        mbar_arrive(&p_full[w]);   // also: S consumed (the next Q K^T may overwrite it)
+      }
+      // ---------------- output ----------------
+      mbar_wait(&pv_done[w], (cnt - 1) & 1u);
+      tc_fence_after();
+      const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+      __nv_bfloat16* orow = p.out + (static_cast<int64_t>(g) * p.R + row) * p.ldo + head * p.d;
+#pragma unroll 1
+      for (int c = 0; c < p.dN; c += 16) {
+        uint32_t ov[16];
+        tmem_ld_x16(tmem_O + lane_base + c, ov);
         tmem_ld_wait();
-        float pv[32];
-        if (plain) {
+        if (!valid) continue;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe));
-        } else {
-          uint32_t mbits = 0xffffffffu;
-          if (mrow != nullptr) {
-            mbits = 0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
+        for (int h = 0; h < 2; ++h) {
+          if (c + h * 8 < p.d) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ov[h * 8 + 0]) * inv, __uint_as_float(ov[h * 8 + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(ov[h * 8 + 2]) * inv, __uint_as_float(ov[h * 8 + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(ov[h * 8 + 4]) * inv, __uint_as_float(ov[h * 8 + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(ov[h * 8 + 6]) * inv, __uint_as_float(ov[h * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c + h * 8) = u;
           }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
-            pv[i] = keep ? fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe)) : 0.f;
-          }
-        }
-        // round to bf16 first so that the row sum matches what the tensor core will accumulate
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-          const float2 back = unpack_bf16x2(pk[i]);
-          l_tile += back.x + back.y;
-        }
-        uint8_t* patom = prow + (c >> 6) * (128 * 128);
-        const uint32_t chunk0 = static_cast<uint32_t>((c & 63) >> 3);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint32_t phys = (chunk0 + v) ^ sw;
-          *reinterpret_cast<uint4*>(patom + phys * 16) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
         }
       }
-      l_run += l_tile;
       tc_fence_before();
-      mbar_arrive(s_empty);      // S consumed (next QK^T may overwrite it)
-      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
-      mbar_arrive(p_full);
-    }
-    // ---------------- output ----------------
-    mbar_wait(pv_done, (n_tiles - 1) & 1);
-    tc_fence_after();
-    const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
-    __nv_bfloat16* orow = p.out + (static_cast<int64_t>(g) * p.R + row) * p.ldo + head * p.d;
-#pragma unroll 1
-    for (int c = 0; c < p.dN; c += 16) {
-      uint32_t ov[16];
-      tmem_ld_x16(tmem_O + lane_base + c, ov);
-      tmem_ld_wait();
-      if (!valid) continue;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (c + h * 8 < p.d) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(ov[h * 8 + 0]) * inv, __uint_as_float(ov[h * 8 + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(ov[h * 8 + 2]) * inv, __uint_as_float(ov[h * 8 + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(ov[h * 8 + 4]) * inv, __uint_as_float(ov[h * 8 + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(ov[h * 8 + 6]) * inv, __uint_as_float(ov[h * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c + h * 8) = u;
-        }
-      }
+      mbar_arrive(&o_free[w]);  // the next item's first P V may overwrite O
     }
   }
   tc_fence_before();
@@ -312,16 +381,21 @@ __global__ void __launch_bounds__(192, (DKA <= 2) ? 2 : 1) attn_tc_kernel(const 
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <int DKA, int KV>
-static int launch_attn(const AttnKParams& kp, dim3 grid, cudaStream_t stream) {
-  using Cfg = AttnCfg<DKA, KV>;
+static int g_attn_sms = 0;
+
+template <int DKA, int KV, int NWG, int STAGES>
+static int launch_attn(const AttnKParams& kp, cudaStream_t stream) {
+  using Cfg = AttnCfg<DKA, KV, NWG, STAGES>;
+  static_assert(Cfg::kSmemBytes <= 232448, "attention configuration exceeds the shared memory of an SM");
   static bool configured = false;
   if (!configured) {
-    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::kSmemBytes));
+    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV, NWG, STAGES>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  attn_tc_kernel<DKA, KV><<<grid, 192, Cfg::kSmemBytes, stream>>>(kp);
+  int grid = (kp.total_items + NWG - 1) / NWG;
+  if (grid > g_attn_sms) grid = g_attn_sms;
+  attn_tc_kernel<DKA, KV, NWG, STAGES><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -342,6 +416,11 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
                (long long)d->ldq);
   ASVA_REQUIRE(d->mask == nullptr || d->mask_rows >= 1, "asva_attention: mask_rows must be >= 1");
   ASVA_REQUIRE(d->kv_rows_per_group >= d->Nk, "asva_attention: kv_rows_per_group < Nk");
+  if (g_attn_sms == 0) {
+    int dev = 0;
+    ASVA_CUDA_OK(cudaGetDevice(&dev));
+    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
 
   AttnKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -360,6 +439,10 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
   kp.ksteps_qk = (d->d + 15) / 16;
   kp.nvb = (kp.dN + 63) / 64;
   kp.scale_log2 = d->scale * 1.4426950408889634f;
+  kp.n_qt = (d->R + 127) / 128;
+  const int64_t items = (int64_t)kp.n_qt * d->heads * d->G;
+  ASVA_REQUIRE(items < (1ll << 30), "asva_attention: too many query tiles");
+  kp.total_items = (int)items;
   const int dka = d->dpad / 64;
   const int kv = (dka == 1) ? 128 : 64;
   {
@@ -378,11 +461,9 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
     int rc = make_tmap_bf16(&kp.tmKV, d->kv, 3, dims, strides, box, el);
     if (rc != 0) return rc;
   }
-  dim3 grid((d->R + 127) / 128, d->heads, d->G);
-  ASVA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "asva_attention: grid too large");
   switch (dka) {
-    case 1: return launch_attn<1, 128>(kp, grid, stream);
-    case 2: return launch_attn<2, 64>(kp, grid, stream);
-    default: return launch_attn<3, 64>(kp, grid, stream);
+    case 1: return launch_attn<1, 128, 2, 4>(kp, stream);
+    case 2: return launch_attn<2, 64, 2, 4>(kp, stream);
+    default: return launch_attn<3, 64, 1, 3>(kp, stream);
   }
 }

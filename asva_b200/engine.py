@@ -407,6 +407,7 @@ class UNetEngine:
                 self.forward(latents, timesteps, out)
             finally:
                 self.be.tuning = False
+            self.be.save_plans()  # no-op unless ASVA_PLAN_CACHE names a file
         B, F, h, w = self.shape
         be, ch, L = self.be, self.chans, self.cfg["layers_per_block"]
         nlev = len(ch)

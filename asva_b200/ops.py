@@ -7,6 +7,7 @@ is `CudaBackend` (ctypes -> libasva_b200.so).  tests/sim_backend.py interprets t
 CPU so the descriptor logic can be checked against the oracle without a GPU - it is test infrastructure and is
 never importable from this package."""
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -216,6 +217,26 @@ class CudaBackend:
         self._ws = {}
         self.tuning = False
         self.plan_cache = {}
+        self._plan_file = os.environ.get("ASVA_PLAN_CACHE", "")
+        if self._plan_file and os.path.exists(self._plan_file):
+            self.load_plans(self._plan_file)
+
+    def load_plans(self, path: str) -> None:
+        """Measured tile plans saved by save_plans (a profiler run must not re-measure them: timings taken under
+        ncu are meaningless)."""
+        import ast
+        with open(path) as f:
+            for line in f:
+                if line.strip():
+                    k, v = line.rstrip("\n").split(" => ")
+                    self.plan_cache[ast.literal_eval(k)] = tuple(ast.literal_eval(v))
+
+    def save_plans(self, path: str = "") -> None:
+        path = path or self._plan_file
+        if path:
+            with open(path, "w") as f:
+                for k, v in self.plan_cache.items():
+                    f.write(f"{k!r} => {list(v)!r}\n")
 
     def splitk_ws(self) -> torch.Tensor:
         """fp32 scratch for split-K partial tiles, one per device, allocated on first use (before any graph

@@ -9,8 +9,8 @@ scaling, no collective on the data path; a single NCCL all-gather of the final l
   e2e          same steps through the pipeline's public session API with HOST latents: every step copies the latents
                host->device from pinned memory, runs the step and reads the updated latents back device->host
   roofline     dominant kernel family (tcgen05 GEMM / implicit-GEMM conv, asva_gemm): algorithmic GEMM FLOPs per step
-               / its summed per-launch duration (CUDA events around every launch in one eager step) vs the measured
-               sustained bf16 peak in MEASURED_PEAKS.json
+               / the duration of that family's launches of one step (re-captured as one CUDA graph and timed with
+               CUDA events) vs the measured sustained bf16 peak in MEASURED_PEAKS.json
   cpu_baseline the reference's own UNet code (oracle/_ref staged copy; else the oracle port) timed on this box's host
                cores on a bounded sample (rank 0, N = 1 only)
 `--impl reference` times that CPU implementation as its own arm."""
@@ -252,7 +252,9 @@ def run_product_arm(args):
     ms_e2e = timed(lambda i: e2e_clip(K, W) if i == 0 else None, 1)
     lat_bytes = host_in.numel() * 4
 
-    # ---- roofline of the dominant kernel family, live: one eager step with events around every launch
+    # ---- roofline of the dominant kernel family, live: the launches of one step are recorded per kernel family,
+    #      each family is re-captured as its own CUDA graph (same launches, same order, same buffers) and its replay
+    #      is timed with CUDA events - per-launch durations without host launch overhead in the measurement
     fl = flops.step_flops(2, F, h, w, chans=chans)
     peaks, peak_src = _peaks()
     os.environ["ASVA_NO_GRAPH"] = "1"
@@ -262,13 +264,47 @@ def run_product_arm(args):
     es = eager.open_session(text_d, audio_d, mask_d, F, h, w, n_sched, audio_guidance_scale=4.0)
     es.load_latents(lat.to(dev))
     es.step(0)
-    fam_runs = []
-    for rep in range(3):
-        be.profile_begin()
-        es.step(1 + rep)
-        fam_runs.append(be.profile_end())
+    FAMILIES = {"gemm": "gemm", "attention": "attention", "temporal_attention": "temporal_attention",
+                "layernorm": "layernorm", "groupnorm_stats": "groupnorm", "groupnorm_apply": "groupnorm",
+                "small_linear": "small_linear", "conv_in_im2col": "misc", "conv_out_finish": "misc",
+                "timestep_features": "misc", "cfg_ddim_step": "cfg_step", "cfg_plms_step": "cfg_step"}
+    recorded, originals = [], {}
+    for name, famname in FAMILIES.items():
+        orig = getattr(be, name)
+        originals[name] = orig
+
+        def wrapped(*a, _orig=orig, _fam=famname, **k):
+            recorded.append((_fam, _orig, a, k))
+            return _orig(*a, **k)
+
+        setattr(be, name, wrapped)
+    es.step(1)
+    for name, orig in originals.items():
+        setattr(be, name, orig)
+    torch.cuda.synchronize()
     os.environ.pop("ASVA_NO_GRAPH", None)
-    fam = {k: (fam_runs[0][k][0], sum(r[k][1] for r in fam_runs) / len(fam_runs)) for k in fam_runs[0]}
+    fam = {}
+    for famname in sorted(set(FAMILIES.values())):
+        calls = [(fn, a, k) for f_, fn, a, k in recorded if f_ == famname]
+        if not calls:
+            continue
+        n0 = be.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for fn, a, k in calls:
+                fn(*a, **k)
+        n_launch = be.launches - n0
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        fam[famname] = (n_launch, e0.elapsed_time(e1) / reps)
+        del g
     gemm_calls, gemm_ms = fam.get("gemm", (0, 0.0))
     kernel_ms_total = sum(t for _, t in fam.values())
     step_ms = ms / K
