@@ -23,7 +23,8 @@
 namespace asva {
 
 struct AttnKParams {
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmKV;   // temporal mode: tmQ = the q columns, tmKV = the k columns ...
+  CUtensorMap tmV;         // ... and tmV = the v columns, all as 5-D (d, heads, N, F, B) views of the qkv buffer
   const uint8_t* mask;
   __nv_bfloat16* out;
   int64_t ldo, mask_ld;
@@ -32,6 +33,7 @@ struct AttnKParams {
   int32_t nvb;        // number of 64-wide V column blocks = ceil(dN/64)
   int32_t n_qt;       // query tiles per (group, head)
   int32_t total_items;
+  int32_t tP, tF, tN, tPB;  // temporal mode: pixels per tile, frames, pixels per frame, pixel blocks per clip
   float scale_log2;   // scale * log2(e)
 };
 
@@ -66,7 +68,11 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128_mn(uint32_t saddr, uint32_t
          (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int DKA, int KV, int NWG, int STAGES>
+// TEMPORAL: attention over the frame axis per pixel (ff_spatio_audio_temp_transformer_3d.py:352-358). An item is a
+// block of tP pixels of one (clip, head): its tP*tF (<= KV) rows, ordered (frame, pixel), are both the queries and the
+// single key tile, fetched with 5-D boxes straight from the [b][f][n][3C] projection output; row r attends key c iff
+// they belong to the same pixel (c % tP == r % tP) - a block-diagonal mask evaluated arithmetically.
+template <int DKA, int KV, int NWG, int STAGES, bool TEMPORAL>
 __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<DKA, KV, NWG, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -85,6 +91,7 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
   uint64_t* kv_empty = kv_full + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + STAGES);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.Nk + KV - 1) / KV;
@@ -111,10 +118,18 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  if constexpr (TEMPORAL) {
+    // the boxes write tP*tF rows; the rows above them are multiplied too (as masked keys / unused queries) and must
+    // not hold NaN bit patterns: clear Q and the key ring once
+    for (int i = threadIdx.x; i < (NWG * Cfg::kQBytes + STAGES * Cfg::kStageBytes) / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -134,10 +149,17 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
           gh[w] = item / p.n_qt;  // g * heads + head
           const int g = gh[w] / p.heads, head = gh[w] % p.heads;
           mbar_wait(&q_free[w], (round & 1) ^ 1);
-          mbar_arrive_expect_tx(&q_full[w], Cfg::kQBytes);
+          if constexpr (TEMPORAL) {
+            mbar_arrive_expect_tx(&q_full[w], static_cast<uint32_t>(DKA) * p.tP * p.tF * 128u);
 #pragma unroll
-          for (int a = 0; a < DKA; ++a)
-            tma_load_3d(sQ + w * Cfg::kQBytes + a * 128 * 128, &p.tmQ, &q_full[w], a * 64, head, g * p.R + qt * 128);
+            for (int a = 0; a < DKA; ++a)
+              tma_load_5d(sQ + w * Cfg::kQBytes + a * 128 * 128, &p.tmQ, &q_full[w], a * 64, head, qt * p.tP, 0, g);
+          } else {
+            mbar_arrive_expect_tx(&q_full[w], Cfg::kQBytes);
+#pragma unroll
+            for (int a = 0; a < DKA; ++a)
+              tma_load_3d(sQ + w * Cfg::kQBytes + a * 128 * 128, &p.tmQ, &q_full[w], a * 64, head, g * p.R + qt * 128);
+          }
         }
         for (int j = 0; j < n_tiles; ++j) {
 #pragma unroll
@@ -146,14 +168,24 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
             const int g = gh[w] / p.heads, head = gh[w] % p.heads;
             const uint32_t s = pos % STAGES, ph = (pos / STAGES) & 1u;
             mbar_wait(&kv_empty[s], ph ^ 1u);
-            mbar_arrive_expect_tx(&kv_full[s], kv_tx);
             uint8_t* sk = sKV + s * Cfg::kStageBytes;
             uint8_t* sv = sk + Cfg::kKBytes;
+            if constexpr (TEMPORAL) {
+              const int qt = (item0 + w) % p.n_qt;
+              mbar_arrive_expect_tx(&kv_full[s], static_cast<uint32_t>(DKA + p.nvb) * p.tP * p.tF * 128u);
 #pragma unroll
-            for (int a = 0; a < DKA; ++a)
-              tma_load_3d(sk + a * KV * 128, &p.tmKV, &kv_full[s], p.k_col0 + head * p.d + a * 64, j * KV, g);
-            for (int a = 0; a < p.nvb; ++a)
-              tma_load_3d(sv + a * KV * 128, &p.tmKV, &kv_full[s], p.v_col0 + head * p.d + a * 64, j * KV, g);
+              for (int a = 0; a < DKA; ++a)
+                tma_load_5d(sk + a * KV * 128, &p.tmKV, &kv_full[s], a * 64, head, qt * p.tP, 0, g);
+              for (int a = 0; a < p.nvb; ++a)
+                tma_load_5d(sv + a * KV * 128, &p.tmV, &kv_full[s], a * 64, head, qt * p.tP, 0, g);
+            } else {
+              mbar_arrive_expect_tx(&kv_full[s], kv_tx);
+#pragma unroll
+              for (int a = 0; a < DKA; ++a)
+                tma_load_3d(sk + a * KV * 128, &p.tmKV, &kv_full[s], p.k_col0 + head * p.d + a * 64, j * KV, g);
+              for (int a = 0; a < p.nvb; ++a)
+                tma_load_3d(sv + a * KV * 128, &p.tmKV, &kv_full[s], p.v_col0 + head * p.d + a * 64, j * KV, g);
+            }
             ++pos;
           }
         }
@@ -237,11 +269,18 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
       const int qt = item % p.n_qt;
       const int ghh = item / p.n_qt;
       const int g = ghh / p.heads, head = ghh % p.heads;
-      const int row = qt * 128 + r;
-      const bool valid = row < p.R;
+      int row = qt * 128 + r;
+      bool valid = row < p.R;
       const uint8_t* mrow = nullptr;
-      if (p.mask != nullptr && valid)
+      int t_mod = 0;  // temporal: this row's pixel within the block
+      if constexpr (TEMPORAL) {
+        t_mod = r % p.tP;
+        const int f = r / p.tP, n = qt * p.tP + t_mod;
+        valid = (f < p.tF) && (n < p.tN);
+        row = f * p.tN + n;  // row inside clip g (p.R = tF * tN)
+      } else if (p.mask != nullptr && valid) {
         mrow = p.mask + ((static_cast<int64_t>(g) * p.R + row) / p.mask_rows) * p.mask_ld;
+      }
       float m_run = -INFINITY, l_run = 0.f;
 
       for (int j = 0; j < n_tiles; ++j, ++cnt) {
@@ -249,7 +288,7 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
         tc_fence_after();
         const int key0 = j * KV;
         // pass 1: row maximum (interior tiles without a mask skip every per-key predicate)
-        const bool plain = (mrow == nullptr) && (key0 + KV <= p.Nk);
+        const bool plain = !TEMPORAL && (mrow == nullptr) && (key0 + KV <= p.Nk);
         // columns of this tile that can hold keys, rounded up to the 16-key granularity of the P V product and to
         // the 32-column chunks processed here (everything past Nk is written as zero probability)
         const int cols = (p.Nk - key0 >= KV) ? KV : (((p.Nk - key0 + 15) >> 4) << 4);
@@ -264,7 +303,15 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
             for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sv[i]));
           } else {
             uint32_t mbits = 0xffffffffu;
-            if (mrow != nullptr) {
+            if constexpr (TEMPORAL) {
+              mbits = 0;  // same pixel <=> same residue modulo tP
+              int rem = c % p.tP;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (rem == t_mod) mbits |= (1u << i);
+                if (++rem == p.tP) rem = 0;
+              }
+            } else if (mrow != nullptr) {
               mbits = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -313,7 +360,15 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
             for (int i = 0; i < 32; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe));
           } else {
             uint32_t mbits = 0xffffffffu;
-            if (mrow != nullptr) {
+            if constexpr (TEMPORAL) {
+              mbits = 0;  // same pixel <=> same residue modulo tP
+              int rem = c % p.tP;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (rem == t_mod) mbits |= (1u << i);
+                if (++rem == p.tP) rem = 0;
+              }
+            } else if (mrow != nullptr) {
               mbits = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -383,20 +438,25 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
 
 static int g_attn_sms = 0;
 
-template <int DKA, int KV, int NWG, int STAGES>
+template <int DKA, int KV, int NWG, int STAGES, bool TEMPORAL>
 static int launch_attn(const AttnKParams& kp, cudaStream_t stream) {
   using Cfg = AttnCfg<DKA, KV, NWG, STAGES>;
   static_assert(Cfg::kSmemBytes <= 232448, "attention configuration exceeds the shared memory of an SM");
   static bool configured = false;
   if (!configured) {
-    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV, NWG, STAGES>,
+    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV, NWG, STAGES, TEMPORAL>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
+  if (g_attn_sms == 0) {
+    int dev = 0;
+    ASVA_CUDA_OK(cudaGetDevice(&dev));
+    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   int grid = (kp.total_items + NWG - 1) / NWG;
   if (grid > g_attn_sms) grid = g_attn_sms;
-  attn_tc_kernel<DKA, KV, NWG, STAGES><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
-  ASVA_CUDA_OK(cudaGetLastError());
+  ASVA_CUDA_OK(launch_k(attn_tc_kernel<DKA, KV, NWG, STAGES, TEMPORAL>, dim3(grid), dim3(Cfg::kThreads),
+                        Cfg::kSmemBytes, stream, 1, kp));
   return 0;
 }
 
@@ -462,8 +522,62 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
     if (rc != 0) return rc;
   }
   switch (dka) {
-    case 1: return launch_attn<1, 128, 2, 4>(kp, stream);
-    case 2: return launch_attn<2, 64, 2, 4>(kp, stream);
-    default: return launch_attn<3, 64, 1, 3>(kp, stream);
+    case 1: return launch_attn<1, 128, 2, 4, false>(kp, stream);
+    case 2: return launch_attn<2, 64, 2, 4, false>(kp, stream);
+    default: return launch_attn<3, 64, 1, 3, false>(kp, stream);
+  }
+}
+
+extern "C" int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                       int32_t d, float scale, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(qkv && out, "asva_temporal_attention: null operand");
+  ASVA_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "asva_temporal_attention: head dim %d unsupported", d);
+  ASVA_REQUIRE(B >= 1 && N >= 1 && heads >= 1 && F >= 1 && F <= 64, "asva_temporal_attention: bad shape (F=%d)", F);
+  ASVA_REQUIRE(scale > 0.f, "asva_temporal_attention: scale must be positive");
+  const int C = heads * d;
+  const int dka = (d + 63) / 64;
+  const int kv = (dka == 1) ? 128 : 64;
+  int P = kv / F;  // pixels per tile: tP * tF rows are queries and keys at once
+  if (P > N) P = N;
+  ASVA_REQUIRE(P >= 1, "asva_temporal_attention: F=%d exceeds the key tile of %d", F, kv);
+
+  AttnKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.out = reinterpret_cast<__nv_bfloat16*>(out);
+  kp.ldo = C;
+  kp.R = F * N;
+  kp.Nk = P * F;
+  kp.d = d;
+  kp.dN = ((d + 15) / 16) * 16;
+  kp.heads = heads;
+  kp.mask_rows = 1;
+  kp.ksteps_qk = (d + 15) / 16;
+  kp.nvb = (kp.dN + 63) / 64;
+  kp.scale_log2 = scale * 1.4426950408889634f;
+  kp.tP = P;
+  kp.tF = F;
+  kp.tN = N;
+  kp.tPB = (N + P - 1) / P;
+  kp.n_qt = kp.tPB;
+  const int64_t items = (int64_t)kp.tPB * heads * B;
+  ASVA_REQUIRE(items < (1ll << 30), "asva_temporal_attention: too many tiles");
+  kp.total_items = (int)items;
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  for (int part = 0; part < 3; ++part) {
+    uint64_t dims[5] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)F, (uint64_t)B};
+    uint64_t strides[4] = {(uint64_t)d * 2u, (uint64_t)3 * C * 2u, (uint64_t)N * 3 * C * 2u,
+                           (uint64_t)F * N * 3 * C * 2u};
+    uint32_t box[5] = {64u, 1u, (uint32_t)P, (uint32_t)F, 1u};
+    uint32_t el[5] = {1u, 1u, 1u, 1u, 1u};
+    CUtensorMap* tm = part == 0 ? &kp.tmQ : (part == 1 ? &kp.tmKV : &kp.tmV);
+    int rc = make_tmap_bf16(tm, base + (int64_t)part * C, 5, dims, strides, box, el);
+    if (rc != 0) return rc;
+  }
+  switch (dka) {
+    case 1: return launch_attn<1, 128, 2, 4, true>(kp, stream);
+    case 2: return launch_attn<2, 64, 2, 4, true>(kp, stream);
+    default: return launch_attn<3, 64, 1, 3, true>(kp, stream);
   }
 }

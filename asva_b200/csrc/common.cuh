@@ -20,6 +20,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the step is launched with the programmatic-serialization attribute
+// (host_common.h: launch_k), so its CTAs may start while the previous kernel of the stream is still draining.
+// pdl_trigger() lets the NEXT kernel begin launching; pdl_wait() blocks until the PREVIOUS kernel has completed and
+// its writes are visible - it must precede the first access to anything an earlier kernel produced. Both are no-ops
+// for a kernel launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -322,6 +332,15 @@ __device__ __forceinline__ void bulk_wait() {
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------

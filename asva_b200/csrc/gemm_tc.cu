@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   uint64_t* res_empty_bar = res_full_bar + 2 * kResSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 2 * kResSlots);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are read from here on
 
   // The producer and MMA loops run in one thread each and are paced by their own instruction and mbarrier latency,
   // so they are written for a minimal dependent-instruction count: ring position kept as (stage, phase) counters,
@@ -479,6 +481,8 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
                                                               int add_div, const __nv_bfloat16* res0, int64_t ld0,
                                                               const __nv_bfloat16* res1, int64_t ld1, void* out,
                                                               int64_t ldo, int out_fp32) {
+  pdl_trigger();
+  pdl_wait();
   const int nchunk = N >> 3;
   const int64_t total = M * nchunk;
   const int64_t plane = M * static_cast<int64_t>(N);
@@ -655,24 +659,7 @@ static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t strea
   }
   const int want = kp.total_tiles * CG;
   const int grid = want < max_ctas ? want : max_ctas;
-  if (CG == 1) {
-    gemm_tc_kernel<BN, GEGLU, CG><<<grid, kGemmThreads, smem_bytes, stream>>>(kp);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(kGemmThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute at;
-    at.id = cudaLaunchAttributeClusterDimension;
-    at.val.clusterDim.x = 2;
-    at.val.clusterDim.y = 1;
-    at.val.clusterDim.z = 1;
-    cfg.attrs = &at;
-    cfg.numAttrs = 1;
-    ASVA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, GEGLU, CG>, kp));
-  }
+  ASVA_CUDA_OK(launch_k(gemm_tc_kernel<BN, GEGLU, CG>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, CG, kp));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -939,10 +926,10 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   const int64_t chunks = M * (d->N / 8);
   int64_t blocks = (chunks + 255) / 256;
   if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
-  splitk_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
-      reinterpret_cast<const float*>(d->ws), plan.split, M, d->N, d->bias, d->add.ptr, d->add.ld,
-      d->add.div > 0 ? d->add.div : 1, reinterpret_cast<const __nv_bfloat16*>(res[0]), res_ld[0],
-      reinterpret_cast<const __nv_bfloat16*>(res[1]), res_ld[1], d->out, d->ldo, d->out_fp32);
+  ASVA_CUDA_OK(launch_k(splitk_finalize_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1,
+                        reinterpret_cast<const float*>(d->ws), plan.split, M, d->N, d->bias, d->add.ptr, d->add.ld,
+                        d->add.div > 0 ? d->add.div : 1, reinterpret_cast<const __nv_bfloat16*>(res[0]), res_ld[0],
+                        reinterpret_cast<const __nv_bfloat16*>(res[1]), res_ld[1], d->out, d->ldo, d->out_fp32));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/asva_b200.h"
 
@@ -25,6 +26,37 @@ enum { TMAP_BF16 = 0, TMAP_F32 = 1 };
 enum { TMAP_SW_NONE = 0, TMAP_SW64 = 1, TMAP_SW128 = 2 };
 int make_tmap(CUtensorMap* out, const void* base, int dtype, int swizzle, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+
+// Kernel launch with the programmatic-dependent-launch attribute (and optionally a cluster of `cluster_x` CTAs).
+// ASVA_NO_PDL=1 in the environment launches plainly (A/B measurements, debugging).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define ASVA_CUDA_OK(expr)                                                                         \
   do {                                                                                             \

@@ -12,6 +12,8 @@ namespace asva {
 __global__ void __launch_bounds__(256) conv_in_im2col_kernel(const float* __restrict__ lat,
                                                              __nv_bfloat16* __restrict__ out, int B, int Bs, int Cl,
                                                              int F, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(B) * F * h * w * 8;  // 8 chunks of 8 columns per row
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -50,6 +52,8 @@ __global__ void __launch_bounds__(256) conv_out_finish_kernel(const float* __res
                                                               const float* __restrict__ wt,
                                                               const float* __restrict__ bt, float* __restrict__ out,
                                                               int B, int Co, int F, int hw) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(B) * F * hw;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -80,6 +84,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
                                                            const __nv_bfloat16* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out,
                                                            int M, int N, int K, int act_in, int act_out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float xs[];  // [4][K]
   const int m0 = blockIdx.y * 4;
   const int mrows = min(4, M - m0);
@@ -120,6 +126,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 
 __global__ void timestep_features_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim,
                                          int flip) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= B * half) return;
@@ -139,12 +147,11 @@ __global__ void timestep_features_kernel(const float* __restrict__ t, float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// Temporal attention core: one warp per (batch, pixel, head); F x F scores over the frame axis.
-// q/k/v rows are staged in shared memory as fp32 with odd row pitch (bank-conflict free).
-// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) temporal_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                             __nv_bfloat16* __restrict__ out, int B, int F, int N,
                                                             int heads, int d, float scale, int64_t total_items) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pitch = d + 1;
@@ -225,6 +232,8 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__
                                                        const float* __restrict__ coef,
                                                        const int32_t* __restrict__ slots, int C, int F, int hw,
                                                        int plms) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t per_c = static_cast<int64_t>(F - 1) * hw;
   const int64_t total = per_c * C;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -259,8 +268,7 @@ extern "C" int asva_conv_in_im2col(const float* latents, void* out, int32_t B, i
   ASVA_REQUIRE(Cl >= 1 && 9 * Cl <= 64, "asva_conv_in_im2col: Cl=%d unsupported (9*Cl must be <= 64)", Cl);
   ASVA_REQUIRE(B >= 1 && Bs >= 1 && F >= 1 && h >= 1 && w >= 1, "asva_conv_in_im2col: empty problem");
   const int64_t total = static_cast<int64_t>(B) * F * h * w * 8;
-  conv_in_im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      latents, reinterpret_cast<__nv_bfloat16*>(out), B, Bs, Cl, F, h, w);
+  ASVA_CUDA_OK(launch_k(conv_in_im2col_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1, latents, reinterpret_cast<__nv_bfloat16*>(out), B, Bs, Cl, F, h, w));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -272,8 +280,8 @@ extern "C" int asva_conv_out_finish(const float* y, int32_t ldy, const float* wt
   ASVA_REQUIRE(y && wt && bt && out, "asva_conv_out_finish: null operand");
   ASVA_REQUIRE(Co >= 1 && Co <= 8 && ldy >= Co, "asva_conv_out_finish: Co=%d unsupported", Co);
   const int64_t total = static_cast<int64_t>(B) * F * h * w;
-  conv_out_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(y, ldy, wt, bt, out, B, Co,
-                                                                                         F, h * w);
+  ASVA_CUDA_OK(launch_k(conv_out_finish_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1, y, ldy, wt, bt, out, B, Co,
+                                                                                         F, h * w));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -290,8 +298,7 @@ extern "C" int asva_small_linear(const float* x, const void* w, const float* bia
     configured = true;
   }
   dim3 grid((N + 7) / 8, (M + 3) / 4);
-  small_linear_kernel<<<grid, 256, static_cast<size_t>(4) * K * sizeof(float), stream>>>(
-      x, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N, K, act_in, act_out);
+  ASVA_CUDA_OK(launch_k(small_linear_kernel, dim3(grid), dim3(256), static_cast<size_t>(4) * K * sizeof(float), stream, 1, x, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N, K, act_in, act_out));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -302,30 +309,7 @@ extern "C" int asva_timestep_features(const float* t, float* out, int32_t B, int
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ASVA_REQUIRE(t && out && B >= 1 && dim >= 2 && dim % 2 == 0, "asva_timestep_features: bad arguments");
   const int total = B * (dim / 2);
-  timestep_features_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, out, B, dim, flip_sin_to_cos);
-  ASVA_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
-                                       int32_t d, float scale, asva_stream_t stream_) {
-  using namespace asva;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ASVA_REQUIRE(qkv && out, "asva_temporal_attention: null operand");
-  ASVA_REQUIRE(d % 8 == 0 && d >= 8 && F >= 1 && F <= 64, "asva_temporal_attention: d=%d F=%d unsupported", d, F);
-  const size_t smem = static_cast<size_t>(4) * (3 * F * (d + 1) + F * F) * sizeof(float);
-  ASVA_REQUIRE(smem <= 200 * 1024, "asva_temporal_attention: F=%d d=%d needs %zu B smem", F, d, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    ASVA_CUDA_OK(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  const int64_t items = static_cast<int64_t>(B) * N * heads;
-  int64_t blocks = (items + 3) / 4;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  temporal_attn_kernel<<<static_cast<unsigned>(blocks), 128, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), B, F, N, heads, d, scale,
-      items);
+  ASVA_CUDA_OK(launch_k(timestep_features_kernel, dim3((total + 127) / 128), dim3(128), 0, stream, 1, t, out, B, dim, flip_sin_to_cos));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -336,8 +320,8 @@ extern "C" int asva_cfg_ddim_step(const float* eps, int32_t k, float* latents, c
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ASVA_REQUIRE(eps && latents && coef && k >= 1 && k <= 3 && F >= 2, "asva_cfg_ddim_step: bad arguments");
   const int64_t total = static_cast<int64_t>(C) * (F - 1) * hw;
-  cfg_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(eps, k, latents, nullptr, coef,
-                                                                                  nullptr, C, F, hw, 0);
+  ASVA_CUDA_OK(launch_k(cfg_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1, eps, k, latents, nullptr, coef,
+                                                                                  nullptr, C, F, hw, 0));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -349,8 +333,8 @@ extern "C" int asva_cfg_plms_step(const float* eps, int32_t k, float* latents, f
   ASVA_REQUIRE(eps && latents && hist && coef && slots && k >= 1 && k <= 3 && F >= 2,
                "asva_cfg_plms_step: bad arguments");
   const int64_t total = static_cast<int64_t>(C) * (F - 1) * hw;
-  cfg_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(eps, k, latents, hist, coef, slots,
-                                                                                  C, F, hw, 1);
+  ASVA_CUDA_OK(launch_k(cfg_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1, eps, k, latents, hist, coef, slots,
+                                                                                  C, F, hw, 1));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }

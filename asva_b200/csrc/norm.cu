@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ pos,
                                                         __nv_bfloat16* __restrict__ out, int64_t M, int C, float eps,
                                                         int N, int F) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -111,6 +113,8 @@ __global__ void __launch_bounds__(256) gn_stats_stage1(const __nv_bfloat16* __re
                                                        const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
                                                        int splits, int cw, int rows_per_pass,
                                                        float* __restrict__ ws) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red[];  // [rows_per_pass][cw*8][2]
   const int Ctot = C0 + C1;
   const int nchunk = Ctot >> 3;
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(128) gn_stats_stage2(const float* __restrict__
                                                          int groups, int64_t rows, float eps,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   // one CTA per (instance, group): threads stride over splits x channels-in-group, fp64 reduction, then the
   // per-channel affine  y = x * scale + shift  (scale = rstd * gamma, shift = beta - mean * scale) is written
   __shared__ double red[2][4];
@@ -222,6 +228,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ stats, int img_per_inst, int h,
                                                        int w, int silu, int up, __nv_bfloat16* __restrict__ out,
                                                        int64_t total_chunks) {
+  pdl_trigger();
+  pdl_wait();
   const int Ctot = C0 + C1;
   const int nchunk = Ctot >> 3;
   const int ho = up ? 2 * h : h, wo = up ? 2 * w : w;
@@ -277,10 +285,10 @@ extern "C" int asva_layernorm(const void* x, const float* gamma, const float* be
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
   const int n = N > 0 ? N : 1, f = F > 0 ? F : 1;
 #define ASVA_LN_CASE(K) \
-  case K: layernorm_kernel<K><<<blocks, 256, 0, stream>>>(xp, gamma, beta, pos, op, M, C, eps, n, f); break;
+  case K: ASVA_CUDA_OK(launch_k(layernorm_kernel<K>, dim3(blocks), dim3(256), 0, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f)); break;
   switch ((C / 8 + 31) / 32) {
     ASVA_LN_CASE(1) ASVA_LN_CASE(2) ASVA_LN_CASE(3) ASVA_LN_CASE(4) ASVA_LN_CASE(5) ASVA_LN_CASE(6) ASVA_LN_CASE(7)
-    default: layernorm_kernel<8><<<blocks, 256, 0, stream>>>(xp, gamma, beta, pos, op, M, C, eps, n, f); break;
+    default: ASVA_CUDA_OK(launch_k(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f)); break;
   }
 #undef ASVA_LN_CASE
   ASVA_CUDA_OK(cudaGetLastError());
@@ -307,12 +315,12 @@ extern "C" int asva_groupnorm_stats(const void* x0, int32_t C0, const void* x1, 
   GnStatsPlan pl = gn_plan(n_inst, rows, Ctot);
   dim3 grid(pl.splits, n_inst, pl.cblocks);
   const size_t smem = static_cast<size_t>(pl.rows_per_pass) * pl.cw * 8 * 2 * sizeof(float);
-  gn_stats_stage1<<<grid, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x0), C0,
+  ASVA_CUDA_OK(launch_k(gn_stats_stage1, dim3(grid), dim3(256), smem, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x0), C0,
                                                reinterpret_cast<const __nv_bfloat16*>(x1), C1, rows, pl.splits,
-                                               pl.cw, pl.rows_per_pass, partial_ws);
+                                               pl.cw, pl.rows_per_pass, partial_ws));
   ASVA_CUDA_OK(cudaGetLastError());
-  gn_stats_stage2<<<n_inst * groups, 128, 0, stream>>>(partial_ws, n_inst, pl.splits, Ctot, groups, rows, eps, gamma,
-                                                        beta, stats);
+  ASVA_CUDA_OK(launch_k(gn_stats_stage2, dim3(n_inst * groups), dim3(128), 0, stream, 1, partial_ws, n_inst, pl.splits, Ctot, groups, rows, eps, gamma,
+                                                        beta, stats));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -332,9 +340,8 @@ extern "C" int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, 
   const int64_t total = static_cast<int64_t>(n_img) * ho * wo * (Ctot / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, stats,
-      n_inst > 0 ? n_img / n_inst : 1, h, w, silu, upsample, reinterpret_cast<__nv_bfloat16*>(out), total);
+  ASVA_CUDA_OK(launch_k(gn_apply_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, stats,
+      n_inst > 0 ? n_img / n_inst : 1, h, w, silu, upsample, reinterpret_cast<__nv_bfloat16*>(out), total));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
