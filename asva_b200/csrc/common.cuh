@@ -469,7 +469,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (torch F.gelu default): 0.5 x (1 + erf(x / sqrt 2)).  erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7:
+// 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1 / (1 + p |z|)) - two MUFU ops and ~12 FMA-pipe instructions, half of
+// erff()'s branch-free sequence; the epilogue of the GEGLU GEMM is bound by exactly this instruction count.
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.f);           // erf(|x| / sqrt 2)
+  const float half_x = 0.5f * x;
+  return fmaf(fabsf(half_x), erf_abs, half_x);         // 0.5 x + 0.5 |x| erf(|z|) = 0.5 x (1 + erf(z))
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
