@@ -26,7 +26,7 @@
 namespace asva {
 
 constexpr int kMaxStages = 8;
-constexpr int kResSlots = 2;          // residual-panel slots per epilogue group
+constexpr int kMaxResSlots = 4;       // residual-panel slots per epilogue group (runtime: n_res_slots)
 constexpr int kResSlotBytes = 8192;   // 128 rows x 32 bf16
 constexpr int kGemmThreads = 384;
 constexpr int kSmemLimit = 232448;    // 227 KB opt-in maximum per CTA
@@ -41,7 +41,7 @@ struct GemmKParams {
   SegK seg[ASVA_GEMM_MAX_SEG];
   int32_t box[3], trav[3], out_dims[3], tiles[3];
   int32_t rows_per_tile, N, n_out, num_kb, n_tiles_n, mn_tiles, total_tiles, split_k, kb_per_split;
-  int32_t n_stages, n_res, out_fp32, dbg;  // dbg (ASVA_GEMM_DBG): 1 = skip TMA loads, 2 = skip MMAs (timing only)
+  int32_t n_stages, n_res, n_res_slots, out_fp32, dbg;  // dbg (ASVA_GEMM_DBG): 1 = skip TMA loads, 2 = skip MMAs (timing only)
   const float* bias;
   const float* add_ptr;
   int64_t add_ld;
@@ -98,16 +98,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_stages = p.n_stages;
   uint8_t* res_ring = smem + n_stages * kSuperBytes;
-  uint8_t* out_ring = res_ring + (p.n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0);
+  uint8_t* out_ring = res_ring + 2 * p.n_res_slots * kResSlotBytes;
   const int out_slot_bytes = p.out_fp32 ? 16384 : 8192;
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_ring + 4 * out_slot_bytes);
   uint64_t* full_bar = bars;                     // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2 * kResSlots]
-  uint64_t* res_empty_bar = res_full_bar + 2 * kResSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 2 * kResSlots);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2 groups][kMaxResSlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 2 * kMaxResSlots);
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5;
@@ -124,10 +123,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 8 * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
-    for (int s = 0; s < 2 * kResSlots; ++s) {
-      mbar_init(&res_full_bar[s], 1);
-      mbar_init(&res_empty_bar[s], 4);   // one arrival per warp of the owning group
-    }
+    for (int s = 0; s < 2 * kMaxResSlots; ++s) mbar_init(&res_full_bar[s], 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmW);
@@ -284,30 +280,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       }
     }
     __syncwarp();
-  } else if (warp == 2) {
-    // ---------------- epilogue loader (residual panels) ----------------
-    if (lane == 0 && p.n_res > 0) {
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.rows_per_tile) * 64u;
-      uint32_t pc = 0, cnt[2] = {0u, 0u};
-      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
-        const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
-        const int n_panels = tile_panels<BN, GEGLU>(p, tc.n0);
-        for (int q = 0; q < n_panels; ++q) {
-          const uint32_t g = (pc + q) & 1u;
-          for (int i = 0; i < p.n_res; ++i) {
-            const uint32_t slot = g * kResSlots + cnt[g] % kResSlots;
-            const uint32_t ph = (cnt[g] / kResSlots) & 1u;
-            mbar_wait(&res_empty_bar[slot], ph ^ 1u);
-            mbar_arrive_expect_tx(&res_full_bar[slot], tx_bytes);
-            tma_load_4d(res_ring + slot * kResSlotBytes, i ? &p.tmR1 : &p.tmR0, &res_full_bar[slot],
-                        tc.n0 + q * 32, tc.o1, tc.o2, tc.o3);
-            ++cnt[g];
-          }
-        }
-        pc += n_panels;
-      }
-    }
-    __syncwarp();
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const uint32_t g = static_cast<uint32_t>(warp - 4) >> 2;
@@ -321,7 +293,44 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if constexpr (CG == 2) mbar_arrive_pair_leader(bar); else mbar_arrive(bar);
     };
     uint8_t* my_out = out_ring + g * 2 * out_slot_bytes;
-    uint32_t pc = 0, ocnt = 0, rcnt = 0, t = 0;
+    uint32_t pc = 0, ocnt = 0, t = 0;
+    // Residual operands: each group streams the residual panels of ITS OWN upcoming output panels through a private
+    // ring of D slots, D panels ahead of where it is working (across tile boundaries). One lane of the group issues
+    // the TMA loads; a slot is refilled right after the group barrier that follows its last read, so no "empty"
+    // barrier is needed, and no single thread has to issue the residual loads of both groups.
+    const uint32_t D = static_cast<uint32_t>(p.n_res_slots);
+    const bool pf_lane = (qd == 1) && (lane == 0) && (p.n_res > 0);
+    const uint32_t res_tx = static_cast<uint32_t>(p.rows_per_tile) * 64u;
+    uint32_t rslot = 0, rph = 0;              // consumer position in the ring
+    int pf_tile = tile0, pf_q = 0, pf_i = 0;  // producer position: next (tile, panel, residual) to fetch
+    uint32_t pf_pc = 0, pf_slot = 0;
+    TileCoord pf_tc = decode_tile<BN, CG>(p, tile0 < p.total_tiles ? tile0 : 0, rank);
+    int pf_np = tile_panels<BN, GEGLU>(p, pf_tc.n0);
+    auto pf_issue = [&]() {
+      while (pf_tile < p.total_tiles) {  // advance to the next panel this group owns
+        while (pf_q < pf_np && (((pf_pc + pf_q) & 1u) != g)) ++pf_q;
+        if (pf_q < pf_np) break;
+        pf_pc += pf_np;
+        pf_tile += tile_step;
+        pf_q = 0;
+        if (pf_tile < p.total_tiles) {
+          pf_tc = decode_tile<BN, CG>(p, pf_tile, rank);
+          pf_np = tile_panels<BN, GEGLU>(p, pf_tc.n0);
+        }
+      }
+      if (pf_tile >= p.total_tiles) return;
+      const uint32_t slot = g * kMaxResSlots + pf_slot;
+      mbar_arrive_expect_tx(&res_full_bar[slot], res_tx);
+      tma_load_4d(res_ring + (g * D + pf_slot) * kResSlotBytes, pf_i ? &p.tmR1 : &p.tmR0, &res_full_bar[slot],
+                  pf_tc.n0 + pf_q * 32, pf_tc.o1, pf_tc.o2, pf_tc.o3);
+      if (++pf_slot == D) pf_slot = 0;
+      if (++pf_i == p.n_res) {
+        pf_i = 0;
+        ++pf_q;
+      }
+    };
+    if (pf_lane)
+      for (uint32_t i = 0; i < D; ++i) pf_issue();
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
       const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
       const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
@@ -383,10 +392,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
           }
           for (int i = 0; i < p.n_res; ++i) {
-            const uint32_t slot = g * kResSlots + rcnt % kResSlots;
-            const uint32_t ph = (rcnt / kResSlots) & 1u;
-            mbar_wait(&res_full_bar[slot], ph);
-            const uint8_t* rp = res_ring + slot * kResSlotBytes;
+            mbar_wait(&res_full_bar[g * kMaxResSlots + rslot], rph);
+            const uint8_t* rp = res_ring + (g * D + rslot) * kResSlotBytes;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t lin = static_cast<uint32_t>(r) * 64u + j * 16u;
@@ -402,9 +409,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               v[8 * j + 6] = __float_as_uint(__uint_as_float(v[8 * j + 6]) + f3.x);
               v[8 * j + 7] = __float_as_uint(__uint_as_float(v[8 * j + 7]) + f3.y);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&res_empty_bar[slot]);
-            ++rcnt;
+            if (++rslot == D) {
+              rslot = 0;
+              rph ^= 1u;
+            }
           }
         } else {
           // tile columns [0,64) = value h, [64,128) = gate g; output = (h + bh) * gelu(g + bg)
@@ -435,6 +443,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         uint8_t* op = my_out + (ocnt & 1u) * out_slot_bytes;
         if (leader) bulk_wait_read<1>();  // the store that last used this slot has finished reading it
         named_bar_sync(1 + g, 128);
+        if (pf_lane)  // every warp of the group is past its reads of this panel's residual slots: refill them
+          for (int i = 0; i < p.n_res; ++i) pf_issue();
         if (!p.out_fp32) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       }
       pc += n_panels;
     }
-    if (leader) bulk_wait<0>();
+    if (leader) bulk_wait_read<0>();  // shared memory may be released; completion of the writes is the grid's completion
   }
   tc_fence_before();
   __syncthreads();
@@ -537,16 +547,30 @@ struct GemmPlan {
   int bn, split, stages, cg;
 };
 
-static int fixed_smem(int n_res, int out_fp32) {
-  return 1024 /*align*/ + kBarBytes + 4 * (out_fp32 ? 16384 : 8192) + (n_res > 0 ? 2 * kResSlots * kResSlotBytes : 0);
+static int fixed_smem(int res_slots, int out_fp32) {
+  return 1024 /*align*/ + kBarBytes + 4 * (out_fp32 ? 16384 : 8192) + 2 * res_slots * kResSlotBytes;
 }
-// ring stages of two 64-wide K blocks each
-static int stages_for(int bn, int cg, int n_res, int out_fp32) {
-  const int s = (kSmemLimit - fixed_smem(n_res, out_fp32)) / (2 * (16384 + (bn / cg) * 128));
+// ring stages of two 64-wide K blocks each, given the residual slots per epilogue group
+static int stages_with(int bn, int cg, int res_slots, int out_fp32) {
+  const int s = (kSmemLimit - fixed_smem(res_slots, out_fp32)) / (2 * (16384 + (bn / cg) * 128));
   return s > kMaxStages ? kMaxStages : s;
 }
-static int smem_for(int bn, int cg, int stages, int n_res, int out_fp32) {
-  return fixed_smem(n_res, out_fp32) + stages * 2 * (16384 + (bn / cg) * 128);
+// Shared memory split between the main-loop ring and the residual ring: as many residual slots (<= 4 per group) as
+// leave the main loop the stages it can use (3, or fewer for a short K loop), never fewer than 2 of either.
+static int res_slots_for(int bn, int cg, int n_res, int out_fp32, int num_kb) {
+  if (n_res == 0) return 0;
+  int want = (num_kb + 1) / 2;
+  if (want > 3) want = 3;
+  if (want < 2) want = 2;
+  for (int d = kMaxResSlots; d > 2; --d)
+    if (stages_with(bn, cg, d, out_fp32) >= want) return d;
+  return 2;
+}
+static int stages_for(int bn, int cg, int n_res, int out_fp32, int num_kb) {
+  return stages_with(bn, cg, res_slots_for(bn, cg, n_res, out_fp32, num_kb), out_fp32);
+}
+static int smem_for(int bn, int cg, int stages, int res_slots, int out_fp32) {
+  return fixed_smem(res_slots, out_fp32) + stages * 2 * (16384 + (bn / cg) * 128);
 }
 
 // Cost model (cycles) behind the automatic tile-width / CTA-pair / split-K choice. Per 64-wide K block a CTA needs
@@ -609,7 +633,7 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
         const int kbps = (num_kb + sp - 1) / sp;
         if ((num_kb + kbps - 1) / kbps != sp) continue;  // would leave an empty split
         const int nr = sp > 1 ? 0 : n_res;
-        if (stages_for(bn, cg, nr, sp > 1 ? 1 : d->out_fp32) < 2) continue;
+        if (stages_for(bn, cg, nr, sp > 1 ? 1 : d->out_fp32, (num_kb + sp - 1) / sp) < 2) continue;
         const double c = plan_cost(bn, cg, sp, d->N, m_tiles, num_kb, M, sms);
         if (c < best_cost) {
           best_cost = c;
@@ -621,7 +645,7 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
     }
   }
   const int nr = best.split > 1 ? 0 : n_res;
-  best.stages = stages_for(best.bn, best.cg, nr, best.split > 1 ? 1 : d->out_fp32);
+  best.stages = stages_for(best.bn, best.cg, nr, best.split > 1 ? 1 : d->out_fp32, (num_kb + best.split - 1) / best.split);
   const int cap = env_int("ASVA_GEMM_STAGES");
   if (cap >= 2 && best.stages > cap) best.stages = cap;
   return best;
@@ -853,6 +877,7 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   kp.n_res = split ? 0 : n_res;
   kp.out_fp32 = split ? 1 : d->out_fp32;
   kp.n_stages = plan.stages;
+  kp.n_res_slots = res_slots_for(bn, plan.cg, kp.n_res, kp.out_fp32, kp.kb_per_split);
   kp.dbg = env_int("ASVA_GEMM_DBG");
   ASVA_REQUIRE(plan.stages >= 2, "asva_gemm: no shared memory left for a pipeline (block_n=%d)", bn);
   ASVA_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "asva_gemm: unsupported block_n=%d", bn);
@@ -919,7 +944,7 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   ASVA_REQUIRE(m_tiles * kp.n_tiles_n * plan.split < (1ll << 31), "asva_gemm: too many tiles");
   kp.mn_tiles = (int)(((m_tiles + plan.cg - 1) / plan.cg) * kp.n_tiles_n);  // pairs of m tiles when cg == 2
   kp.total_tiles = kp.mn_tiles * plan.split;
-  const int smem = smem_for(bn, plan.cg, plan.stages, kp.n_res, kp.out_fp32);
+  const int smem = smem_for(bn, plan.cg, plan.stages, kp.n_res_slots, kp.out_fp32);
   const int rc = plan.cg == 2 ? dispatch_gemm<2>(kp, bn, d->geglu != 0, smem, stream)
                               : dispatch_gemm<1>(kp, bn, d->geglu != 0, smem, stream);
   if (rc != 0 || !split) return rc;
