@@ -10,12 +10,12 @@
 //   warp 1       TMEM allocator + single-thread tcgen05.mma issuer (8 x K=16 per stage, one barrier wait and one
 //                commit per stage, the next stage's barrier probed before the MMAs are issued); the accumulator is
 //                double buffered in TMEM (2 x BN columns), so tile t+1's main loop runs under tile t's epilogue
-//   warp 2       epilogue loader: streams the residual operands of each 32-column output panel through a second
-//                TMA ring (64B-swizzled [128 rows][32 bf16] slots), ahead of the epilogue warps
 //   warps 4..11  epilogue, two groups of 4 warps (warp % 4 = TMEM lane quadrant, thread = output row); the groups
 //                take alternate 32-column panels: tcgen05.ld -> + bias / per-row-block addend / residual panels
 //                (from smem) [or GEGLU] -> swizzled staging slot -> one elected thread issues the TMA store
-//                (tails are clipped by the tensor map). Staging slots are double buffered per group.
+//                (tails are clipped by the tensor map). Staging slots are double buffered per group. Residual
+//                operands arrive by TMA in a private ring per group (64B-swizzled [128 rows][32 bf16] slots) that one
+//                lane of the group keeps filled D panels ahead of the group's own position, across tile boundaries.
 // Split-K (small-M, long-K problems): tiles are (split, m, n) triples writing fp32 partial tiles to a scratch
 // buffer through the same TMA-store path; splitk_finalize_kernel then reduces them and applies the epilogue.
 #include "common.cuh"
