@@ -258,7 +258,43 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__
   lat[idx] = cs * lat[idx] + ce * ehat;
 }
 
+// ------------------------------------------------------------------------------------------------
+// conv_temp operand gather for levels whose frames have fewer than 128 pixels: rows [y_f | y_max(f-1,0) | y_0]
+// so that the temporal conv is one plain GEMM with full 128-row tiles (instead of tiles of one frame's few pixels).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tconv_gather_kernel(const __nv_bfloat16* __restrict__ y,
+                                                           __nv_bfloat16* __restrict__ out, int F, int N, int C,
+                                                           int64_t total_chunks) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  const int nchunk = 3 * C / 8;
+  const int ch = static_cast<int>(i % nchunk);
+  const int64_t row = i / nchunk;
+  const int part = ch / (C / 8), c = (ch % (C / 8)) * 8;
+  const int64_t bf = row / N;
+  const int n = static_cast<int>(row % N), f = static_cast<int>(bf % F);
+  const int64_t b = bf / F;
+  const int fs = part == 0 ? f : (part == 1 ? (f > 0 ? f - 1 : 0) : 0);
+  const uint4 u = *reinterpret_cast<const uint4*>(y + ((b * F + fs) * N + n) * C + c);
+  *reinterpret_cast<uint4*>(out + row * 3 * C + part * C + c) = u;
+}
+
 }  // namespace asva
+
+extern "C" int asva_tconv_gather(const void* y, void* out, int32_t B, int32_t F, int32_t N, int32_t C,
+                                 asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(y && out, "asva_tconv_gather: null operand");
+  ASVA_REQUIRE(B >= 1 && F >= 1 && N >= 1 && C >= 8 && C % 8 == 0, "asva_tconv_gather: bad shape");
+  const int64_t total = static_cast<int64_t>(B) * F * N * (3 * C / 8);
+  ASVA_CUDA_OK(launch_k(tconv_gather_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1,
+                        reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(out), F, N, C,
+                        total));
+  return 0;
+}
 
 extern "C" int asva_conv_in_im2col(const float* latents, void* out, int32_t B, int32_t Bs, int32_t Cl, int32_t F,
                                    int32_t h, int32_t w, asva_stream_t stream_) {

@@ -294,6 +294,17 @@ class UNetEngine:
 
     # ------------------------------------------------------------------------------------------ building blocks
     def _ffconv_tail(self, cv: _Conv, y, out, B, F, N, tproj=None, res1=None):
+        if N < 64:
+            # a frame is smaller than half a tile: gather the three taps so the GEMM gets full 128-row tiles
+            # (one-frame tiles would leave 3/4 of every MMA empty and re-read the weights 4x as often)
+            C = cv.cout
+            g = self.buf("tc_gather", (B * F * N, 3 * C))
+            self.be.tconv_gather(y, g, B, F, N, C)
+            sp = ops.spec_linear(g, cv.w4[:, :3 * C], out, bias=cv.bt, res0=y, res1=res1)
+            if tproj is not None:
+                sp.add = ops.RowAdd(tproj, self._tproj_total, div=F * N)
+            self.be.gemm(sp)
+            return
         self.be.gemm(ops.spec_tconv(y, cv.w4, out, B=B, F=F, N=N, bias=cv.bt, tproj=tproj,
                                     tproj_ld=self._tproj_total, res1=res1))
 

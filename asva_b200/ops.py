@@ -425,6 +425,13 @@ class CudaBackend:
                    "asva_conv_in_im2col")
         self.launches += 1
 
+    def tconv_gather(self, y, out, B, F, N, C) -> None:
+        self._chk_dev(y, out)
+        with self._timed('misc'):
+            _lib.check(self.lib.asva_tconv_gather(y.data_ptr(), out.data_ptr(), B, F, N, C, self._stream()),
+                       "asva_tconv_gather")
+        self.launches += 1
+
     def conv_out_finish(self, y, ldy, wt, bt, out, B, Co, F, h, w) -> None:
         self._chk_dev(y, wt, bt, out)
         with self._timed('misc'):

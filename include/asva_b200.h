@@ -170,6 +170,11 @@ int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, int32_t C1,
 int asva_conv_in_im2col(const float* latents, void* out, int32_t B, int32_t Bs, int32_t Cl, int32_t F, int32_t h,
                         int32_t w, asva_stream_t stream);
 
+/* conv_temp operand gather (utils.py:43-52 builds exactly this with index + cat): y bf16 [B][F][N][C] ->
+ * out bf16 [B*F*N][3C] = [y_f | y_max(f-1,0) | y_0].  Used only where a frame has fewer than 128 pixels, so that the
+ * temporal conv runs as one plain asva_gemm with full tiles; the larger levels read the three taps in place. */
+int asva_tconv_gather(const void* y, void* out, int32_t B, int32_t F, int32_t N, int32_t C, asva_stream_t stream);
+
 /* conv_out back end: y fp32 [B*F*h*w][ldy] (first Co columns valid) -> conv_temp (Linear(3Co -> Co) over
  * [frame 0 | previous frame | current frame], utils.py:43-53) -> fp32 [B][Co][F][h][w]. */
 int asva_conv_out_finish(const float* y, int32_t ldy, const float* wt, const float* bt, float* out, int32_t B,

@@ -178,6 +178,12 @@ class SimBackend:
         o[:, : 9 * Cl] = t
         out.view(B * F * h * w, 64).copy_(o.to(out.dtype))
 
+    def tconv_gather(self, y, out, B, F, N, C) -> None:
+        self.launches += 1
+        v = y.view(B, F, N, C)
+        prev = torch.cat([v[:, :1], v[:, :-1]], dim=1)
+        out.view(B, F, N, 3 * C).copy_(torch.cat([v, prev, v[:, :1].expand_as(v)], dim=3))
+
     def conv_out_finish(self, y, ldy, wt, bt, out, B, Co, F, h, w) -> None:
         self.launches += 1
         hw = h * w

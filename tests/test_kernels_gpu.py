@@ -322,6 +322,17 @@ def test_conv_in_and_out(cuda_backend):
     _report("conv_out_finish", r_cu.view(-1, w), r_ref.view(-1, w), 1e-5)
 
 
+@pytest.mark.parametrize("B,F,N,C", [(2, 12, 16, 1280), (1, 5, 7, 64), (2, 1, 4, 320)])
+def test_tconv_gather_conv_in_group(cuda_backend, B, F, N, C):
+    y = _rand((B * F * N, C), 70)
+    got = torch.zeros(B * F * N, 3 * C, dtype=torch.bfloat16, device=DEV)
+    ref = torch.zeros_like(got)
+    cuda_backend.tconv_gather(y, got, B, F, N, C)
+    SimBackend().tconv_gather(y, ref, B, F, N, C)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)  # pure data movement: bit exact
+
+
 @pytest.mark.parametrize("M,N,K,ai,ao", [(2, 1280, 320, 0, 1), (2, 1280, 1280, 0, 0), (2, 18560, 1280, 1, 0),
                                          (12, 320, 320, 0, 1), (5, 77, 64, 1, 1)])
 def test_small_linear(cuda_backend, M, N, K, ai, ao):

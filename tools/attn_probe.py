@@ -43,12 +43,79 @@ def make(name):
                         kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d))
 
 
+def sweep(out_path):
+    """BASELINE.json config 5: spatial 32^2..64^2 tokens x head dims, temporal 8..24 frames, cross-attention 1..256 keys.
+    Core FLOPs = 4 Nq Nk d per (group, head); bytes = Q + O + K + V in bf16."""
+    import math as _m
+    be = ops.backend()
+    H = 8
+    lines = ["| kind | tokens / frames / keys | C | d | us | core TFLOP/s | Q+O+KV GB/s |", "|---|---|---|---|---|---|---|"]
+
+    def timeit(fn):
+        fn()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(5):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 200
+
+    B, F = 2, 12
+    for side in (32, 48, 64):
+        for C in (320, 640, 1280):
+            d, N = C // H, side * side
+            G, R, Nk = B, F * N, N
+            q, kv = rnd((G * R, C), 1), rnd((G * Nk, 2 * C), 2)
+            o = torch.zeros(G * R, C, dtype=torch.bfloat16, device=DEV)
+            sp = ops.AttnSpec(q=q, kv=kv, out=o, G=G, heads=H, R=R, Nk=Nk, d=d, dpad=((d + 63) // 64) * 64, ldq=C,
+                              ldkv=2 * C, ldo=C, kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1 / _m.sqrt(d))
+            us = timeit(lambda: be.attention(sp))
+            fl, by = 4.0 * G * R * Nk * C, 2.0 * (2 * G * R * C + 2 * G * Nk * C)
+            lines.append(f"| spatial (first-frame keys) | {side}x{side} | {C} | {d} | {us:.1f} | {fl / us / 1e6:.0f} | {by / us / 1e3:.0f} |")
+            print(lines[-1], flush=True)
+            del q, kv, o
+    for Ft in (8, 12, 16, 24):
+        for C, N in ((320, 1024), (640, 256), (1280, 64)):
+            d = C // H
+            qkv = rnd((B * Ft * N, 3 * C), 3)
+            o = torch.zeros(B * Ft * N, C, dtype=torch.bfloat16, device=DEV)
+            us = timeit(lambda: be.temporal_attention(qkv, o, B, Ft, N, H, d, 1 / _m.sqrt(d)))
+            fl, by = 4.0 * B * N * Ft * Ft * C, 2.0 * 4 * B * Ft * N * C
+            lines.append(f"| temporal | {Ft} frames x {N} px | {C} | {d} | {us:.1f} | {fl / us / 1e6:.1f} | {by / us / 1e3:.0f} |")
+            print(lines[-1], flush=True)
+    for Nk in (1, 25, 77, 229, 256):
+        for C, N in ((320, 1024), (640, 256), (1280, 64)):
+            d = C // H
+            G, R = B * F, N
+            q, kv = rnd((G * R, C), 4), rnd((G * Nk, 2 * C), 5)
+            o = torch.zeros(G * R, C, dtype=torch.bfloat16, device=DEV)
+            sp = ops.AttnSpec(q=q, kv=kv, out=o, G=G, heads=H, R=R, Nk=Nk, d=d, dpad=((d + 63) // 64) * 64, ldq=C,
+                              ldkv=2 * C, ldo=C, kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1 / _m.sqrt(d))
+            us = timeit(lambda: be.attention(sp))
+            fl, by = 4.0 * G * R * Nk * C, 2.0 * (2 * G * R * C + 2 * G * Nk * C)
+            lines.append(f"| cross | {Nk} keys x {N} queries x {G} frames | {C} | {d} | {us:.1f} | {fl / us / 1e6:.1f} | {by / us / 1e3:.0f} |")
+            print(lines[-1], flush=True)
+    if out_path:
+        with open(out_path, "w") as f:
+            f.write("\n".join(lines) + "\n")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", action="store_true", help="the BASELINE.json config-5 attention microbenchmark sweep")
     ap.add_argument("--shapes", default=",".join(k for k in SHAPES if not k.endswith("_hr")))
     ap.add_argument("--single", default="")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
+    if args.sweep:
+        sweep(args.out)
+        return
     be = ops.backend()
     if args.single:
         s = make(args.single)
