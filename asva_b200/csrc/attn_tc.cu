@@ -18,6 +18,7 @@
 // (avgen/models/unets/utils.py:151-153 and diffusers AttnProcessor2_0).
 #include "common.cuh"
 #include "host_common.h"
+#include <stdlib.h>
 #include <string.h>
 
 namespace asva {
@@ -33,9 +34,12 @@ struct AttnKParams {
   int32_t nvb;        // number of 64-wide V column blocks = ceil(dN/64)
   int32_t n_qt;       // query tiles per (group, head)
   int32_t total_items;
+  long long* trace;         // ASVA_ATTN_TRACE=1: per-phase clock64 sums of block 0, warpgroup 0, thread 0 (debug)
   int32_t tP, tF, tN, tPB;  // temporal mode: pixels per tile, frames, pixels per frame, pixel blocks per clip
   float scale_log2;   // scale * log2(e)
 };
+
+constexpr int kPolyOf8 = 3;  // of every 8 exponentials of an unmasked tile, this many avoid the MUFU pipe
 
 template <int DKA, int KV, int NWG, int STAGES>
 struct AttnCfg {
@@ -44,10 +48,11 @@ struct AttnCfg {
   static constexpr int kVBytes = DKA * KV * 128;  // nvb <= DKA
   static constexpr int kStageBytes = kKBytes + kVBytes;
   static constexpr int kPBytes = (KV / 64) * 128 * 128;
-  static constexpr int kONCols = DKA == 1 ? 64 : (DKA == 2 ? 128 : 192);  // TMEM columns reserved per O accumulator
+  static constexpr int kONCols = DKA * 64 + 16;  // TMEM columns per O accumulator + the 16 row-sum columns after it
   static constexpr int kTmemNeed = NWG * (KV + kONCols);
   static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = NWG * (kQBytes + kPBytes) + STAGES * kStageBytes + 1024 + 256;
+  static constexpr int kOnesBytes = 2048;  // 16 x 64 bf16 ones: B operand of the row-sum MMA
+  static constexpr int kSmemBytes = NWG * (kQBytes + kPBytes) + STAGES * kStageBytes + kOnesBytes + 256;
   static constexpr int kThreads = 64 + 128 * NWG + (NWG > 1 ? 32 : 0);  // + the second MMA-issuing warp
 };
 
@@ -55,6 +60,21 @@ __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2, flush-to-zer
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f through the 1.5 * 2^23 magic number,
+// degree-3 minimax 2^f on [-0.5, 0.5] (relative error 7.7e-5, far below the bf16 rounding of P), n added into the
+// exponent field. The softmax of the spatial attention is bound by the MUFU pipe (measured: ~12 cycles per warp-wide
+// ex2 with two warps per scheduler), so a share of the exponentials is computed this way instead, as in
+// FlashAttention-4.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float q = fmaf(0.05508868f, f, 0.24260405f);
+  q = fmaf(q, f, 0.69327623f);
+  q = fmaf(q, f, 0.99992895f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
 }
 
 // idesc for P(bf16, K-major, from smem) x V(bf16, MN-major): b_major bit 16 set
@@ -76,11 +96,18 @@ template <int DKA, int KV, int NWG, int STAGES, bool TEMPORAL>
 __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<DKA, KV, NWG, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // the dynamic shared memory of a kernel without static shared memory starts at the (1024-byte aligned) base of the
+  // CTA's window; the 128B-swizzled tiles need that alignment and there is no room for slack - checked, not assumed
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("[asva] attention: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem;                                // [NWG][kQBytes]
   uint8_t* sKV = sQ + NWG * Cfg::kQBytes;            // [STAGES][K | V]
   uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;     // [NWG][kPBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NWG * Cfg::kPBytes);
+  uint8_t* sOnes = sP + NWG * Cfg::kPBytes;          // [16][64] bf16 1.0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + Cfg::kOnesBytes);
   uint64_t* q_full = bars;              // [2]  Q tile of the warpgroup's item landed
   uint64_t* q_free = bars + 2;          // [2]  every S = Q K^T of the item has been issued and completed
   uint64_t* s_full = bars + 4;          // [2]
@@ -118,6 +145,9 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
+  fence_proxy_async_smem();
   if constexpr (TEMPORAL) {
     // the boxes write tP*tF rows; the rows above them are multiplied too (as masked keys / unused queries) and must
     // not hold NaN bit patterns: clear Q and the key ring once
@@ -196,26 +226,38 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
     // ---------------- MMA issuers: one thread per warpgroup (warp 1 -> warpgroup 0, the last warp -> warpgroup 1), so a
     // warpgroup's S = Q K^T never queues behind the other warpgroup's barrier waits ----------------
     const int w = (warp == 1) ? 0 : 1;
-    if (lane == 0 && w < NWG) {
+    if (w < NWG) {
+      // warp-uniform loop: every lane runs it with identical values, the tcgen05 instructions are predicated on one
+      // elected lane - the issue cost per MMA (descriptor adds in uniform registers) is what paces this warp
+      const uint32_t el = elect_one();
       constexpr uint32_t idesc_s = make_idesc_bf16(128, KV);
+      constexpr uint32_t idesc_l = make_idesc_bf16(128, 16);
       const uint32_t idesc_o = make_idesc_bf16_bmn(128, static_cast<uint32_t>(p.dN));
-      const uint32_t q_addr = smem_u32(sQ + w * Cfg::kQBytes);
-      const uint32_t p_addr = smem_u32(sP + w * Cfg::kPBytes);
-      const uint32_t kv_addr0 = smem_u32(sKV);
+      constexpr uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);          // K-major, SW128
+      constexpr uint64_t desc_hi_mn = desc_hi | (static_cast<uint64_t>((KV * 128u) >> 4) << 16);  // MN-major: LBO
+      auto lo = [](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
+      const uint32_t q_lo = lo(smem_u32(sQ + w * Cfg::kQBytes)) | (1u << 16);
+      const uint32_t p_lo = lo(smem_u32(sP + w * Cfg::kPBytes)) | (1u << 16);
+      const uint32_t kv_lo0 = lo(smem_u32(sKV));
+      const uint64_t ones_desc = desc_hi | (lo(smem_u32(sOnes)) | (1u << 16));
       const uint32_t tmem_s = tmem_base + w * KV;
       const uint32_t tmem_o = tmem_base + NWG * KV + w * Cfg::kONCols;
+      const uint32_t tmem_l = tmem_o + p.dN;
+      const uint32_t kvf0 = smem_u32(kv_full), kve0 = smem_u32(kv_empty);
+      const uint32_t sfull = smem_u32(&s_full[w]), pfull = smem_u32(&p_full[w]), pvdone = smem_u32(&pv_done[w]);
+      const uint32_t qfree = smem_u32(&q_free[w]), qfull = smem_u32(&q_full[w]), ofree = smem_u32(&o_free[w]);
       uint32_t cnt = 0;  // key tiles finished (phase of p_full / pv_done)
       auto issue_s = [&](uint32_t pos) {
         const uint32_t s = pos % STAGES, ph = (pos / STAGES) & 1u;
-        mbar_wait(&kv_full[s], ph);
+        mbar_wait_a(kvf0 + 8u * s, ph);
         tc_fence_after();
-        const uint32_t k_addr = kv_addr0 + s * Cfg::kStageBytes;
+        const uint32_t k_lo = (kv_lo0 + s * (Cfg::kStageBytes >> 4)) | (1u << 16);
         for (int ks = 0; ks < p.ksteps_qk; ++ks) {
-          const uint32_t a = ks >> 2, o = (ks & 3) * 32u;
-          umma_bf16_ss(tmem_s, make_sdesc_sw128(q_addr + a * 128u * 128u + o),
-                       make_sdesc_sw128(k_addr + a * KV * 128u + o), idesc_s, ks != 0 ? 1u : 0u);
+          const uint32_t off = static_cast<uint32_t>(ks >> 2) * ((128u * 128u) >> 4) + static_cast<uint32_t>(ks & 3) * 2u;
+          const uint32_t koff = static_cast<uint32_t>(ks >> 2) * ((KV * 128u) >> 4) + static_cast<uint32_t>(ks & 3) * 2u;
+          umma_bf16_ss_p(el, tmem_s, desc_hi | (q_lo + off), desc_hi | (k_lo + koff), idesc_s, ks != 0 ? 1u : 0u);
         }
-        tc_commit(&s_full[w]);
+        tc_commit_p(el, sfull);
       };
       for (int round = 0;; ++round) {
         const int item0 = round * item_stride + static_cast<int>(blockIdx.x) * NWG;
@@ -223,30 +265,35 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
         // ring positions follow the producer's order: rounds, then key tiles, then the active warpgroups
         const uint32_t nact = (item0 + NWG - 1 < p.total_items) ? NWG : 1;
         const uint32_t pos0 = static_cast<uint32_t>(round) * n_tiles * NWG + w;
-        mbar_wait(&q_full[w], round & 1);
+        mbar_wait_a(qfull, round & 1);
         issue_s(pos0);
-        if (n_tiles == 1) tc_commit(&q_free[w]);
+        if (n_tiles == 1) tc_commit_p(el, qfree);
         for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait(&p_full[w], cnt & 1u);
+          mbar_wait_a(pfull, cnt & 1u);
           // P(j) is ready and S is free: start S(j+1) first (the warpgroup is idle until it lands), then the longer
           // P V product of tile j
           if (j + 1 < n_tiles) {
             issue_s(pos0 + (j + 1) * nact);
-            if (j + 2 == n_tiles) tc_commit(&q_free[w]);
+            if (j + 2 == n_tiles) tc_commit_p(el, qfree);
           }
-          if (j == 0) mbar_wait(&o_free[w], (round & 1) ^ 1);  // the previous item's O has been read out
+          if (j == 0) mbar_wait_a(ofree, (round & 1) ^ 1);  // the previous item's O has been read out
           tc_fence_after();
           const uint32_t s = (pos0 + j * nact) % STAGES;
-          const uint32_t v_addr = kv_addr0 + s * Cfg::kStageBytes + Cfg::kKBytes;
+          const uint32_t v_lo = kv_lo0 + s * (Cfg::kStageBytes >> 4) + (Cfg::kKBytes >> 4);
           const int kvalid = p.Nk - j * KV;  // keys of this tile that exist; P is zero beyond them
           const int ksteps = kvalid >= KV ? KV / 16 : (kvalid + 15) >> 4;
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adesc = make_sdesc_sw128(p_addr + (ks >> 2) * 128u * 128u + (ks & 3) * 32u);
-            const uint64_t bdesc = make_sdesc_sw128_mn(v_addr + ks * 16u * 128u, KV * 128u);
-            umma_bf16_ss(tmem_o, adesc, bdesc, idesc_o, (j | ks) != 0 ? 1u : 0u);
+            const uint64_t adesc = desc_hi | (p_lo + static_cast<uint32_t>(ks >> 2) * ((128u * 128u) >> 4) +
+                                              static_cast<uint32_t>(ks & 3) * 2u);
+            const uint64_t bdesc = desc_hi_mn | (v_lo + static_cast<uint32_t>(ks) * ((16u * 128u) >> 4));
+            const uint32_t accf = (j | ks) != 0 ? 1u : 0u;
+            umma_bf16_ss_p(el, tmem_o, adesc, bdesc, idesc_o, accf);
+            // row sums l += P 1: the same P against a tile of ones, 16 columns right after O - the softmax warps
+            // never add the probabilities up themselves, and l is exactly the sum of the bf16 P that P V uses
+            umma_bf16_ss_p(el, tmem_l, adesc, ones_desc, idesc_l, accf);
           }
-          tc_commit(&kv_empty[s]);
-          tc_commit(&pv_done[w]);
+          tc_commit_p(el, kve0 + 8u * s);
+          tc_commit_p(el, pvdone);
           ++cnt;
         }
       }
@@ -260,7 +307,7 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
     const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t tmem_S = tmem_base + w * KV;
     const uint32_t tmem_O = tmem_base + NWG * KV + w * Cfg::kONCols;
-    uint8_t* prow = sP + w * Cfg::kPBytes + r * 128;
+    const uint32_t prow_s = smem_u32(sP + w * Cfg::kPBytes + r * 128);  // this row of the P tile (shared address)
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     uint32_t cnt = 0;
     for (int round = 0;; ++round) {
@@ -281,62 +328,124 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
       } else if (p.mask != nullptr && valid) {
         mrow = p.mask + ((static_cast<int64_t>(g) * p.R + row) / p.mask_rows) * p.mask_ld;
       }
-      float m_run = -INFINITY, l_run = 0.f;
-
+      // Online softmax with a LAZY exponent offset: tile 0 is anchored on its exact row maximum (pass 1); later tiles
+      // are exponentiated in ONE pass against the offset already in use while their own maximum is tracked, and the
+      // offset moves (O and the row sum are rescaled, the tile redone) only when a row's maximum outgrows it by more
+      // than 2^8 - probabilities then stay <= 256, exact in bf16 range and harmless in the fp32 accumulators, and the
+      // final O / l normalisation is unchanged. This removes the second read of S and nearly every O rescale.
+      float m_used = 0.f;
+      bool anchored = false;  // m_used comes from a real maximum of this row (false while every key was masked)
+      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && warp == 2 && lane == 0;
+      long long t_a = 0, t_b = 0;
       for (int j = 0; j < n_tiles; ++j, ++cnt) {
+        if (tr) t_a = clock64();
         mbar_wait(&s_full[w], cnt & 1u);
         tc_fence_after();
+        if (tr) { t_b = clock64(); p.trace[0] += t_b - t_a; t_a = t_b; }
         const int key0 = j * KV;
-        // pass 1: row maximum (interior tiles without a mask skip every per-key predicate)
+        // interior tiles without a mask skip every per-key predicate
         const bool plain = !TEMPORAL && (mrow == nullptr) && (key0 + KV <= p.Nk);
         // columns of this tile that can hold keys, rounded up to the 16-key granularity of the P V product and to
         // the 32-column chunks processed here (everything past Nk is written as zero probability)
         const int cols = (p.Nk - key0 >= KV) ? KV : (((p.Nk - key0 + 15) >> 4) << 4);
-        float m_tile = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < cols; c += 32) {
-          uint32_t sv[32];
-          tmem_ld_x32(tmem_S + lane_base + c, sv);
-          tmem_ld_wait();
-          if (plain) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sv[i]));
-          } else {
-            uint32_t mbits = 0xffffffffu;
-            if constexpr (TEMPORAL) {
-              mbits = 0;  // same pixel <=> same residue modulo tP
-              int rem = c % p.tP;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (rem == t_mod) mbits |= (1u << i);
-                if (++rem == p.tP) rem = 0;
-              }
-            } else if (mrow != nullptr) {
-              mbits = 0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
-            }
+        auto chunk_mask = [&](int c) -> uint32_t {  // bit i: key key0 + c + i may be attended (non-plain tiles)
+          uint32_t mbits = 0xffffffffu;
+          if constexpr (TEMPORAL) {
+            mbits = 0;  // same pixel <=> same residue modulo tP
+            int rem = c % p.tP;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
-              m_tile = fmaxf(m_tile, keep ? __uint_as_float(sv[i]) : -INFINITY);
+              if (rem == t_mod) mbits |= (1u << i);
+              if (++rem == p.tP) rem = 0;
+            }
+          } else if (mrow != nullptr) {
+            mbits = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
+          }
+          const int left = p.Nk - key0 - c;  // keys past Nk do not exist
+          if (left < 32) mbits &= (left <= 0) ? 0u : ((1u << left) - 1u);
+          return mbits;
+        };
+        auto row_max = [&]() -> float {  // pass 1 (tile 0 only)
+          float m = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < cols; c += 32) {
+            uint32_t sv[32];
+            tmem_ld_x32(tmem_S + lane_base + c, sv);
+            tmem_ld_wait();
+            if (plain) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(sv[i]));
+            } else {
+              const uint32_t mbits = chunk_mask(c);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m = fmaxf(m, ((mbits >> i) & 1u) ? __uint_as_float(sv[i]) : -INFINITY);
             }
           }
-        }
-        m_tile *= p.scale_log2;  // scale > 0: max commutes with the scaling
-        const float m_new = fmaxf(m_run, m_tile);
-        const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = fast_exp2(m_run - m_safe);  // m_run = -inf -> 0
-        const bool changed = (m_new > m_run) && (j > 0);
-        m_run = m_new;
-        l_run *= alpha;
-        if (j > 0) {
+          return m;
+        };
+        // exponentiate against offset m_off, write the bf16 P tile (K-major, 128B swizzle), return the raw row max
+        // (the row sums come out of the tensor core: see the ones MMA next to P V)
+        auto exp_pass = [&](float m_off, float& mt) {
+          mt = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < cols; c += 32) {
+            uint32_t sv[32];
+            tmem_ld_x32(tmem_S + lane_base + c, sv);
+            tmem_ld_wait();
+            float pv[32];
+            if (plain) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                mt = fmaxf(mt, __uint_as_float(sv[i]));
+                const float x = fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_off);
+                pv[i] = ((i & 7) < kPolyOf8) ? poly_exp2(x) : fast_exp2(x);  // balance the MUFU and FMA pipes
+              }
+            } else {
+              const uint32_t mbits = chunk_mask(c);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const bool keep = (mbits >> i) & 1u;
+                mt = fmaxf(mt, keep ? __uint_as_float(sv[i]) : -INFINITY);
+                pv[i] = keep ? fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_off)) : 0.f;
+              }
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+            const uint32_t patom = prow_s + static_cast<uint32_t>(c >> 6) * (128u * 128u);
+            const uint32_t chunk0 = static_cast<uint32_t>((c & 63) >> 3);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const uint32_t phys = (chunk0 + v) ^ sw;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(patom + phys * 16u), "r"(pk[4 * v]),
+                           "r"(pk[4 * v + 1]), "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
+                           : "memory");
+            }
+          }
+        };
+        if (j == 0) {
+          const float mt0 = row_max();
+          anchored = mt0 > -INFINITY;
+          m_used = anchored ? mt0 * p.scale_log2 : 0.f;  // scale > 0: max commutes with the scaling
+          if (tr) { t_b = clock64(); p.trace[1] += t_b - t_a; t_a = t_b; }
+        } else {
           mbar_wait(&pv_done[w], (cnt - 1) & 1u);  // P V of the previous tile finished: O is stable, P smem is free
           tc_fence_after();
-          if (__any_sync(0xffffffffu, changed)) {
+          if (tr) { t_b = clock64(); p.trace[2] += t_b - t_a; t_a = t_b; }
+        }
+        float mt;
+        exp_pass(m_used, mt);
+        if (j > 0) {
+          const float mts = mt * p.scale_log2;
+          const bool re = (mt > -INFINITY) && (!anchored || mts > m_used + 8.f);
+          if (__any_sync(0xffffffffu, re)) {  // rare: some row of this warp outgrew its offset - re-anchor and redo
+            const float m_new = re ? mts : m_used;
+            const float alpha = (re && anchored) ? fast_exp2(m_used - m_new) : 1.f;  // unanchored rows hold O = 0
 #pragma unroll 1
-            for (int c = 0; c < p.dN; c += 16) {
+            for (int c = 0; c < p.dN + 16; c += 16) {  // O and the row-sum columns behind it
               uint32_t ov[16];
               tmem_ld_x16(tmem_O + lane_base + c, ov);
               tmem_ld_wait();
@@ -345,68 +454,27 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
               tmem_st_x16(tmem_O + lane_base + c, ov);
             }
             tmem_st_wait();
+            m_used = m_new;
+            anchored = anchored || re;
+            exp_pass(m_used, mt);
           }
         }
-        // pass 2: probabilities -> bf16 P tile in smem (K-major, 128B swizzle), row sum
-        float l_tile = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < cols; c += 32) {
-          uint32_t sv[32];
-          tmem_ld_x32(tmem_S + lane_base + c, sv);
-          tmem_ld_wait();
-          float pv[32];
-          if (plain) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe));
-          } else {
-            uint32_t mbits = 0xffffffffu;
-            if constexpr (TEMPORAL) {
-              mbits = 0;  // same pixel <=> same residue modulo tP
-              int rem = c % p.tP;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (rem == t_mod) mbits |= (1u << i);
-                if (++rem == p.tP) rem = 0;
-              }
-            } else if (mrow != nullptr) {
-              mbits = 0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (key0 + c + i < p.Nk && mrow[key0 + c + i] != 0) mbits |= (1u << i);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const bool keep = (key0 + c + i < p.Nk) && ((mbits >> i) & 1u);
-              pv[i] = keep ? fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_safe)) : 0.f;
-            }
-          }
-          // the row sum is taken in fp32 before the bf16 rounding of P (the rounding errors average out over the
-          // row; bf16 keeps 8 bits, the sum of >= 16 terms is good to ~1e-3 relative either way)
-          uint32_t pk[16];
-          float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-            l0 += pv[2 * i];
-            l1 += pv[2 * i + 1];
-          }
-          l_tile += l0 + l1;
-          uint8_t* patom = prow + (c >> 6) * (128 * 128);
-          const uint32_t chunk0 = static_cast<uint32_t>((c & 63) >> 3);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const uint32_t phys = (chunk0 + v) ^ sw;
-            *reinterpret_cast<uint4*>(patom + phys * 16) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-          }
-        }
-        l_run += l_tile;
+        if (tr) { t_b = clock64(); p.trace[3] += t_b - t_a; t_a = t_b; }
         tc_fence_before();
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
         mbar_arrive(&p_full[w]);   // also: S consumed (the next Q K^T may overwrite it)
+        if (tr) { t_b = clock64(); p.trace[4] += t_b - t_a; p.trace[5] += 1; }
       }
       // ---------------- output ----------------
       mbar_wait(&pv_done[w], (cnt - 1) & 1u);
       tc_fence_after();
+      float l_run;
+      {
+        uint32_t lv[16];
+        tmem_ld_x16(tmem_O + lane_base + p.dN, lv);
+        tmem_ld_wait();
+        l_run = __uint_as_float(lv[0]);
+      }
       const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
       __nv_bfloat16* orow = p.out + (static_cast<int64_t>(g) * p.R + row) * p.ldo + head * p.d;
 #pragma unroll 1
@@ -521,11 +589,32 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
     int rc = make_tmap_bf16(&kp.tmKV, d->kv, 3, dims, strides, box, el);
     if (rc != 0) return rc;
   }
-  switch (dka) {
-    case 1: return launch_attn<1, 128, 2, 4, false>(kp, stream);
-    case 2: return launch_attn<2, 64, 2, 4, false>(kp, stream);
-    default: return launch_attn<3, 64, 1, 3, false>(kp, stream);
+  static long long* trace_buf = nullptr;
+  static int trace_on = -1;
+  if (trace_on < 0) {
+    const char* e = getenv("ASVA_ATTN_TRACE");
+    trace_on = (e != nullptr && e[0] == '1') ? 1 : 0;
+    if (trace_on) cudaMalloc(&trace_buf, 8 * sizeof(long long));
   }
+  if (trace_on) {
+    cudaMemsetAsync(trace_buf, 0, 8 * sizeof(long long), stream);
+    kp.trace = trace_buf;
+  }
+  int rc;
+  switch (dka) {
+    case 1: rc = launch_attn<1, 128, 2, 4, false>(kp, stream); break;
+    case 2: rc = launch_attn<2, 64, 2, 4, false>(kp, stream); break;
+    default: rc = launch_attn<3, 64, 1, 3, false>(kp, stream); break;
+  }
+  if (trace_on && rc == 0) {
+    long long h[8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    if (h[5] > 0)
+      printf("[asva attn trace] tiles %lld: wait S %.0f | pass1 %.0f | wait PV + rescale %.0f | pass2 %.0f | arrive %.0f cycles per tile\n",
+             h[5], (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5]);
+  }
+  return rc;
 }
 
 extern "C" int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
