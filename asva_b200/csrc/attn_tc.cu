@@ -41,7 +41,11 @@ struct AttnKParams {
 
 constexpr int kPolyOf8 = 3;  // of every 8 exponentials of an unmasked tile, this many avoid the MUFU pipe
 
-template <int DKA, int KV, int NWG, int STAGES>
+// NB = S buffers in TMEM and P buffers in shared memory per warpgroup. NB = 2 lets the tensor core compute S(j+1) while
+// the softmax works on S(j), and lets the softmax write P(j) while P V(j-1) still reads P(j-1): the per-tile critical
+// path shrinks from (MMA issue + softmax) to the softmax alone. It needs 64-key tiles for head dims <= 64 and does
+// not fit shared memory for larger heads.
+template <int DKA, int KV, int NWG, int STAGES, int NB = 1>
 struct AttnCfg {
   static constexpr int kQBytes = DKA * 128 * 128;
   static constexpr int kKBytes = DKA * KV * 128;
@@ -49,10 +53,10 @@ struct AttnCfg {
   static constexpr int kStageBytes = kKBytes + kVBytes;
   static constexpr int kPBytes = (KV / 64) * 128 * 128;
   static constexpr int kONCols = DKA * 64 + 16;  // TMEM columns per O accumulator + the 16 row-sum columns after it
-  static constexpr int kTmemNeed = NWG * (KV + kONCols);
+  static constexpr int kTmemNeed = NWG * (NB * KV + kONCols);
   static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);
   static constexpr int kOnesBytes = 2048;  // 16 x 64 bf16 ones: B operand of the row-sum MMA
-  static constexpr int kSmemBytes = NWG * (kQBytes + kPBytes) + STAGES * kStageBytes + kOnesBytes + 256;
+  static constexpr int kSmemBytes = NWG * (kQBytes + NB * kPBytes) + STAGES * kStageBytes + kOnesBytes + 512;
   static constexpr int kThreads = 64 + 128 * NWG + (NWG > 1 ? 32 : 0);  // + the second MMA-issuing warp
 };
 
@@ -92,9 +96,10 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128_mn(uint32_t saddr, uint32_t
 // block of tP pixels of one (clip, head): its tP*tF (<= KV) rows, ordered (frame, pixel), are both the queries and the
 // single key tile, fetched with 5-D boxes straight from the [b][f][n][3C] projection output; row r attends key c iff
 // they belong to the same pixel (c % tP == r % tP) - a block-diagonal mask evaluated arithmetically.
-template <int DKA, int KV, int NWG, int STAGES, bool TEMPORAL>
+template <int DKA, int KV, int NWG, int STAGES, int NB, bool TEMPORAL>
 __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = AttnCfg<DKA, KV, NWG, STAGES>;
+  using Cfg = AttnCfg<DKA, KV, NWG, STAGES, NB>;
+  static_assert(STAGES >= (NB + 1) * NWG, "key ring too shallow for the tiles in flight");
   extern __shared__ uint8_t smem_raw[];
   // the dynamic shared memory of a kernel without static shared memory starts at the (1024-byte aligned) base of the
   // CTA's window; the 128B-swizzled tiles need that alignment and there is no room for slack - checked, not assumed
@@ -105,16 +110,16 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
   }
   uint8_t* sQ = smem;                                // [NWG][kQBytes]
   uint8_t* sKV = sQ + NWG * Cfg::kQBytes;            // [STAGES][K | V]
-  uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;     // [NWG][kPBytes]
-  uint8_t* sOnes = sP + NWG * Cfg::kPBytes;          // [16][64] bf16 1.0
+  uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;     // [NWG][NB][kPBytes]
+  uint8_t* sOnes = sP + NWG * NB * Cfg::kPBytes;     // [16][64] bf16 1.0
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + Cfg::kOnesBytes);
-  uint64_t* q_full = bars;              // [2]  Q tile of the warpgroup's item landed
-  uint64_t* q_free = bars + 2;          // [2]  every S = Q K^T of the item has been issued and completed
-  uint64_t* s_full = bars + 4;          // [2]
-  uint64_t* p_full = bars + 6;          // [2]  P tile written (and S consumed)
-  uint64_t* pv_done = bars + 8;         // [2]
-  uint64_t* o_free = bars + 10;         // [2]  the warpgroup has read the item's O out of TMEM
-  uint64_t* kv_full = bars + 12;        // [STAGES]
+  uint64_t* q_full = bars;              // [2]      Q tile of the warpgroup's item landed
+  uint64_t* q_free = bars + 2;          // [2]      every S = Q K^T of the item has been issued and completed
+  uint64_t* o_free = bars + 4;          // [2]      the warpgroup has read the item's O out of TMEM
+  uint64_t* s_full = bars + 6;          // [2][NB]  per warpgroup and S buffer
+  uint64_t* p_full = bars + 6 + 2 * NB;   // [2][NB]  P tile written (and S consumed)
+  uint64_t* pv_done = bars + 6 + 4 * NB;  // [2][NB]
+  uint64_t* kv_full = bars + 6 + 6 * NB;  // [STAGES]
   uint64_t* kv_empty = kv_full + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + STAGES);
 
@@ -128,10 +133,12 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
     for (int w = 0; w < 2; ++w) {
       mbar_init(&q_full[w], 1);
       mbar_init(&q_free[w], 1);
-      mbar_init(&s_full[w], 1);
-      mbar_init(&p_full[w], 128);
-      mbar_init(&pv_done[w], 1);
       mbar_init(&o_free[w], 128);
+      for (int b = 0; b < NB; ++b) {
+        mbar_init(&s_full[w * NB + b], 1);
+        mbar_init(&p_full[w * NB + b], 128);
+        mbar_init(&pv_done[w * NB + b], 1);
+      }
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -237,65 +244,71 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
       constexpr uint64_t desc_hi_mn = desc_hi | (static_cast<uint64_t>((KV * 128u) >> 4) << 16);  // MN-major: LBO
       auto lo = [](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
       const uint32_t q_lo = lo(smem_u32(sQ + w * Cfg::kQBytes)) | (1u << 16);
-      const uint32_t p_lo = lo(smem_u32(sP + w * Cfg::kPBytes)) | (1u << 16);
+      const uint32_t p_lo0 = lo(smem_u32(sP + w * NB * Cfg::kPBytes)) | (1u << 16);
       const uint32_t kv_lo0 = lo(smem_u32(sKV));
       const uint64_t ones_desc = desc_hi | (lo(smem_u32(sOnes)) | (1u << 16));
-      const uint32_t tmem_s = tmem_base + w * KV;
-      const uint32_t tmem_o = tmem_base + NWG * KV + w * Cfg::kONCols;
+      const uint32_t tmem_s0 = tmem_base + w * (NB * KV + Cfg::kONCols);
+      const uint32_t tmem_o = tmem_s0 + NB * KV;
       const uint32_t tmem_l = tmem_o + p.dN;
       const uint32_t kvf0 = smem_u32(kv_full), kve0 = smem_u32(kv_empty);
-      const uint32_t sfull = smem_u32(&s_full[w]), pfull = smem_u32(&p_full[w]), pvdone = smem_u32(&pv_done[w]);
+      const uint32_t sfull0 = smem_u32(&s_full[w * NB]), pfull0 = smem_u32(&p_full[w * NB]);
+      const uint32_t pvdone0 = smem_u32(&pv_done[w * NB]);
       const uint32_t qfree = smem_u32(&q_free[w]), qfull = smem_u32(&q_full[w]), ofree = smem_u32(&o_free[w]);
-      uint32_t cnt = 0;  // key tiles finished (phase of p_full / pv_done)
-      auto issue_s = [&](uint32_t pos) {
+      // this warpgroup's items are item(it) = (it * gridDim.x + blockIdx.x) * NWG + w; its key tiles form one sequence
+      // c = it * n_tiles + j, tile c lives in S / P buffer c % NB
+      int n_items = 0;
+      for (int it = 0; it * item_stride + static_cast<int>(blockIdx.x) * NWG + w < p.total_items; ++it) ++n_items;
+      const int total_c = n_items * n_tiles;
+      auto ring_pos = [&](int c) -> uint32_t {  // the producer's order: rounds, then key tiles, then active warpgroups
+        const int it = c / n_tiles, j = c - it * n_tiles;
+        const int item0 = it * item_stride + static_cast<int>(blockIdx.x) * NWG;
+        const uint32_t nact = (item0 + NWG - 1 < p.total_items) ? NWG : 1;
+        return static_cast<uint32_t>(it) * n_tiles * NWG + static_cast<uint32_t>(j) * nact + w;
+      };
+      auto issue_s = [&](int c) {
+        const int it = c / n_tiles, j = c - it * n_tiles;
+        if (j == 0) mbar_wait_a(qfull, it & 1);  // this item's Q tile has landed
+        const uint32_t pos = ring_pos(c);
         const uint32_t s = pos % STAGES, ph = (pos / STAGES) & 1u;
         mbar_wait_a(kvf0 + 8u * s, ph);
         tc_fence_after();
         const uint32_t k_lo = (kv_lo0 + s * (Cfg::kStageBytes >> 4)) | (1u << 16);
+        const uint32_t tmem_s = tmem_s0 + static_cast<uint32_t>(c % NB) * KV;
         for (int ks = 0; ks < p.ksteps_qk; ++ks) {
           const uint32_t off = static_cast<uint32_t>(ks >> 2) * ((128u * 128u) >> 4) + static_cast<uint32_t>(ks & 3) * 2u;
           const uint32_t koff = static_cast<uint32_t>(ks >> 2) * ((KV * 128u) >> 4) + static_cast<uint32_t>(ks & 3) * 2u;
           umma_bf16_ss_p(el, tmem_s, desc_hi | (q_lo + off), desc_hi | (k_lo + koff), idesc_s, ks != 0 ? 1u : 0u);
         }
-        tc_commit_p(el, sfull);
+        tc_commit_p(el, sfull0 + 8u * static_cast<uint32_t>(c % NB));
+        if (j == n_tiles - 1) tc_commit_p(el, qfree);  // the item's Q tile is no longer needed once this completes
       };
-      for (int round = 0;; ++round) {
-        const int item0 = round * item_stride + static_cast<int>(blockIdx.x) * NWG;
-        if (item0 + w >= p.total_items) break;
-        // ring positions follow the producer's order: rounds, then key tiles, then the active warpgroups
-        const uint32_t nact = (item0 + NWG - 1 < p.total_items) ? NWG : 1;
-        const uint32_t pos0 = static_cast<uint32_t>(round) * n_tiles * NWG + w;
-        mbar_wait_a(qfull, round & 1);
-        issue_s(pos0);
-        if (n_tiles == 1) tc_commit_p(el, qfree);
-        for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait_a(pfull, cnt & 1u);
-          // P(j) is ready and S is free: start S(j+1) first (the warpgroup is idle until it lands), then the longer
-          // P V product of tile j
-          if (j + 1 < n_tiles) {
-            issue_s(pos0 + (j + 1) * nact);
-            if (j + 2 == n_tiles) tc_commit_p(el, qfree);
-          }
-          if (j == 0) mbar_wait_a(ofree, (round & 1) ^ 1);  // the previous item's O has been read out
-          tc_fence_after();
-          const uint32_t s = (pos0 + j * nact) % STAGES;
-          const uint32_t v_lo = kv_lo0 + s * (Cfg::kStageBytes >> 4) + (Cfg::kKBytes >> 4);
-          const int kvalid = p.Nk - j * KV;  // keys of this tile that exist; P is zero beyond them
-          const int ksteps = kvalid >= KV ? KV / 16 : (kvalid + 15) >> 4;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adesc = desc_hi | (p_lo + static_cast<uint32_t>(ks >> 2) * ((128u * 128u) >> 4) +
-                                              static_cast<uint32_t>(ks & 3) * 2u);
-            const uint64_t bdesc = desc_hi_mn | (v_lo + static_cast<uint32_t>(ks) * ((16u * 128u) >> 4));
-            const uint32_t accf = (j | ks) != 0 ? 1u : 0u;
-            umma_bf16_ss_p(el, tmem_o, adesc, bdesc, idesc_o, accf);
-            // row sums l += P 1: the same P against a tile of ones, 16 columns right after O - the softmax warps
-            // never add the probabilities up themselves, and l is exactly the sum of the bf16 P that P V uses
-            umma_bf16_ss_p(el, tmem_l, adesc, ones_desc, idesc_l, accf);
-          }
-          tc_commit_p(el, kve0 + 8u * s);
-          tc_commit_p(el, pvdone);
-          ++cnt;
+      for (int c = 0; c < NB && c < total_c; ++c) issue_s(c);
+      for (int c = 0; c < total_c; ++c) {
+        const int it = c / n_tiles, j = c - it * n_tiles;
+        const uint32_t b = static_cast<uint32_t>(c % NB), bph = static_cast<uint32_t>(c / NB) & 1u;
+        mbar_wait_a(pfull0 + 8u * b, bph);
+        // P(c) is ready and S buffer b is free: start S(c + NB) first (the softmax must never wait for it), then the
+        // longer P V product of tile c
+        if (c + NB < total_c) issue_s(c + NB);
+        if (j == 0) mbar_wait_a(ofree, (it & 1) ^ 1);  // the previous item's O has been read out
+        tc_fence_after();
+        const uint32_t s = ring_pos(c) % STAGES;
+        const uint32_t v_lo = kv_lo0 + s * (Cfg::kStageBytes >> 4) + (Cfg::kKBytes >> 4);
+        const uint32_t p_lo = p_lo0 + b * (Cfg::kPBytes >> 4);
+        const int kvalid = p.Nk - j * KV;  // keys of this tile that exist; P is zero beyond them
+        const int ksteps = kvalid >= KV ? KV / 16 : (kvalid + 15) >> 4;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t adesc = desc_hi | (p_lo + static_cast<uint32_t>(ks >> 2) * ((128u * 128u) >> 4) +
+                                            static_cast<uint32_t>(ks & 3) * 2u);
+          const uint64_t bdesc = desc_hi_mn | (v_lo + static_cast<uint32_t>(ks) * ((16u * 128u) >> 4));
+          const uint32_t accf = (j | ks) != 0 ? 1u : 0u;
+          umma_bf16_ss_p(el, tmem_o, adesc, bdesc, idesc_o, accf);
+          // row sums l += P 1: the same P against a tile of ones, 16 columns right after O - the softmax warps
+          // never add the probabilities up themselves, and l is exactly the sum of the bf16 P that P V uses
+          umma_bf16_ss_p(el, tmem_l, adesc, ones_desc, idesc_l, accf);
         }
+        tc_commit_p(el, kve0 + 8u * s);
+        tc_commit_p(el, pvdone0 + 8u * b);
       }
     }
     __syncwarp();
@@ -305,9 +318,9 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t tmem_S = tmem_base + w * KV;
-    const uint32_t tmem_O = tmem_base + NWG * KV + w * Cfg::kONCols;
-    const uint32_t prow_s = smem_u32(sP + w * Cfg::kPBytes + r * 128);  // this row of the P tile (shared address)
+    const uint32_t tmem_S0 = tmem_base + w * (NB * KV + Cfg::kONCols);
+    const uint32_t tmem_O = tmem_S0 + NB * KV;
+    const uint32_t prow_s0 = smem_u32(sP + w * NB * Cfg::kPBytes + r * 128);  // this row of P buffer 0 (shared address)
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     uint32_t cnt = 0;
     for (int round = 0;; ++round) {
@@ -339,7 +352,10 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
       long long t_a = 0, t_b = 0;
       for (int j = 0; j < n_tiles; ++j, ++cnt) {
         if (tr) t_a = clock64();
-        mbar_wait(&s_full[w], cnt & 1u);
+        const uint32_t b = cnt % NB, bph = (cnt / NB) & 1u;  // S / P buffer of this tile and its barrier phase
+        const uint32_t tmem_S = tmem_S0 + b * KV;
+        const uint32_t prow_s = prow_s0 + b * Cfg::kPBytes;
+        mbar_wait(&s_full[w * NB + b], bph);
         tc_fence_after();
         if (tr) { t_b = clock64(); p.trace[0] += t_b - t_a; t_a = t_b; }
         const int key0 = j * KV;
@@ -431,17 +447,22 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
           anchored = mt0 > -INFINITY;
           m_used = anchored ? mt0 * p.scale_log2 : 0.f;  // scale > 0: max commutes with the scaling
           if (tr) { t_b = clock64(); p.trace[1] += t_b - t_a; t_a = t_b; }
-        } else {
-          mbar_wait(&pv_done[w], (cnt - 1) & 1u);  // P V of the previous tile finished: O is stable, P smem is free
-          tc_fence_after();
-          if (tr) { t_b = clock64(); p.trace[2] += t_b - t_a; t_a = t_b; }
         }
+        if (cnt >= NB) {  // the P V product that last read this P buffer (tile cnt - NB) has finished
+          mbar_wait(&pv_done[w * NB + b], bph ^ 1u);
+          tc_fence_after();
+        }
+        if (tr) { t_b = clock64(); p.trace[2] += t_b - t_a; t_a = t_b; }
         float mt;
         exp_pass(m_used, mt);
         if (j > 0) {
           const float mts = mt * p.scale_log2;
           const bool re = (mt > -INFINITY) && (!anchored || mts > m_used + 8.f);
           if (__any_sync(0xffffffffu, re)) {  // rare: some row of this warp outgrew its offset - re-anchor and redo
+            if (NB > 1) {  // O must hold every product up to tile cnt - 1 before it is rescaled
+              mbar_wait(&pv_done[w * NB + (cnt - 1) % NB], ((cnt - 1) / NB) & 1u);
+              tc_fence_after();
+            }
             const float m_new = re ? mts : m_used;
             const float alpha = (re && anchored) ? fast_exp2(m_used - m_new) : 1.f;  // unanchored rows hold O = 0
 #pragma unroll 1
@@ -462,11 +483,11 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
         if (tr) { t_b = clock64(); p.trace[3] += t_b - t_a; t_a = t_b; }
         tc_fence_before();
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
-        mbar_arrive(&p_full[w]);   // also: S consumed (the next Q K^T may overwrite it)
+        mbar_arrive(&p_full[w * NB + b]);  // also: S consumed (a later Q K^T may overwrite this buffer)
         if (tr) { t_b = clock64(); p.trace[4] += t_b - t_a; p.trace[5] += 1; }
       }
       // ---------------- output ----------------
-      mbar_wait(&pv_done[w], (cnt - 1) & 1u);
+      mbar_wait(&pv_done[w * NB + (cnt - 1) % NB], ((cnt - 1) / NB) & 1u);
       tc_fence_after();
       float l_run;
       {
@@ -506,13 +527,13 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
 
 static int g_attn_sms = 0;
 
-template <int DKA, int KV, int NWG, int STAGES, bool TEMPORAL>
+template <int DKA, int KV, int NWG, int STAGES, int NB, bool TEMPORAL>
 static int launch_attn(const AttnKParams& kp, cudaStream_t stream) {
-  using Cfg = AttnCfg<DKA, KV, NWG, STAGES>;
+  using Cfg = AttnCfg<DKA, KV, NWG, STAGES, NB>;
   static_assert(Cfg::kSmemBytes <= 232448, "attention configuration exceeds the shared memory of an SM");
   static bool configured = false;
   if (!configured) {
-    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV, NWG, STAGES, TEMPORAL>,
+    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV, NWG, STAGES, NB, TEMPORAL>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
@@ -523,7 +544,7 @@ static int launch_attn(const AttnKParams& kp, cudaStream_t stream) {
   }
   int grid = (kp.total_items + NWG - 1) / NWG;
   if (grid > g_attn_sms) grid = g_attn_sms;
-  ASVA_CUDA_OK(launch_k(attn_tc_kernel<DKA, KV, NWG, STAGES, TEMPORAL>, dim3(grid), dim3(Cfg::kThreads),
+  ASVA_CUDA_OK(launch_k(attn_tc_kernel<DKA, KV, NWG, STAGES, NB, TEMPORAL>, dim3(grid), dim3(Cfg::kThreads),
                         Cfg::kSmemBytes, stream, 1, kp));
   return 0;
 }
@@ -572,7 +593,7 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
   ASVA_REQUIRE(items < (1ll << 30), "asva_attention: too many query tiles");
   kp.total_items = (int)items;
   const int dka = d->dpad / 64;
-  const int kv = (dka == 1) ? 128 : 64;
+  const int kv = 64;  // key tile of every non-temporal configuration below
   {
     uint64_t dims[3] = {(uint64_t)d->d, (uint64_t)d->heads, (uint64_t)d->G * (uint64_t)d->R};
     uint64_t strides[2] = {(uint64_t)d->d * 2u, (uint64_t)d->ldq * 2u};
@@ -602,9 +623,9 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
   }
   int rc;
   switch (dka) {
-    case 1: rc = launch_attn<1, 128, 2, 4, false>(kp, stream); break;
-    case 2: rc = launch_attn<2, 64, 2, 4, false>(kp, stream); break;
-    default: rc = launch_attn<3, 64, 1, 3, false>(kp, stream); break;
+    case 1: rc = launch_attn<1, 64, 2, 8, 2, false>(kp, stream); break;
+    case 2: rc = launch_attn<2, 64, 2, 4, 1, false>(kp, stream); break;
+    default: rc = launch_attn<3, 64, 1, 3, 1, false>(kp, stream); break;
   }
   if (trace_on && rc == 0) {
     long long h[8];
@@ -665,8 +686,8 @@ extern "C" int asva_temporal_attention(const void* qkv, void* out, int32_t B, in
     if (rc != 0) return rc;
   }
   switch (dka) {
-    case 1: return launch_attn<1, 128, 2, 4, true>(kp, stream);
-    case 2: return launch_attn<2, 64, 2, 4, true>(kp, stream);
-    default: return launch_attn<3, 64, 1, 3, true>(kp, stream);
+    case 1: return launch_attn<1, 128, 2, 4, 1, true>(kp, stream);
+    case 2: return launch_attn<2, 64, 2, 4, 1, true>(kp, stream);
+    default: return launch_attn<3, 64, 1, 3, 1, true>(kp, stream);
   }
 }
