@@ -236,3 +236,40 @@ def test_engine_logic_ragged_audio_mask_and_frame_varying_context():
     sig = eng.ctx_sig
     eng.set_context(text, audio[:, :1].expand(B, F, 229, 768), synth.audio_segment_mask(F)[None].expand(B, -1, -1))
     assert eng.ctx_sig != sig and eng.ctx["mask"] is None  # equal counts per frame: no mask left at all
+
+
+def test_plan_cache_roundtrip_and_signature(tmp_path):
+    """Measured GEMM tile plans are cached per problem shape and can be persisted (ASVA_PLAN_CACHE): the signature
+    must depend on the shape and epilogue flags only (not on pointers), and save -> load must reproduce the cache."""
+    import torch
+    from asva_b200 import ops
+    be = ops.CudaBackend()  # loads the .so (no GPU needed for that); never launches here
+    x = torch.zeros(256, 320, dtype=torch.bfloat16)
+    w = torch.zeros(640, 320, dtype=torch.bfloat16)
+    bias = torch.zeros(640)
+    s1 = ops.spec_linear(x, w, torch.zeros(256, 640, dtype=torch.bfloat16), bias=bias)
+    s2 = ops.spec_linear(x.clone(), w.clone(), torch.zeros(256, 640, dtype=torch.bfloat16), bias=bias.clone())
+    s3 = ops.spec_linear(x, w, torch.zeros(256, 640, dtype=torch.bfloat16))  # no bias: a different epilogue
+    assert be.gemm_signature(s1) == be.gemm_signature(s2) != be.gemm_signature(s3)
+    be.plan_cache[be.gemm_signature(s1)] = (160, 1, 2)
+    be.plan_cache[be.gemm_signature(s3)] = (128, 4, 1)
+    path = str(tmp_path / "plans.txt")
+    be.save_plans(path)
+    be2 = ops.CudaBackend()
+    be2.load_plans(path)
+    assert be2.plan_cache == be.plan_cache
+
+
+def test_tconv_spec_single_frame_tiles():
+    """conv_temp as one GEMM: three K segments (own rows, previous frame, frame 0) over one-frame tiles, with the
+    frame-0 weight block swapped for the tiles of frame 0 (utils.py:43-53 restated in ops.spec_tconv)."""
+    import torch
+    from asva_b200 import ops
+    B, F, N, C = 2, 12, 256, 320
+    y = torch.zeros(B * F * N, C, dtype=torch.bfloat16)
+    w4 = torch.zeros(C, 4 * C, dtype=torch.bfloat16)
+    sp = ops.spec_tconv(y, w4, torch.zeros_like(y), B=B, F=F, N=N)
+    assert sp.box[1] == 1 and sp.box[0] * sp.box[2] <= 128
+    assert [(g.off, g.wk, g.wk_first, g.fix2) for g in sp.segs] == [((0, 0, 0), 0, -1, -1), ((0, -1, 0), C, -1, -1),
+                                                                     ((0, 0, 0), 2 * C, 3 * C, 0)]
+    assert sp.K == 3 * C and sp.wcols == 4 * C
