@@ -1,4 +1,6 @@
 // LayerNorm and GroupNorm kernels (HBM/L2-bound elementwise + reductions; CUDA cores, 16-byte vector access).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_common.h"
 
@@ -270,6 +272,444 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused GroupNorm: statistics + apply (+SiLU) in ONE launch.  The grid is sized to be co-resident (<= kGnCtasPerSm
+// CTAs per SM), CTA (inst, split, cb) reduces its rows x channel block, folds the sums per group into fp64
+// accumulators in global memory (atomicAdd), the whole grid meets at a counter barrier, and every CTA then normalises
+// exactly the rows it reduced (second read served by L1 / L2).  Three launches and a partials round trip become one
+// launch whose HBM traffic is one read and one write of the tensor.  The accumulators and both counters are left
+// zeroed by the last CTA that passes the exit counter, so the workspace only has to be zeroed once, at allocation.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnCtasPerSm = 4;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void gn_accum8(const uint4& u, float (&s)[8], float (&q)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j] += f[j];
+    q[j] = fmaf(f[j], f[j], q[j]);
+  }
+}
+
+__device__ __forceinline__ uint4 gn_affine8(const uint4& u, const float4 (&t)[4], int silu) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = fmaf(f[2 * j], t[j].x, t[j].y);
+    f[2 * j + 1] = fmaf(f[2 * j + 1], t[j].z, t[j].w);
+  }
+  if (silu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+__global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+                                                       const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
+                                                       int splits, int cblocks, int cw, int rows_per_pass, int groups,
+                                                       float eps, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int silu,
+                                                       __nv_bfloat16* __restrict__ out, double* __restrict__ acc,
+                                                       unsigned* __restrict__ ctr, int n_acc) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[256 * 16];  // [rows_per_pass][cw*8][2]
+  __shared__ __align__(16) float chs[1024 * 2];  // per-channel (sum, sumsq) of this CTA, later the (scale, shift) table
+  __shared__ int s_last;
+  const int Ctot = C0 + C1;
+  const int nchunk = Ctot >> 3;
+  const int cpg = Ctot / groups;
+  const int cb = blockIdx.x % cblocks;
+  const int split = (blockIdx.x / cblocks) % splits;
+  const int inst = blockIdx.x / (cblocks * splits);
+  const int rl = threadIdx.x / cw;
+  const int cl = threadIdx.x % cw;
+  const int ch = cb * cw + cl;
+  const bool active = (rl < rows_per_pass) && (ch < nchunk);
+  const int64_t rbeg = rows * split / splits, rend = rows * (split + 1) / splits;
+  const int c = ch * 8;
+  const __nv_bfloat16* src = x0;
+  int64_t ld = C0;
+  if (active) {
+    if (c < C0) { src = x0 + c; } else { src = x1 + (c - C0); ld = C1; }
+    src += static_cast<int64_t>(inst) * rows * ld;
+  }
+  const int64_t rstep = rows_per_pass;
+  // ---------------- phase 1: sums over this CTA's rows ----------------
+  {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    if (active) {
+      int64_t r = rbeg + rl;
+      for (; r + 3 * rstep < rend; r += 4 * rstep) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(src + r * ld);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(src + (r + rstep) * ld);
+        const uint4 u2 = *reinterpret_cast<const uint4*>(src + (r + 2 * rstep) * ld);
+        const uint4 u3 = *reinterpret_cast<const uint4*>(src + (r + 3 * rstep) * ld);
+        gn_accum8(u0, s, q);
+        gn_accum8(u1, s, q);
+        gn_accum8(u2, s, q);
+        gn_accum8(u3, s, q);
+      }
+      for (; r < rend; r += rstep) gn_accum8(*reinterpret_cast<const uint4*>(src + r * ld), s, q);
+    }
+    if (rl < rows_per_pass) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red[((rl * cw + cl) * 8 + j) * 2 + 0] = s[j];
+        red[((rl * cw + cl) * 8 + j) * 2 + 1] = q[j];
+      }
+    }
+  }
+  __syncthreads();
+  const int c_lo = cb * cw * 8;
+  const int c_hi = min(c_lo + cw * 8, Ctot);
+  for (int t = threadIdx.x; t < cw * 8; t += blockDim.x) {
+    float ss = 0.f, qq = 0.f;
+    for (int r = 0; r < rows_per_pass; ++r) {
+      ss += red[((r * cw) * 8 + t) * 2 + 0];
+      qq += red[((r * cw) * 8 + t) * 2 + 1];
+    }
+    chs[2 * t] = ss;
+    chs[2 * t + 1] = qq;
+  }
+  __syncthreads();
+  {
+    const int g_lo = c_lo / cpg, g_hi = (c_hi - 1) / cpg;
+    for (int g = g_lo + threadIdx.x; g <= g_hi; g += blockDim.x) {
+      const int a = max(g * cpg, c_lo), b = min((g + 1) * cpg, c_hi);
+      double ss = 0.0, qq = 0.0;
+      for (int k = a; k < b; ++k) {
+        ss += static_cast<double>(chs[2 * (k - c_lo)]);
+        qq += static_cast<double>(chs[2 * (k - c_lo) + 1]);
+      }
+      double* dst = acc + (static_cast<int64_t>(inst) * groups + g) * 2;
+      atomicAdd(dst, ss);
+      atomicAdd(dst + 1, qq);
+    }
+  }
+  // ---------------- grid barrier (all CTAs are resident by construction) ----------------
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(ctr) < gridDim.x) {
+      if (clock64() - t0 > (1ll << 32)) __trap();  // ~2 s: never spin forever on a misconfigured launch
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---------------- phase 2: (scale, shift) of this CTA's channels ----------------
+  for (int t = threadIdx.x; t < cw * 8; t += blockDim.x) {
+    const int chn = c_lo + t;
+    if (chn >= Ctot) continue;
+    const int g = chn / cpg;
+    const double* a = acc + (static_cast<int64_t>(inst) * groups + g) * 2;
+    const double cnt = static_cast<double>(rows) * cpg;
+    const double mean = __ldcg(a) / cnt;
+    double var = __ldcg(a + 1) / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = rstd * gamma[chn];
+    chs[2 * t] = sc;
+    chs[2 * t + 1] = beta[chn] - static_cast<float>(mean) * sc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicAdd(ctr + 1, 1u);
+    s_last = (old == gridDim.x - 1) ? 1 : 0;
+  }
+  // ---------------- phase 3: normalise the same rows ----------------
+  if (active) {
+    float4 t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = *reinterpret_cast<const float4*>(&chs[(cl * 8 + 2 * j) * 2]);
+    __nv_bfloat16* dst = out + static_cast<int64_t>(inst) * rows * Ctot + c;
+    int64_t r = rbeg + rl;
+    for (; r + 3 * rstep < rend; r += 4 * rstep) {
+      const uint4 u0 = *reinterpret_cast<const uint4*>(src + r * ld);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(src + (r + rstep) * ld);
+      const uint4 u2 = *reinterpret_cast<const uint4*>(src + (r + 2 * rstep) * ld);
+      const uint4 u3 = *reinterpret_cast<const uint4*>(src + (r + 3 * rstep) * ld);
+      *reinterpret_cast<uint4*>(dst + r * Ctot) = gn_affine8(u0, t, silu);
+      *reinterpret_cast<uint4*>(dst + (r + rstep) * Ctot) = gn_affine8(u1, t, silu);
+      *reinterpret_cast<uint4*>(dst + (r + 2 * rstep) * Ctot) = gn_affine8(u2, t, silu);
+      *reinterpret_cast<uint4*>(dst + (r + 3 * rstep) * Ctot) = gn_affine8(u3, t, silu);
+    }
+    for (; r < rend; r += rstep)
+      *reinterpret_cast<uint4*>(dst + r * Ctot) = gn_affine8(*reinterpret_cast<const uint4*>(src + r * ld), t, silu);
+  }
+  __syncthreads();
+  if (s_last) {  // every CTA has read the accumulators: leave the workspace zeroed for the next launch
+    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) acc[i] = 0.0;
+    if (threadIdx.x == 0) {
+      ctr[0] = 0u;
+      ctr[1] = 0u;
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fused GroupNorm, cluster form (the fast path): one thread-block cluster owns one (instance, bundle of gb groups)
+// unit - a column strip of gb * C/groups channels (a multiple of 8, so 16-byte chunks never leave the strip) - and its
+// CTAs split the instance's rows.  Each CTA reduces its rows (fp32 per thread, warp shuffles, fp64 across warps),
+// the cluster exchanges the per-group sums through distributed shared memory (one barrier.cluster, no global
+// atomics, no grid barrier), and every CTA normalises its own rows: from REGISTERS when its slice is at most KMAX
+// chunks per thread (the tensor is read from HBM once), else with a second read that L2 serves.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_dsmem_f64(const double* p, uint32_t rank) {
+  uint32_t a = smem_u32(p), ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+constexpr int kGnMaxGb = 8;  // groups per bundle (8 / gcd(C/groups, 8) <= 8)
+
+template <int KMAX>
+__global__ void __launch_bounds__(512) gn_cluster_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+                                                         const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
+                                                         int groups, int gb, int cs, float eps,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int silu,
+                                                         __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  __shared__ double wpart[16][kGnMaxGb][2];  // per-warp group sums
+  __shared__ double part[kGnMaxGb][2];       // this CTA's group sums (read by the cluster)
+  __shared__ float stat[kGnMaxGb][2];        // (mean, rstd) of the bundle's groups
+  const int Ctot = C0 + C1;
+  const int cpg = Ctot / groups;
+  const int bch = gb * cpg;  // channels of a bundle
+  const int bw = bch >> 3;   // ... in 16-byte chunks
+  const int nb = groups / gb;
+  const int rank = (cs > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit = blockIdx.x / cs;
+  const int inst = unit / nb, bundle = unit - inst * nb;
+  const int rpp = blockDim.x / bw;
+  const int rl = threadIdx.x / bw, col = threadIdx.x - rl * bw;
+  const bool active = rl < rpp;
+  const int64_t rbeg = rows * rank / cs, rend = rows * (rank + 1) / cs;
+  const int c = bundle * bch + col * 8;  // first channel of this thread's chunk
+  const __nv_bfloat16* src = x0;
+  int64_t ld = C0;
+  if (c < C0) { src = x0 + c; } else { src = x1 + (c - C0); ld = C1; }
+  src += static_cast<int64_t>(inst) * rows * ld;
+  pdl_wait();
+  // ---------------- phase 1 ----------------
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  uint4 v[KMAX > 0 ? KMAX : 1];
+  // rows of this thread: rbeg + rl + k * rpp, k < nk
+  const int nk = (active && rbeg + rl < rend) ? static_cast<int>((rend - rbeg - rl + rpp - 1) / rpp) : 0;
+  const int64_t pstep = static_cast<int64_t>(rpp) * ld;
+  if (active) {
+    if constexpr (KMAX > 0) {
+      const __nv_bfloat16* pp = src + (rbeg + rl) * ld;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < nk) v[k] = *reinterpret_cast<const uint4*>(pp);
+        pp += pstep;
+      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < nk) gn_accum8(v[k], s, q);
+    } else {
+      int64_t r = rbeg + rl;
+      for (; r + 7 * rpp < rend; r += 8 * rpp) {
+        uint4 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = *reinterpret_cast<const uint4*>(src + (r + static_cast<int64_t>(k) * rpp) * ld);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gn_accum8(u[k], s, q);
+      }
+      for (; r < rend; r += rpp) gn_accum8(*reinterpret_cast<const uint4*>(src + r * ld), s, q);
+    }
+  }
+  // group of each of this thread's channels inside the bundle
+  int gj[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gj[j] = (col * 8 + j) / cpg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = 0; g < gb; ++g) {
+    float ss = 0.f, qq = 0.f;
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ss += (gj[j] == g) ? s[j] : 0.f;
+        qq += (gj[j] == g) ? q[j] : 0.f;
+      }
+    }
+    ss = warp_sum(ss);
+    qq = warp_sum(qq);
+    if (lane == 0) {
+      wpart[warp][g][0] = static_cast<double>(ss);
+      wpart[warp][g][1] = static_cast<double>(qq);
+    }
+  }
+  // the affine parameters are fetched here, behind the barriers below (and not earlier: the held rows need the registers)
+  float ga[8], be[8];
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c) + 1);
+    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+  }
+  __syncthreads();
+  if (threadIdx.x < gb * 2) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    double a = 0.0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) a += wpart[w][g][k];
+    part[g][k] = a;
+  }
+  if (cs > 1) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x < gb) {
+    const int g = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (cs > 1) {
+      for (int rk = 0; rk < cs; ++rk) {  // same order in every CTA: identical statistics across the cluster
+        a += ld_dsmem_f64(&part[g][0], rk);
+        b += ld_dsmem_f64(&part[g][1], rk);
+      }
+    } else {
+      a = part[g][0];
+      b = part[g][1];
+    }
+    const double cnt = static_cast<double>(rows) * cpg;
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[g][0] = static_cast<float>(mean);
+    stat[g][1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  // ---------------- phase 2: normalise this CTA's rows ----------------
+  if (active) {
+    float4 t[4];
+    {
+      float sc[8], sh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = stat[gj[j]][1] * ga[j];
+        sh[j] = be[j] - stat[gj[j]][0] * sc[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = make_float4(sc[2 * j], sh[2 * j], sc[2 * j + 1], sh[2 * j + 1]);
+    }
+    __nv_bfloat16* dst = out + static_cast<int64_t>(inst) * rows * Ctot + c;
+    if constexpr (KMAX > 0) {
+      __nv_bfloat16* dp = dst + (rbeg + rl) * Ctot;
+      const int64_t dstep = static_cast<int64_t>(rpp) * Ctot;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < nk) *reinterpret_cast<uint4*>(dp) = gn_affine8(v[k], t, silu);
+        dp += dstep;
+      }
+    } else {
+      int64_t r = rbeg + rl;
+      for (; r + 3 * rpp < rend; r += 4 * rpp) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(src + (r + static_cast<int64_t>(k) * rpp) * ld);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(dst + (r + static_cast<int64_t>(k) * rpp) * Ctot) = gn_affine8(u[k], t, silu);
+      }
+      for (; r < rend; r += rpp)
+        *reinterpret_cast<uint4*>(dst + r * Ctot) = gn_affine8(*reinterpret_cast<const uint4*>(src + r * ld), t, silu);
+    }
+  }
+  if (cs > 1) cluster_sync_all();  // no CTA leaves while a peer may still read its sums
+}
+
+struct GnClusterPlan {
+  int ok, gb, cs, threads, kmax, grid;
+};
+
+static GnClusterPlan gn_cluster_plan(int n_inst, int64_t rows, int Ctot, int groups) {
+  GnClusterPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  const int cpg = Ctot / groups;
+  int g8 = 8;  // gcd(cpg, 8)
+  while (cpg % g8 != 0) g8 >>= 1;
+  pl.gb = 8 / g8;
+  if (groups % pl.gb != 0) return pl;
+  const int bw = pl.gb * cpg / 8;
+  if (bw > 128) return pl;
+  const int64_t units = static_cast<int64_t>(n_inst) * (groups / pl.gb);
+  if (units * 8 > (1ll << 30)) return pl;
+  // Measured on B200 (tools/norm_probe.py --sweep): the launch should fill the SMs in ONE wave.  Many units -> one
+  // small streaming CTA each; few units -> clusters that split the rows, 512 threads, slices held in registers.
+  bool hold = true;
+  if (units >= 296) {
+    pl.cs = 1;
+    hold = false;
+  } else if (units >= 148) {
+    pl.cs = 2;
+    hold = false;
+  } else {
+    pl.cs = 8;
+    while (pl.cs > 1 && units * pl.cs > 160) pl.cs >>= 1;
+  }
+  while (pl.cs > 1 && rows / pl.cs < 64) pl.cs >>= 1;
+  const char* e_cs = getenv("ASVA_GN_CS");  // experiments
+  const char* e_t = getenv("ASVA_GN_T");
+  const char* e_k = getenv("ASVA_GN_KMAX");
+  if (e_cs != nullptr) pl.cs = atoi(e_cs);
+  const int64_t rows_cta = (rows + pl.cs - 1) / pl.cs;
+  const int64_t chunks = rows_cta * bw;
+  if (hold)
+    pl.threads = chunks >= 1024 ? 512 : (chunks >= 256 ? 256 : 128);
+  else
+    pl.threads = chunks >= 512 ? 256 : 128;
+  if (e_t != nullptr) pl.threads = atoi(e_t);
+  if (pl.threads < bw) pl.threads = ((bw + 31) / 32) * 32;
+  const int rpp = pl.threads / bw;
+  const int64_t k = (rows_cta + rpp - 1) / rpp;
+  pl.kmax = !hold ? 0 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 0)));
+  if (e_k != nullptr) pl.kmax = (k <= atoi(e_k)) ? (k <= 4 ? 4 : (k <= 8 ? 8 : 16)) : 0;
+  pl.grid = static_cast<int>(units * pl.cs);
+  pl.ok = 1;
+  return pl;
+}
+
+static int g_gn_cap = 0;  // co-resident CTAs of gn_fused_kernel on this device
+
+static GnStatsPlan gn_fused_plan(int n_inst, int64_t rows, int Ctot, int cap) {
+  GnStatsPlan pl;
+  const int nchunk = Ctot / 8;
+  pl.cblocks = (nchunk + 127) / 128;
+  pl.cw = (nchunk + pl.cblocks - 1) / pl.cblocks;
+  pl.rows_per_pass = 256 / pl.cw;
+  if (pl.rows_per_pass < 1) pl.rows_per_pass = 1;
+  int64_t want = cap / ((int64_t)n_inst * pl.cblocks);
+  int64_t max_splits = rows / (2 * (int64_t)pl.rows_per_pass);
+  if (max_splits < 1) max_splits = 1;
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  pl.splits = (int)want;
+  return pl;
+}
+
 }  // namespace asva
 
 extern "C" int asva_layernorm(const void* x, const float* gamma, const float* beta, const float* pos, void* out,
@@ -342,6 +782,78 @@ extern "C" int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, 
   if (blocks > 148 * 16) blocks = 148 * 16;
   ASVA_CUDA_OK(launch_k(gn_apply_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, stats,
       n_inst > 0 ? n_img / n_inst : 1, h, w, silu, upsample, reinterpret_cast<__nv_bfloat16*>(out), total));
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t asva_groupnorm_sync_bytes(void) { return 8 + 2 * 8 * 4096; }
+
+extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t n_inst, int64_t rows,
+                              int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
+                              void* out, void* sync_ws, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (x1 == nullptr) C1 = 0;
+  const int Ctot = C0 + C1;
+  ASVA_REQUIRE(x0 && out && sync_ws && gamma && beta, "asva_groupnorm: null operand");
+  ASVA_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && Ctot >= 8, "asva_groupnorm: channels must be multiples of 8");
+  ASVA_REQUIRE(groups >= 1 && Ctot % groups == 0, "asva_groupnorm: C=%d not divisible by groups=%d", Ctot, groups);
+  ASVA_REQUIRE(n_inst >= 1 && rows >= 1, "asva_groupnorm: empty problem");
+  ASVA_REQUIRE((int64_t)n_inst * groups <= 4096, "asva_groupnorm: n_inst * groups = %lld exceeds the workspace",
+               (long long)n_inst * groups);
+  {
+    static int no_cluster = -1;
+    if (no_cluster < 0) {
+      const char* e = getenv("ASVA_GN_NO_CLUSTER");
+      no_cluster = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    const GnClusterPlan cp = gn_cluster_plan(n_inst, rows, Ctot, groups);
+    // few units x many rows (a whole clip per instance at the top resolution): 8 CTAs per unit cannot fill the GPU
+    // and narrow column strips waste DRAM bursts - the grid-barrier kernel below reads full rows instead
+    const int64_t bytes = static_cast<int64_t>(n_inst) * rows * Ctot * 2;
+    const bool narrow = cp.ok && (int64_t)n_inst * (groups / cp.gb) <= 16 && bytes > (12ll << 20);
+    if (cp.ok && !no_cluster && !narrow) {
+      const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(x0);
+      const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#define ASVA_GN_LAUNCH(K)                                                                                          \
+  ASVA_CUDA_OK(launch_k(gn_cluster_kernel<K>, dim3(cp.grid), dim3(cp.threads), 0, stream, cp.cs, a0, C0, a1, C1, rows, \
+                        groups, cp.gb, cp.cs, eps, gamma, beta, silu, o))
+      switch (cp.kmax) {
+        case 4: ASVA_GN_LAUNCH(4); break;
+        case 8: ASVA_GN_LAUNCH(8); break;
+        case 16: ASVA_GN_LAUNCH(16); break;
+        default: ASVA_GN_LAUNCH(0); break;
+      }
+#undef ASVA_GN_LAUNCH
+      ASVA_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+  }
+  // generic form (channel groups that do not bundle into 16-byte strips): grid-barrier kernel
+  if (g_gn_cap == 0) {
+    int dev = 0, sms = 0, occ = 0;
+    ASVA_CUDA_OK(cudaGetDevice(&dev));
+    ASVA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ASVA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel, 256, 0));
+    ASVA_REQUIRE(occ >= 1, "asva_groupnorm: kernel does not fit an SM");
+    int per_sm = occ < kGnCtasPerSm ? occ : kGnCtasPerSm;
+    const char* e = getenv("ASVA_GN_CTAS_PER_SM");
+    if (e != nullptr && atoi(e) >= 1 && atoi(e) <= occ) per_sm = atoi(e);
+    g_gn_cap = per_sm * sms;
+  }
+  const int nchunk = Ctot / 8;
+  const int cblocks = (nchunk + 127) / 128;
+  ASVA_REQUIRE((int64_t)n_inst * cblocks <= g_gn_cap, "asva_groupnorm: %d instances do not fit a co-resident grid",
+               n_inst);
+  GnStatsPlan pl = gn_fused_plan(n_inst, rows, Ctot, g_gn_cap);
+  const unsigned grid = static_cast<unsigned>(n_inst) * pl.splits * pl.cblocks;
+  unsigned* ctr = reinterpret_cast<unsigned*>(sync_ws);
+  double* acc = reinterpret_cast<double*>(reinterpret_cast<char*>(sync_ws) + 8);
+  ASVA_CUDA_OK(launch_k(gn_fused_kernel, dim3(grid), dim3(256), 0, stream, 1,
+                        reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1,
+                        rows, pl.splits, pl.cblocks, pl.cw, pl.rows_per_pass, groups, eps, gamma, beta, silu,
+                        reinterpret_cast<__nv_bfloat16*>(out), acc, ctr, n_inst * groups * 2));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -308,14 +308,6 @@ class UNetEngine:
         self.be.gemm(ops.spec_tconv(y, cv.w4, out, B=B, F=F, N=N, bias=cv.bt, tproj=tproj,
                                     tproj_ld=self._tproj_total, res1=res1))
 
-    def _gn_stats(self, x0, C0, x1, C1, n_inst, rows, eps, gamma, beta):
-        """-> fp32 [n_inst, C, 2] per-channel (scale, shift) so that GroupNorm(x) = x * scale + shift."""
-        st = self.buf("gn_stats", (n_inst, C0 + C1, 2), torch.float32)
-        need = max(16, int(self.be.groupnorm_ws_floats(n_inst, rows, C0 + C1)))
-        ws = self.buf("gn_ws", (need,), torch.float32)
-        self.be.groupnorm_stats(x0, C0, x1, C1, n_inst, rows, self.groups, eps, gamma, beta, st, ws)
-        return st
-
     def _conv3(self, cv: _Conv, a, B, F, h, w, stride=1):
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
         y = self.buf("conv_y", (B * F * ho * wo, cv.cout))
@@ -327,16 +319,14 @@ class UNetEngine:
         M = B * F * N
         C0, C1 = x0.shape[1], (x1.shape[1] if x1 is not None else 0)
         cin, cout = C0 + C1, r["conv1"].cout
-        st = self._gn_stats(x0, C0, x1, C1, B, F * N, self.eps, r["g1"], r["b1"])
         a = self.buf("gn_out", (M, cin))
-        be.groupnorm_apply(x0, C0, x1, C1, st, B, B * F, h, w, True, False, a)
+        be.groupnorm(x0, C0, x1, C1, B, F * N, self.groups, self.eps, r["g1"], r["b1"], True, a)
         y, _, _ = self._conv3(r["conv1"], a, B, F, h, w)
         h1 = self.buf("res_h1", (M, cout))
         tp = self.tproj[:, r["tproj_off"]: r["tproj_off"] + cout]
         self._ffconv_tail(r["conv1"], y, h1, B, F, N, tproj=tp)
-        st = self._gn_stats(h1, cout, None, 0, B, F * N, self.eps, r["g2"], r["b2"])
         a2 = self.buf("gn_out", (M, cout))
-        be.groupnorm_apply(h1, cout, None, 0, st, B, B * F, h, w, True, False, a2)
+        be.groupnorm(h1, cout, None, 0, B, F * N, self.groups, self.eps, r["g2"], r["b2"], True, a2)
         y2, _, _ = self._conv3(r["conv2"], a2, B, F, h, w)
         if r["short"] is not None:
             sc = r["short"]
@@ -366,9 +356,8 @@ class UNetEngine:
     def _transformer(self, a: dict, x, B, F, h, w, idx: int, out_tag: str):
         be, N, C = self.be, h * w, a["C"]
         M = B * F * N
-        st = self._gn_stats(x, C, None, 0, B * F, N, 1e-6, a["gn_g"], a["gn_b"])
         g = self.buf("gn_out", (M, C))
-        be.groupnorm_apply(x, C, None, 0, st, B * F, B * F, h, w, False, False, g)
+        be.groupnorm(x, C, None, 0, B * F, N, self.groups, 1e-6, a["gn_g"], a["gn_b"], False, g)
         t = self.buf("tok", (M, C))
         be.gemm(ops.spec_linear(g, a["pi_w"], t, bias=a["pi_b"]))
         n = self.buf("ln_out", (M, C))
@@ -486,9 +475,8 @@ class UNetEngine:
                 self._ffconv_tail(blk["up"], y, x, B, F, hh * ww)
         # conv_norm_out -> SiLU -> conv_out (3x3 to 4 channels, fp32) -> its temporal 3-tap in fp32
         C = ch[0]
-        st = self._gn_stats(x, C, None, 0, B, F * N, self.eps, self.out_g, self.out_b)
         a = self.buf("gn_out", (B * F * N, C))
-        be.groupnorm_apply(x, C, None, 0, st, B, B * F, h, w, True, False, a)
+        be.groupnorm(x, C, None, 0, B, F * N, self.groups, self.eps, self.out_g, self.out_b, True, a)
         yo = self.buf("out_y", (B * F * N, 8), torch.float32)
         be.gemm(ops.spec_conv3x3(a, self.conv_out.w, yo, n_img=B * F, h=h, wd=w, bias=self.conv_out.b, out_fp32=True))
         be.conv_out_finish(yo, 8, self.conv_out.wt_full, self.conv_out.bt, out, B, self.cfg["out_channels"], F, h, w)

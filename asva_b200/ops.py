@@ -213,6 +213,7 @@ class CudaBackend:
     def __init__(self) -> None:
         self.lib = _lib.load()
         self.launches = 0
+        self._gn_sync = None  # grid-barrier workspace of the fused GroupNorm
         self._prof = None
         self._ws = {}
         self.tuning = False
@@ -408,6 +409,18 @@ class CudaBackend:
                                                      gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
                                                      ws.data_ptr(), self._stream()), "asva_groupnorm_stats")
         self.launches += 2
+
+    def groupnorm(self, x0, C0, x1, C1, n_inst, rows, groups, eps, gamma, beta, silu, out) -> None:
+        """Fused statistics + apply (+SiLU) of one GroupNorm: out bf16 [n_inst*rows, C0+C1] (one launch)."""
+        self._chk_dev(x0, x1, gamma, beta, out)
+        if self._gn_sync is None:  # zeroed once; the kernel leaves it zeroed
+            self._gn_sync = torch.zeros(int(self.lib.asva_groupnorm_sync_bytes()), dtype=torch.uint8,
+                                        device=x0.device)
+        with self._timed('groupnorm'):
+            _lib.check(self.lib.asva_groupnorm(x0.data_ptr(), C0, _ptr(x1), C1, n_inst, rows, groups, eps,
+                                               gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
+                                               self._gn_sync.data_ptr(), self._stream()), "asva_groupnorm")
+        self.launches += 1
 
     def groupnorm_apply(self, x0, C0, x1, C1, stats, n_inst, n_img, h, w, silu, upsample, out) -> None:
         self._chk_dev(x0, x1, stats, out)

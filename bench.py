@@ -265,7 +265,8 @@ def run_product_arm(args):
     es.load_latents(lat.to(dev))
     es.step(0)
     FAMILIES = {"gemm": "gemm", "attention": "attention", "temporal_attention": "temporal_attention",
-                "layernorm": "layernorm", "groupnorm_stats": "groupnorm", "groupnorm_apply": "groupnorm",
+                "layernorm": "layernorm", "groupnorm": "groupnorm", "groupnorm_stats": "groupnorm",
+                "groupnorm_apply": "groupnorm",
                 "small_linear": "small_linear", "conv_in_im2col": "misc", "conv_out_finish": "misc", "tconv_gather": "misc",
                 "timestep_features": "misc", "cfg_ddim_step": "cfg_step", "cfg_plms_step": "cfg_step"}
     recorded, originals = [], {}

@@ -164,6 +164,18 @@ int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, int32_t C1,
                          int32_t n_img, int32_t h, int32_t w, int32_t silu, int32_t upsample, void* out,
                          asva_stream_t stream);
 
+/* Fused GroupNorm (+ optional SiLU, + channel concat of two sources): statistics and apply in ONE launch, the form the
+ * engine uses wherever no upsample sits between the statistics and the apply (every nn.GroupNorm of the UNet:
+ * ff_spatio_temp_resnet_3d.py:164,175, ff_spatio_audio_temp_transformer_3d.py:117,
+ * audio_cond_unet_3d_condition.py:791).  Same operand meaning as asva_groupnorm_stats / asva_groupnorm_apply;
+ * out bf16 [n_inst*rows][C0+C1].  The grid synchronises through sync_ws (asva_groupnorm_sync_bytes() bytes of device
+ * memory, zeroed ONCE by the caller at allocation; the kernel leaves it zeroed), so launches that share a sync_ws
+ * must be ordered on one stream.  Needs n_inst * groups <= 4096. */
+int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t n_inst, int64_t rows,
+                   int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu, void* out,
+                   void* sync_ws, asva_stream_t stream);
+int64_t asva_groupnorm_sync_bytes(void);
+
 /* conv_in front end: fp32 latents [Bs][Cl][F][h][w] (Cl<=7) -> bf16 im2col rows [B*F*h*w][64] for the 3x3, pad 1
  * conv (column = tap*Cl + c, zero padded to 64); batch b reads latent b % Bs (CFG duplication,
  * pipeline_audio_cond_animation.py:331-336). */

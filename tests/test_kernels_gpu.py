@@ -302,6 +302,37 @@ def test_groupnorm(cuda_backend, n_inst, rows, C0, C1):
     assert torch.equal(o_ref, o_cu)  # pure nearest-upsample copy
 
 
+@pytest.mark.parametrize("n_inst,rows,C0,C1,silu", [(2, 12 * 1024, 320, 0, 1), (24, 1024, 320, 0, 0),
+                                                     (2, 12 * 1024, 640, 320, 1), (24, 256, 640, 0, 0),
+                                                     (2, 768, 1280, 1280, 1), (2, 192, 640, 320, 1),
+                                                     (2, 192, 1280, 0, 1), (24, 16, 1280, 0, 0), (3, 50, 64, 0, 1),
+                                                     (1, 2, 32, 0, 0)])
+def test_groupnorm_fused(cuda_backend, n_inst, rows, C0, C1, silu):
+    """One-launch GroupNorm (statistics + apply) against torch's group_norm; run three times back to back to prove the
+    kernel leaves its barrier workspace clean."""
+    x0 = _rand((n_inst * rows, C0), 74, 2.0) + 0.5
+    x1 = _rand((n_inst * rows, C1), 75) if C1 else None
+    C = C0 + C1
+    g, b = _rand((C,), 76, dtype=torch.float32), _rand((C,), 77, dtype=torch.float32)
+    xc = torch.cat([x0.float()] + ([x1.float()] if C1 else []), dim=1).view(n_inst, rows, C).permute(0, 2, 1)
+    want = torch.nn.functional.group_norm(xc, 32, g, b, 1e-5)
+    if silu:
+        want = torch.nn.functional.silu(want)
+    want = want.permute(0, 2, 1).reshape(-1, C)
+    o_sim = torch.zeros(n_inst * rows, C, dtype=torch.bfloat16, device=DEV)
+    SimBackend().groupnorm(x0, C0, x1, C1, n_inst, rows, 32, 1e-5, g, b, silu, o_sim)
+    outs = []
+    for _ in range(3):
+        o = torch.zeros_like(o_sim)
+        cuda_backend.groupnorm(x0, C0, x1, C1, n_inst, rows, 32, 1e-5, g, b, silu, o)
+        outs.append(o)
+    torch.cuda.synchronize()
+    _report("gn fused vs F.group_norm", outs[0], want, 4e-3)
+    _report("gn fused vs sim", outs[0], o_sim, 4e-3)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert int(cuda_backend._gn_sync.view(torch.int32).abs().sum()) == 0  # counters and accumulators back to zero
+
+
 # ------------------------------------------------------------------------------------------------ small kernels
 def test_conv_in_and_out(cuda_backend):
     B, Bs, Cl, F, h, w = 2, 1, 4, 5, 8, 12
