@@ -21,7 +21,8 @@ def main(path, top=45):
             for r in csv.DictReader(lines)]
     starts = [i for i, r in enumerate(rows) if r[0].startswith("timestep_features")]
     ends = [i for i, r in enumerate(rows) if r[0].startswith("cfg_step")]
-    a, b = starts[-1], ends[-1]
+    b = ends[-1]
+    a = [i for i in starts if i < b][-1]  # the capture may end inside a later, incomplete step
     step = rows[a:b + 1]
     total = sum(r[3] for r in step)
     print(f"# last step: launches {a}..{b} ({len(step)} kernels), sum of kernel durations {total / 1e3:.3f} ms "
