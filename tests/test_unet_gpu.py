@@ -91,6 +91,30 @@ def test_unet_vs_oracle_fresh_seed_and_frame_varying_context(cuda_backend):
     _check("no audio mask", y2, ref2, TOL_TOY)
 
 
+@pytest.mark.parametrize("B,F,h,w,n_text,masked", [(1, 8, 24, 40, 77, True), (3, 4, 8, 16, 77, True),
+                                                     (2, 16, 8, 8, 5, True), (2, 24, 16, 16, 77, False),
+                                                     (2, 1, 8, 8, 77, True), (2, 12, 8, 24, 1, True)])
+def test_unet_geometry_sweep(cuda_backend, B, F, h, w, n_text, masked):
+    """Shapes off the headline path: no CFG (B = 1) and 3-way CFG, non-square latents whose rows are not a multiple of
+    the 128-row tile, 1 / 16 / 24 frames (config 4's frame count), 1 .. 77 text keys, with and without the audio
+    segment mask - each against the CPU oracle on a fresh seed."""
+    from oracle import unet_ref
+    chans = (64, 128, 256, 256)
+    m, sd = _model(chans)
+    g = torch.Generator().manual_seed(1000 + 31 * B + 7 * F + h + w + n_text)
+    x = torch.randn(B, 4, F, h, w, generator=g)
+    text = torch.randn(B, 1, n_text, 768, generator=g).expand(B, F, n_text, 768).contiguous()
+    audio = torch.randn(B, 1, 229, 768, generator=g).expand(B, F, 229, 768).contiguous()
+    mask = synth.audio_segment_mask(F)[None].expand(B, -1, -1).contiguous() if masked else None
+    t = 11 + 40 * F
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, t, text, audio, mask)
+    for rep in range(2):  # first call (tuning pass + capture) and the replay
+        y = m(x.cuda(), t, encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
+              audio_attention_mask=mask.cuda() if masked else None).sample
+        _check(f"B{B} F{F} {h}x{w} text{n_text} mask{int(masked)} call {rep}", y, ref, TOL_TOY)
+
+
 @pytest.mark.parametrize("name", ["ddim", "pndm"])
 def test_sampler_trace_vs_golden(cuda_backend, name):
     from avgen.pipelines.pipeline_audio_cond_animation import AudioCondAnimationPipeline
