@@ -258,6 +258,12 @@ __device__ __forceinline__ void umma_bf16_ss_pair_p(uint32_t pred, uint32_t tmem
 // ----------------------------------------------------------------------------------------------
 // TMA tiled loads (global -> shared, completion on an mbarrier)
 // ----------------------------------------------------------------------------------------------
+// L2 prefetch of a 2-D tensor-map box (a hint: no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

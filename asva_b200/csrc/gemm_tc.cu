@@ -41,7 +41,8 @@ struct GemmKParams {
   SegK seg[ASVA_GEMM_MAX_SEG];
   int32_t box[3], trav[3], out_dims[3], tiles[3];
   int32_t rows_per_tile, N, n_out, num_kb, n_tiles_n, mn_tiles, total_tiles, split_k, kb_per_split;
-  int32_t n_stages, n_res, n_res_slots, out_fp32, dbg;  // dbg (ASVA_GEMM_DBG): 1 = skip TMA loads, 2 = skip MMAs (timing only)
+  int32_t n_stages, n_res, n_res_slots, out_fp32, dbg;
+  int32_t pf_blocks, w_kblocks;  // W prefetch: blocks per CTA (0 = off), 64-column blocks of W that exist  // dbg (ASVA_GEMM_DBG): 1 = skip TMA loads, 2 = skip MMAs (timing only)
   const float* bias;
   const float* add_ptr;
   int64_t add_ld;
@@ -143,6 +144,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Weights do not depend on the previous kernel: while that kernel is still finishing, the CTAs of this one pull W
+  // from HBM into L2 (the 2.3 GB of weights per step never survive in L2 from one step to the next) - the whole matrix,
+  // dealt out block by block (64 columns x the TMA box rows) over the grid, earliest K blocks first, up to a cap per CTA.
+  if (warp == 2 && lane == 0 && p.pf_blocks > 0) {
+    const int row_boxes = (p.N + BN / CG - 1) / (BN / CG);
+    const int total = p.w_kblocks * row_boxes;
+    int n = 0;
+    for (int b = blockIdx.x; b < total && n < p.pf_blocks; b += gridDim.x, ++n) {
+      const int kbx = b / row_boxes, rbx = b - kbx * row_boxes;
+      tma_prefetch_l2_2d(&p.tmW, kbx * 64, rbx * (BN / CG));
+    }
+  }
   pdl_wait();  // everything above overlapped the previous kernel's tail; its results are read from here on
 
   // The producer and MMA loops run in one thread each and are paced by their own instruction and mbarrier latency,
@@ -879,6 +892,15 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   kp.n_stages = plan.stages;
   kp.n_res_slots = res_slots_for(bn, plan.cg, kp.n_res, kp.out_fp32, kp.kb_per_split);
   kp.dbg = env_int("ASVA_GEMM_DBG");
+  {
+    static int pf = -2;
+    if (pf == -2) {
+      const char* e = getenv("ASVA_GEMM_PF");
+      pf = e ? atoi(e) : 64;
+    }
+    kp.pf_blocks = pf;
+    kp.w_kblocks = d->wcols / 64;
+  }
   ASVA_REQUIRE(plan.stages >= 2, "asva_gemm: no shared memory left for a pipeline (block_n=%d)", bn);
   ASVA_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "asva_gemm: unsupported block_n=%d", bn);
   ASVA_REQUIRE(plan.cg == 1 || plan.cg == 2, "asva_gemm: cta_group must be 0 (auto), 1 or 2");

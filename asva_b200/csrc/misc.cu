@@ -80,37 +80,61 @@ __global__ void __launch_bounds__(256) conv_out_finish_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 // Skinny linear (M <= 32 rows): one warp per output column, 16-byte weight loads, rows in groups of 4.
 // ------------------------------------------------------------------------------------------------
+// The weights never depend on the previous kernel, the activations do: a warp pulls its whole weight row into registers
+// (K <= 2048) BEFORE the programmatic-dependent-launch wait, so the 51.6 MB time_emb_proj matrix streams from HBM
+// while the tiny kernels in front of it are still running, and only then stages x.
+constexpr int kSlChunks = 8;  // 8 x 256 elements per warp row held in registers
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x,
                                                            const __nv_bfloat16* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out,
                                                            int M, int N, int K, int act_in, int act_out) {
   pdl_trigger();
-  pdl_wait();
   extern __shared__ float xs[];  // [4][K]
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const bool held = K <= 256 * kSlChunks;
+  uint4 wreg[kSlChunks];
+  if (held && n < N) {
+    const __nv_bfloat16* wr = w + static_cast<int64_t>(n) * K;
+#pragma unroll
+    for (int i = 0; i < kSlChunks; ++i) {
+      const int k = lane * 8 + i * 256;
+      wreg[i] = (k < K) ? __ldg(reinterpret_cast<const uint4*>(wr + k)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  pdl_wait();
   const int m0 = blockIdx.y * 4;
   const int mrows = min(4, M - m0);
-  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) {
-    const int r = i / K, k = i % K;
-    float v = (r < mrows) ? x[static_cast<int64_t>(m0 + r) * K + k] : 0.f;
-    if (act_in == 1) v = silu_f(v);
-    xs[i] = v;
+  for (int r = 0; r < 4; ++r) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float v = (r < mrows) ? x[static_cast<int64_t>(m0 + r) * K + k] : 0.f;
+      if (act_in == 1) v = silu_f(v);
+      xs[r * K + k] = v;
+    }
   }
   __syncthreads();
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= N) return;
-  const int lane = threadIdx.x & 31;
   const __nv_bfloat16* wr = w + static_cast<int64_t>(n) * K;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k = lane * 8; k < K; k += 256) {
-    const uint4 u = *reinterpret_cast<const uint4*>(wr + k);
+  auto mac = [&](const uint4& u, int k) {
     const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     const float wv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const float* xr = xs + r * K + k;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[r] += wv[j] * xr[j];
+      const float4 x0 = *reinterpret_cast<const float4*>(xs + r * K + k);
+      const float4 x1 = *reinterpret_cast<const float4*>(xs + r * K + k + 4);
+      acc[r] += wv[0] * x0.x + wv[1] * x0.y + wv[2] * x0.z + wv[3] * x0.w + wv[4] * x1.x + wv[5] * x1.y +
+                wv[6] * x1.z + wv[7] * x1.w;
     }
+  };
+  if (held) {
+#pragma unroll
+    for (int i = 0; i < kSlChunks; ++i) {
+      const int k = lane * 8 + i * 256;
+      if (k < K) mac(wreg[i], k);
+    }
+  } else {
+    for (int k = lane * 8; k < K; k += 256) mac(*reinterpret_cast<const uint4*>(wr + k), k);
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
