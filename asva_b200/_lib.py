@@ -53,6 +53,8 @@ class GemmDesc(C.Structure):
         ("split_k", C.c_int32),
         ("ws", C.c_void_p),
         ("ws_bytes", C.c_int64),
+        ("epilogue", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -71,9 +73,10 @@ class AttnDesc(C.Structure):
 ABI = {
     "asva_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "asva_gemm_plan": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "asva_gemm_tune": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
-                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_float)]),
     "asva_attention": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p]),
     "asva_temporal_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_float, C.c_void_p]),

@@ -96,7 +96,7 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128_mn(uint32_t saddr, uint32_t
 // block of tP pixels of one (clip, head): its tP*tF (<= KV) rows, ordered (frame, pixel), are both the queries and the
 // single key tile, fetched with 5-D boxes straight from the [b][f][n][3C] projection output; row r attends key c iff
 // they belong to the same pixel (c % tP == r % tP) - a block-diagonal mask evaluated arithmetically.
-template <int DKA, int KV, int NWG, int STAGES, int NB, bool TEMPORAL>
+template <int DKA, int KV, int NWG, int STAGES, int NB, bool TEMPORAL, int POLY = kPolyOf8, bool PIPE = true>
 __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<DKA, KV, NWG, STAGES, NB>;
   static_assert(STAGES >= (NB + 1) * NWG, "key ring too shallow for the tiles in flight");
@@ -404,41 +404,61 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
         };
         // exponentiate against offset m_off, write the bf16 P tile (K-major, 128B swizzle), return the raw row max
         // (the row sums come out of the tensor core: see the ones MMA next to P V)
+        // one 32-column chunk: exponentiate, pack to bf16, store into the swizzled P tile
+        auto exp_chunk = [&](const uint32_t (&sv)[32], int c, float m_off, float& mt) {
+          float pv[32];
+          if (plain) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              mt = fmaxf(mt, __uint_as_float(sv[i]));
+              const float x = fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_off);
+              pv[i] = ((i & 7) < POLY) ? poly_exp2(x) : fast_exp2(x);  // balance the MUFU and FMA pipes
+            }
+          } else {
+            const uint32_t mbits = chunk_mask(c);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const bool keep = (mbits >> i) & 1u;
+              mt = fmaxf(mt, keep ? __uint_as_float(sv[i]) : -INFINITY);
+              pv[i] = keep ? fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_off)) : 0.f;
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+          const uint32_t patom = prow_s + static_cast<uint32_t>(c >> 6) * (128u * 128u);
+          const uint32_t chunk0 = static_cast<uint32_t>((c & 63) >> 3);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint32_t phys = (chunk0 + v) ^ sw;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(patom + phys * 16u), "r"(pk[4 * v]),
+                         "r"(pk[4 * v + 1]), "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
+                         : "memory");
+          }
+        };
+        // exponentiate against offset m_off, write the bf16 P tile (K-major, 128B swizzle), return the raw row max
+        // (the row sums come out of the tensor core: see the ones MMA next to P V)
         auto exp_pass = [&](float m_off, float& mt) {
           mt = -INFINITY;
-#pragma unroll 1
-          for (int c = 0; c < cols; c += 32) {
-            uint32_t sv[32];
-            tmem_ld_x32(tmem_S + lane_base + c, sv);
+          if constexpr (KV == 64 && !TEMPORAL && PIPE) {
+            // two chunks: the second TMEM load is in flight while the first chunk is exponentiated
+            uint32_t s0[32], s1[32];
+            tmem_ld_x32(tmem_S + lane_base, s0);
             tmem_ld_wait();
-            float pv[32];
-            if (plain) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                mt = fmaxf(mt, __uint_as_float(sv[i]));
-                const float x = fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_off);
-                pv[i] = ((i & 7) < kPolyOf8) ? poly_exp2(x) : fast_exp2(x);  // balance the MUFU and FMA pipes
-              }
-            } else {
-              const uint32_t mbits = chunk_mask(c);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const bool keep = (mbits >> i) & 1u;
-                mt = fmaxf(mt, keep ? __uint_as_float(sv[i]) : -INFINITY);
-                pv[i] = keep ? fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_off)) : 0.f;
-              }
+            const bool two = cols > 32;
+            if (two) tmem_ld_x32(tmem_S + lane_base + 32, s1);
+            exp_chunk(s0, 0, m_off, mt);
+            if (two) {
+              tmem_ld_wait();
+              exp_chunk(s1, 32, m_off, mt);
             }
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-            const uint32_t patom = prow_s + static_cast<uint32_t>(c >> 6) * (128u * 128u);
-            const uint32_t chunk0 = static_cast<uint32_t>((c & 63) >> 3);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const uint32_t phys = (chunk0 + v) ^ sw;
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(patom + phys * 16u), "r"(pk[4 * v]),
-                           "r"(pk[4 * v + 1]), "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
-                           : "memory");
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < cols; c += 32) {
+              uint32_t sv[32];
+              tmem_ld_x32(tmem_S + lane_base + c, sv);
+              tmem_ld_wait();
+              exp_chunk(sv, c, m_off, mt);
             }
           }
         };
@@ -527,13 +547,13 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
 
 static int g_attn_sms = 0;
 
-template <int DKA, int KV, int NWG, int STAGES, int NB, bool TEMPORAL>
+template <int DKA, int KV, int NWG, int STAGES, int NB, bool TEMPORAL, int POLY = kPolyOf8, bool PIPE = true>
 static int launch_attn(const AttnKParams& kp, cudaStream_t stream) {
   using Cfg = AttnCfg<DKA, KV, NWG, STAGES, NB>;
   static_assert(Cfg::kSmemBytes <= 232448, "attention configuration exceeds the shared memory of an SM");
   static bool configured = false;
   if (!configured) {
-    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV, NWG, STAGES, NB, TEMPORAL>,
+    ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV, NWG, STAGES, NB, TEMPORAL, POLY, PIPE>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
@@ -544,7 +564,7 @@ static int launch_attn(const AttnKParams& kp, cudaStream_t stream) {
   }
   int grid = (kp.total_items + NWG - 1) / NWG;
   if (grid > g_attn_sms) grid = g_attn_sms;
-  ASVA_CUDA_OK(launch_k(attn_tc_kernel<DKA, KV, NWG, STAGES, NB, TEMPORAL>, dim3(grid), dim3(Cfg::kThreads),
+  ASVA_CUDA_OK(launch_k(attn_tc_kernel<DKA, KV, NWG, STAGES, NB, TEMPORAL, POLY, PIPE>, dim3(grid), dim3(Cfg::kThreads),
                         Cfg::kSmemBytes, stream, 1, kp));
   return 0;
 }
@@ -623,7 +643,28 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
   }
   int rc;
   switch (dka) {
-    case 1: rc = launch_attn<1, 64, 2, 8, 2, false>(kp, stream); break;
+    case 1: {
+      static int poly = -1;  // ASVA_ATTN_POLY=0..4: exponentials per 8 computed on the FMA pipes (experiments)
+      static bool pipe = true;  // ASVA_ATTN_PIPE=0: serial TMEM loads (the previous form, for A/B timing)
+      if (poly < 0) {
+        const char* e = getenv("ASVA_ATTN_POLY");
+        poly = (e != nullptr && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : kPolyOf8;
+        e = getenv("ASVA_ATTN_PIPE");
+        pipe = !(e != nullptr && e[0] == '0');
+      }
+      if (!pipe) {
+        rc = launch_attn<1, 64, 2, 8, 2, false, kPolyOf8, false>(kp, stream);
+        break;
+      }
+      switch (poly) {
+        case 0: rc = launch_attn<1, 64, 2, 8, 2, false, 0>(kp, stream); break;
+        case 1: rc = launch_attn<1, 64, 2, 8, 2, false, 1>(kp, stream); break;
+        case 2: rc = launch_attn<1, 64, 2, 8, 2, false, 2>(kp, stream); break;
+        case 4: rc = launch_attn<1, 64, 2, 8, 2, false, 4>(kp, stream); break;
+        default: rc = launch_attn<1, 64, 2, 8, 2, false, 3>(kp, stream); break;
+      }
+      break;
+    }
     case 2: rc = launch_attn<2, 64, 2, 4, 1, false>(kp, stream); break;
     default: rc = launch_attn<3, 64, 1, 3, 1, false>(kp, stream); break;
   }

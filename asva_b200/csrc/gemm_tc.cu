@@ -31,6 +31,7 @@ constexpr int kResSlotBytes = 8192;   // 128 rows x 32 bf16
 constexpr int kGemmThreads = 384;
 constexpr int kSmemLimit = 232448;    // 227 KB opt-in maximum per CTA
 constexpr int kBarBytes = 512;
+constexpr int kDefaultEpi = 1;          // epilogue form when neither the descriptor nor ASVA_GEMM_EPI chooses
 
 struct SegK {
   int32_t src, c0, off1, off2, off3, num_kb, wk, wk_first, fix2;
@@ -47,6 +48,11 @@ struct GemmKParams {
   const float* add_ptr;
   int64_t add_ld;
   int32_t add_div;
+  int32_t epi;  // 1 = panel epilogue (TMA residual ring, TMA stores), 2 = per-warp epilogue (direct loads / stores)
+  __nv_bfloat16* out_ptr;  // epi == 2 only
+  int64_t ldo;
+  const __nv_bfloat16* res_ptr[2];
+  int64_t res_ld[2];
 };
 
 struct TileCoord {
@@ -87,6 +93,147 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+
+// Per-warp epilogue (epi == 2; bf16 output, no GEGLU, no split-K). Every epilogue warp owns the 32 x 32 sub-panels of
+// its TMEM lane quadrant in alternate panels and runs on its own - no group barriers, no TMA residual ring, no
+// staging/TMA-store round trip: tcgen05.ld (thread = row) -> fp32 transpose through a private 4 KB shared slab
+// (16-byte chunks XOR-swizzled by the row, conflict free both ways) -> 4 lanes per row add bias / row addend /
+// residuals to their 8 columns and store 16 bytes each (a warp instruction covers 8 rows x 64 contiguous bytes, whole
+// sectors). Residuals are plain global loads in the same layout, fetched one panel ahead - the first panel of a tile
+// while the warp still waits for the tile's accumulator - so L2 latency is off the per-panel chain.
+template <int BN, int CG>
+__device__ __forceinline__ void epilogue_direct(const GemmKParams& p, int warp, int lane, int rank, int tile0,
+                                                int tile_step, uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                                uint64_t* tmem_empty_bar, uint8_t* slabs) {
+  const uint32_t g = static_cast<uint32_t>(warp - 4) >> 2;
+  const int qd = warp & 3;
+  const uint32_t slab = smem_u32(slabs) + static_cast<uint32_t>(warp - 4) * 4096u;
+  const int cp = lane & 3;     // which 8-column chunk of a panel this lane finishes
+  const int rsub = lane >> 2;  // its row inside each 8-row slab
+  int q1[4], q2[4], q3[4];
+  bool in_tile[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int tr = qd * 32 + it * 8 + rsub;
+    q1[it] = tr % p.box[0];
+    q2[it] = (tr / p.box[0]) % p.box[1];
+    q3[it] = tr / (p.box[0] * p.box[1]);
+    in_tile[it] = tr < p.rows_per_tile;
+  }
+  const uint32_t wr_base = slab + static_cast<uint32_t>(lane) * 128u;
+  const uint32_t wr_x = static_cast<uint32_t>(lane & 7);
+  const uint32_t rd0 = static_cast<uint32_t>(((2 * cp) ^ rsub) << 4), rd1 = static_cast<uint32_t>(((2 * cp + 1) ^ rsub) << 4);
+  uint32_t pc = 0, t = 0;
+  for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
+    const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
+    const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
+    const int n_panels = tile_panels<BN, false>(p, tc.n0);
+    int grow[4], arow[4];  // global output row of each of the lane's 4 rows (-1: does not exist), its addend row
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int a1 = tc.o1 + q1[it], a2 = tc.o2 + q2[it], a3 = tc.o3 + q3[it];
+      const bool ok = in_tile[it] && (a1 < p.out_dims[0]) && (a2 < p.out_dims[1]) && (a3 < p.out_dims[2]);
+      grow[it] = ok ? (a3 * p.out_dims[1] + a2) * p.out_dims[0] + a1 : -1;
+      arow[it] = ok ? grow[it] / p.add_div : 0;
+    }
+    const int q_first = ((pc & 1u) == g) ? 0 : 1;
+    int q_last = n_panels - 1;
+    if (((pc + q_last) & 1u) != g) --q_last;
+    uint4 cur[2][4];
+    auto load_res = [&](int q, uint4 (&dst)[2][4]) {
+      const int col = tc.n0 + q * 32 + cp * 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          dst[i][it] = make_uint4(0u, 0u, 0u, 0u);
+          if (i < p.n_res && grow[it] >= 0 && col < p.N)
+            dst[i][it] = *reinterpret_cast<const uint4*>(p.res_ptr[i] + static_cast<int64_t>(grow[it]) * p.res_ld[i] + col);
+        }
+      }
+    };
+    if (q_first <= q_last) load_res(q_first, cur);
+    mbar_wait(&tmem_full_bar[acc], acc_ph);
+    tc_fence_after();
+    if (q_last < q_first) {  // no panel of this tile is ours: hand the accumulator back right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_pair_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]);
+      }
+    }
+    const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(qd * 32) << 16);
+#pragma unroll 1
+    for (int q = q_first; q <= q_last; q += 2) {
+      const int col = tc.n0 + q * 32 + cp * 8;
+      const bool cok = col < p.N;
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (p.bias != nullptr && cok) {
+        b0 = ldg4(p.bias + col);
+        b1 = ldg4(p.bias + col + 4);
+      }
+      {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + q * 32, v);
+        tmem_ld_wait();
+        if (q == q_last) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_pair_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(wr_base + ((static_cast<uint32_t>(j) ^ wr_x) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      __syncwarp();
+      uint4 nxt[2][4];
+      const bool more = q + 2 <= q_last;
+      if (more) load_res(q + 2, nxt);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint32_t ra = slab + static_cast<uint32_t>(it * 8 + rsub) * 128u;
+        float4 x0 = ld_shared_f4(ra + rd0), x1 = ld_shared_f4(ra + rd1);
+        x0.x += b0.x; x0.y += b0.y; x0.z += b0.z; x0.w += b0.w;
+        x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
+        const bool ok = grow[it] >= 0 && cok;
+        if (p.add_ptr != nullptr && ok) {
+          const float* ap = p.add_ptr + static_cast<int64_t>(arow[it]) * p.add_ld + col;
+          const float4 a0 = ldg4(ap), a1 = ldg4(ap + 4);
+          x0.x += a0.x; x0.y += a0.y; x0.z += a0.z; x0.w += a0.w;
+          x1.x += a1.x; x1.y += a1.y; x1.z += a1.z; x1.w += a1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (i < p.n_res) {
+            const uint4 w = cur[i][it];
+            const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z), f3 = unpack_bf16x2(w.w);
+            x0.x += f0.x; x0.y += f0.y; x0.z += f1.x; x0.w += f1.y;
+            x1.x += f2.x; x1.y += f2.y; x1.z += f3.x; x1.w += f3.y;
+          }
+        }
+        if (ok) {
+          uint4 w;
+          w.x = pack_bf16x2(x0.x, x0.y);
+          w.y = pack_bf16x2(x0.z, x0.w);
+          w.z = pack_bf16x2(x1.x, x1.y);
+          w.w = pack_bf16x2(x1.z, x1.w);
+          *reinterpret_cast<uint4*>(p.out_ptr + static_cast<int64_t>(grow[it]) * p.ldo + col) = w;
+        }
+      }
+      __syncwarp();  // every lane is done reading the slab before the next panel overwrites it
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) cur[i][it] = nxt[i][it];
+      }
+    }
+    pc += n_panels;
+  }
+}
 
 template <int BN, bool GEGLU, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
@@ -293,6 +440,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       }
     }
     __syncwarp();
+  } else if (warp >= 4 && !GEGLU && p.epi == 2) {
+    epilogue_direct<BN, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar, tmem_empty_bar, out_ring);
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const uint32_t g = static_cast<uint32_t>(warp - 4) >> 2;
@@ -557,7 +706,7 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
 static int g_num_sms = 0;
 
 struct GemmPlan {
-  int bn, split, stages, cg;
+  int bn, split, stages, cg, epi;
 };
 
 static int fixed_smem(int res_slots, int out_fp32) {
@@ -615,13 +764,17 @@ static int env_int(const char* name) {
 }
 
 static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, int num_kb, int n_res, int sms) {
-  static int env_bn = -1, env_split = -1, env_cg = -1;
+  static int env_bn = -1, env_split = -1, env_cg = -1, env_epi = -1;
   if (env_bn < 0) {
     env_bn = env_int("ASVA_GEMM_BN");
     env_split = env_int("ASVA_GEMM_SPLIT");
     env_cg = env_int("ASVA_GEMM_CG");
+    env_epi = env_int("ASVA_GEMM_EPI");
   }
-  GemmPlan best{128, 1, 2, 1};
+  GemmPlan best{128, 1, 2, 1, 1};
+  // epilogue form: the per-warp one exists for bf16, non-GEGLU, non-split outputs; explicit request > env > default
+  int want_epi = d->epilogue ? d->epilogue : (env_epi ? env_epi : kDefaultEpi);
+  if (d->geglu || d->out_fp32) want_epi = 1;
   const int bns[4] = {64, 128, 160, 256};
   const int splits[10] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
   const int want_bn = d->geglu ? 128 : (d->block_n ? d->block_n : env_bn);
@@ -645,7 +798,7 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
         if (sp > max_split || sp > num_kb) continue;
         const int kbps = (num_kb + sp - 1) / sp;
         if ((num_kb + kbps - 1) / kbps != sp) continue;  // would leave an empty split
-        const int nr = sp > 1 ? 0 : n_res;
+        const int nr = (sp > 1 || want_epi == 2) ? 0 : n_res;
         if (stages_for(bn, cg, nr, sp > 1 ? 1 : d->out_fp32, (num_kb + sp - 1) / sp) < 2) continue;
         const double c = plan_cost(bn, cg, sp, d->N, m_tiles, num_kb, M, sms);
         if (c < best_cost) {
@@ -657,7 +810,8 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
       }
     }
   }
-  const int nr = best.split > 1 ? 0 : n_res;
+  best.epi = best.split > 1 ? 1 : want_epi;
+  const int nr = (best.split > 1 || best.epi == 2) ? 0 : n_res;
   best.stages = stages_for(best.bn, best.cg, nr, best.split > 1 ? 1 : d->out_fp32, (num_kb + best.split - 1) / best.split);
   const int cap = env_int("ASVA_GEMM_STAGES");
   if (cap >= 2 && best.stages > cap) best.stages = cap;
@@ -738,7 +892,7 @@ static int compute_plan(const asva_gemm_desc* d, asva::GemmPlan* out) {
 }
 
 extern "C" int asva_gemm_plan(const asva_gemm_desc* d, int32_t* block_n, int32_t* split_k, int32_t* cta_group,
-                              int32_t* stages) {
+                              int32_t* stages, int32_t* epilogue) {
   asva::GemmPlan pl;
   const int rc = compute_plan(d, &pl);
   if (rc != 0) return rc;
@@ -746,11 +900,12 @@ extern "C" int asva_gemm_plan(const asva_gemm_desc* d, int32_t* block_n, int32_t
   if (split_k) *split_k = pl.split;
   if (cta_group) *cta_group = pl.cg;
   if (stages) *stages = pl.stages;
+  if (epilogue) *epilogue = pl.epi;
   return 0;
 }
 
 extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, int32_t reps, int32_t* block_n,
-                              int32_t* split_k, int32_t* cta_group, float* best_us) {
+                              int32_t* split_k, int32_t* cta_group, int32_t* epilogue, float* best_us) {
   using namespace asva;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ASVA_REQUIRE(d != nullptr && block_n && split_k && cta_group, "asva_gemm_tune: null argument");
@@ -761,18 +916,20 @@ extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, in
   const int bns[4] = {64, 128, 160, 256};
   const int splits[6] = {1, 2, 3, 4, 6, 8};
   float best = 1e30f;
-  int rc = 0, bb = 0, bs = 0, bc = 0;
-  for (int cg = 1; cg <= 2 && rc == 0; ++cg) {
+  int rc = 0, bb = 0, bs = 0, bc = 0, be = 0;
+  for (int ce = 0; ce < 2 * 2 && rc == 0; ++ce) {
+    const int cg = 1 + (ce >> 1), epi = 1 + (ce & 1);
     for (int bi = 0; bi < 4 && rc == 0; ++bi) {
       for (int si = 0; si < 6 && rc == 0; ++si) {
         asva_gemm_desc c = *d;
         c.block_n = d->geglu ? 128 : bns[bi];
         c.split_k = splits[si];
         c.cta_group = cg;
+        c.epilogue = epi;
         if (d->geglu && (bi != 1 || si != 0)) continue;
         GemmPlan pl;
         if (compute_plan(&c, &pl) != 0) continue;
-        if (pl.bn != c.block_n || pl.split != c.split_k || pl.cg != c.cta_group) continue;  // not feasible
+        if (pl.bn != c.block_n || pl.split != c.split_k || pl.cg != c.cta_group || pl.epi != epi) continue;  // not feasible
         if ((rc = asva_gemm(&c, stream_)) != 0) break;  // warm-up (also first-use kernel attribute setup)
         cudaEventRecord(e0, stream);
         for (int r = 0; r < reps && rc == 0; ++r) rc = asva_gemm(&c, stream_);
@@ -790,6 +947,7 @@ extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, in
           bb = c.block_n;
           bs = c.split_k;
           bc = cg;
+          be = epi;
         }
       }
     }
@@ -801,6 +959,7 @@ extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, in
   *block_n = bb;
   *split_k = bs;
   *cta_group = bc;
+  if (epilogue) *epilogue = be;
   if (best_us) *best_us = best;
   return 0;
 }
@@ -890,7 +1049,17 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   kp.n_res = split ? 0 : n_res;
   kp.out_fp32 = split ? 1 : d->out_fp32;
   kp.n_stages = plan.stages;
-  kp.n_res_slots = res_slots_for(bn, plan.cg, kp.n_res, kp.out_fp32, kp.kb_per_split);
+  kp.epi = plan.epi;
+  const bool direct = plan.epi == 2;
+  kp.n_res_slots = direct ? 0 : res_slots_for(bn, plan.cg, kp.n_res, kp.out_fp32, kp.kb_per_split);
+  if (direct) {
+    kp.out_ptr = reinterpret_cast<__nv_bfloat16*>(d->out);
+    kp.ldo = d->ldo;
+    for (int i = 0; i < n_res; ++i) {
+      kp.res_ptr[i] = reinterpret_cast<const __nv_bfloat16*>(res[i]);
+      kp.res_ld[i] = res_ld[i];
+    }
+  }
   kp.dbg = env_int("ASVA_GEMM_DBG");
   {
     static int pf = -2;
@@ -952,7 +1121,7 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
                        rbox, rel);
     if (rc != 0) return rc;
   }
-  for (int i = 0; i < kp.n_res; ++i) {
+  for (int i = 0; i < (direct ? 0 : kp.n_res); ++i) {
     uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->out_dims[0], (uint64_t)d->out_dims[1], (uint64_t)d->out_dims[2]};
     const uint64_t ld = (uint64_t)res_ld[i] * 2u;
     uint64_t strides[3] = {ld, ld * dims[1], ld * dims[1] * dims[2]};
@@ -960,7 +1129,7 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
     if (rc != 0) return rc;
   }
   if (kp.n_res < 2) kp.tmR1 = kp.tmR0;
-  if (kp.n_res < 1) kp.tmR0 = kp.tmR1 = kp.tmO;
+  if (kp.n_res < 1 || direct) kp.tmR0 = kp.tmR1 = kp.tmO;
 
   kp.n_tiles_n = (d->N + bn - 1) / bn;
   ASVA_REQUIRE(m_tiles * kp.n_tiles_n * plan.split < (1ll << 31), "asva_gemm: too many tiles");

@@ -67,6 +67,7 @@ class GemmSpec:
     block_n: int = 0    # 0 = let the library choose (cost model); the engine's tuner sets measured choices
     split_k: int = 0
     cta_group: int = 0
+    epilogue: int = 0   # 0 = auto, 1 = panel (TMA) epilogue, 2 = per-warp (direct) epilogue
 
     def __post_init__(self):
         k = 0
@@ -230,7 +231,8 @@ class CudaBackend:
             for line in f:
                 if line.strip():
                     k, v = line.rstrip("\n").split(" => ")
-                    self.plan_cache[ast.literal_eval(k)] = tuple(ast.literal_eval(v))
+                    v = tuple(ast.literal_eval(v))
+                    self.plan_cache[ast.literal_eval(k)] = v + (0,) * (4 - len(v))  # older files: no epilogue field
 
     def save_plans(self, path: str = "") -> None:
         path = path or self._plan_file
@@ -299,27 +301,27 @@ class CudaBackend:
                 s.out_fp32, tuple(None if a is None else a.dims for a in s.a))
 
     def gemm(self, s: GemmSpec) -> None:
-        if s.block_n == 0 and s.split_k == 0 and s.cta_group == 0:
+        if s.block_n == 0 and s.split_k == 0 and s.cta_group == 0 and s.epilogue == 0:
             sig = self.gemm_signature(s)
             plan = self.plan_cache.get(sig)
             if plan is None and self.tuning:
                 d = self._gemm_desc(s)
-                bn, sp, cg, us = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_float(0.0)
+                bn, sp, cg, ep, us = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_float(0.0)
                 _lib.check(self.lib.asva_gemm_tune(d, self._stream(), 3, C.byref(bn), C.byref(sp), C.byref(cg),
-                                                   C.byref(us)), "asva_gemm_tune")
-                plan = (bn.value, sp.value, cg.value)
+                                                   C.byref(ep), C.byref(us)), "asva_gemm_tune")
+                plan = (bn.value, sp.value, cg.value, ep.value)
                 self.plan_cache[sig] = plan
             if plan is not None:
-                s.block_n, s.split_k, s.cta_group = plan
+                s.block_n, s.split_k, s.cta_group, s.epilogue = (tuple(plan) + (0,) * 4)[:4]
         d = self._gemm_desc(s)
         with self._timed('gemm'):
             _lib.check(self.lib.asva_gemm(d, self._stream()), "asva_gemm")
         self.launches += 2 if (s.split_k or self.gemm_plan(s, d)[1]) > 1 else 1  # split-K adds the reduce kernel
 
     def gemm_plan(self, s: GemmSpec, d=None) -> tuple:
-        """(block_n, split_k, cta_group, stages) the library will use for this spec."""
+        """(block_n, split_k, cta_group, stages, epilogue) the library will use for this spec."""
         d = self._gemm_desc(s) if d is None else d
-        v = [C.c_int32(0) for _ in range(4)]
+        v = [C.c_int32(0) for _ in range(5)]
         _lib.check(self.lib.asva_gemm_plan(d, *[C.byref(x) for x in v]), "asva_gemm_plan")
         return tuple(x.value for x in v)
 
@@ -365,7 +367,7 @@ class CudaBackend:
         d.geglu, d.out_fp32 = int(s.geglu), int(s.out_fp32)
         assert s.out.dtype == (torch.float32 if s.out_fp32 else torch.bfloat16)
         d.out, d.ldo = s.out.data_ptr(), s.ldo
-        d.block_n, d.split_k, d.cta_group = s.block_n, s.split_k, s.cta_group
+        d.block_n, d.split_k, d.cta_group, d.epilogue = s.block_n, s.split_k, s.cta_group, s.epilogue
         ws = self.splitk_ws()
         d.ws, d.ws_bytes = ws.data_ptr(), ws.numel() * 4
         return d

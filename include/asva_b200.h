@@ -91,19 +91,25 @@ typedef struct asva_gemm_desc {
                       kernel); ignored (off) when ws is too small or for GEGLU */
   void* ws;        /* device scratch for split-K partial sums, or NULL */
   int64_t ws_bytes;
+  int32_t epilogue; /* 0 = auto; 1 = panel epilogue (residual panels arrive by TMA, output leaves by TMA store);
+                       2 = per-warp epilogue (each warp finishes its own 32 x 32 sub-panels: direct residual loads
+                       and 16-byte stores; bf16, non-GEGLU, non-split outputs only - otherwise 1 is used) */
+  int32_t reserved;
 } asva_gemm_desc;
 
 int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream);
 
 /* The tile plan asva_gemm would use for `d` (its cost model's choice where block_n / split_k / cta_group are 0). */
-int asva_gemm_plan(const asva_gemm_desc* d, int32_t* block_n, int32_t* split_k, int32_t* cta_group, int32_t* stages);
+int asva_gemm_plan(const asva_gemm_desc* d, int32_t* block_n, int32_t* split_k, int32_t* cta_group, int32_t* stages,
+                   int32_t* epilogue);
 
-/* Measures every feasible (block_n, split_k, cta_group) plan of `d` on the device (CUDA events on `stream`, `reps`
+/* Measures every feasible (block_n, split_k, cta_group, epilogue) plan of `d` on the device (CUDA events on `stream`, `reps`
  * launches each after one warm-up) and returns the fastest.  Runs the GEMM repeatedly - the output (and anything that
  * aliases it) is scratch afterwards - and synchronises with the stream, so it must not be called during graph
- * capture.  Callers cache the result per problem shape and pass it in block_n / split_k / cta_group. */
+ * capture.  Callers cache the result per problem shape and pass it in block_n / split_k / cta_group /
+ * epilogue. */
 int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream, int32_t reps, int32_t* block_n, int32_t* split_k,
-                   int32_t* cta_group, float* best_us);
+                   int32_t* cta_group, int32_t* epilogue, float* best_us);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused softmax(Q K^T * scale [+ mask]) V on tcgen05 (flash-style online softmax, S and O in TMEM).

@@ -251,8 +251,8 @@ def test_plan_cache_roundtrip_and_signature(tmp_path):
     s2 = ops.spec_linear(x.clone(), w.clone(), torch.zeros(256, 640, dtype=torch.bfloat16), bias=bias.clone())
     s3 = ops.spec_linear(x, w, torch.zeros(256, 640, dtype=torch.bfloat16))  # no bias: a different epilogue
     assert be.gemm_signature(s1) == be.gemm_signature(s2) != be.gemm_signature(s3)
-    be.plan_cache[be.gemm_signature(s1)] = (160, 1, 2)
-    be.plan_cache[be.gemm_signature(s3)] = (128, 4, 1)
+    be.plan_cache[be.gemm_signature(s1)] = (160, 1, 2, 2)
+    be.plan_cache[be.gemm_signature(s3)] = (128, 4, 1, 1)
     path = str(tmp_path / "plans.txt")
     be.save_plans(path)
     be2 = ops.CudaBackend()

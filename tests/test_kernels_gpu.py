@@ -50,15 +50,33 @@ def _run_gemm_pair(be, spec, out_shape, out_dtype, fill=0.0):
     (256, 768, 640, 64), (256, 768, 640, 128), (200, 1280, 2560, 0), (24576, 320, 320, 0), (77, 768, 2560, 0),
     (16, 1280, 1280, 0),
 ])
-def test_gemm_linear(cuda_backend, M, K, N, bn):
+@pytest.mark.parametrize("epi", [1, 2])
+def test_gemm_linear(cuda_backend, M, K, N, bn, epi):
     x = _rand((M, K), 1)
     w = _rand((N, K), 2, 1.0 / math.sqrt(K))
     bias = _rand((N,), 3, dtype=torch.float32)
     res = _rand((M, N), 4)
     spec = ops.spec_linear(x, w, torch.empty(M, N, dtype=torch.bfloat16, device=DEV), bias=bias, res0=res)
-    spec.block_n = bn
-    got, ref = _run_gemm_pair(cuda_backend, spec, (M, N), torch.bfloat16)
-    _report(f"linear {M}x{K}x{N}", got, ref, 4e-3)
+    spec.block_n, spec.epilogue = bn, epi
+    got, ref = _run_gemm_pair(cuda_backend, spec, (M, N), torch.bfloat16, fill=7.0)
+    _report(f"linear {M}x{K}x{N} epi{epi}", got, ref, 4e-3)
+
+
+@pytest.mark.parametrize("M,K,N,bn,nres", [(1000, 640, 640, 128, 1), (1100, 320, 320, 160, 2), (2304, 1280, 1288, 256, 0),
+                                           (130, 640, 320, 64, 2)])
+def test_gemm_cta_pair_direct_epilogue(cuda_backend, M, K, N, bn, nres):
+    # CTA pairs (odd tile counts: the last pair's second tile does not exist) with the per-warp epilogue; N = 1288
+    # leaves a panel with a single 8-column chunk
+    x = _rand((M, K), 71)
+    w = _rand((N, K), 72, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 73, dtype=torch.float32)
+    r0, r1 = (_rand((M, N), 74) if nres > 0 else None), (_rand((M, N), 75) if nres > 1 else None)
+    spec = ops.spec_linear(x, w, torch.empty(M, N, dtype=torch.bfloat16, device=DEV), bias=bias, res0=r0, res1=r1)
+    spec.block_n, spec.split_k, spec.cta_group, spec.epilogue = bn, 1, 2, 2
+    got, ref = _run_gemm_pair(cuda_backend, spec, (M, N), torch.bfloat16, fill=7.0)
+    pl = cuda_backend.gemm_plan(spec)
+    assert pl[2] == 2 and pl[4] == 2, pl
+    _report(f"pair+direct {M}x{K}x{N} bn{bn}", got, ref, 4e-3)
 
 
 def test_gemm_linear_fp32_out_no_epilogue(cuda_backend):
@@ -93,13 +111,15 @@ def test_gemm_geglu(cuda_backend, M, C):
     (2, 16, 32, 320, 640, 1), (3, 32, 32, 320, 320, 2), (4, 8, 8, 1280, 1280, 2), (2, 6, 10, 128, 64, 1),
     (2, 16, 16, 960, 320, 1),
 ])
-def test_gemm_conv3x3(cuda_backend, n_img, h, w, Cin, Cout, stride):
+@pytest.mark.parametrize("epi", [1, 2])
+def test_gemm_conv3x3(cuda_backend, n_img, h, w, Cin, Cout, stride, epi):
     x = _rand((n_img * h * w, Cin), 13)
     wt = _rand((Cout, 9 * Cin), 14, 1.0 / math.sqrt(9 * Cin))
     bias = _rand((Cout,), 15, dtype=torch.float32)
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     spec = ops.spec_conv3x3(x, wt, torch.empty(n_img * ho * wo, Cout, dtype=torch.bfloat16, device=DEV),
                             n_img=n_img, h=h, wd=w, stride=stride, bias=bias)
+    spec.epilogue = epi
     got, ref = _run_gemm_pair(cuda_backend, spec, (n_img * ho * wo, Cout), torch.bfloat16)
     _report(f"conv3x3 {n_img}x{h}x{w} {Cin}->{Cout} s{stride}", got, ref, 4e-3)
     # and against torch's own conv2d (checks the K ordering convention of the spec, not only sim == cuda)
@@ -111,7 +131,8 @@ def test_gemm_conv3x3(cuda_backend, n_img, h, w, Cin, Cout, stride):
 
 @pytest.mark.parametrize("B,F,N,C", [(2, 12, 64, 320), (1, 8, 16, 1280), (2, 5, 100, 640), (2, 3, 256, 320),
                                      (3, 4, 16, 640)])
-def test_gemm_tconv(cuda_backend, B, F, N, C):
+@pytest.mark.parametrize("epi", [1, 2])
+def test_gemm_tconv(cuda_backend, B, F, N, C, epi):
     y = _rand((B * F * N, C), 16)
     w3 = _rand((C, 3 * C), 17, 0.02)
     bt = _rand((C,), 18, 0.1, dtype=torch.float32)
@@ -121,6 +142,7 @@ def test_gemm_tconv(cuda_backend, B, F, N, C):
     w4 = torch.cat([wc, wp, wh, (wh.float() + wp.float()).to(torch.bfloat16)], dim=1).contiguous()
     spec = ops.spec_tconv(y, w4, torch.empty(B * F * N, C, dtype=torch.bfloat16, device=DEV), B=B, F=F, N=N,
                           bias=bt, tproj=tproj, tproj_ld=C, res1=res1)
+    spec.epilogue = epi
     got, ref = _run_gemm_pair(cuda_backend, spec, (B * F * N, C), torch.bfloat16)
     _report(f"tconv {B}x{F}x{N}x{C}", got, ref, 4e-3)
     # direct restatement of FFInflatedConv3d's temporal part (utils.py:43-53) + tproj + extra residual
@@ -145,7 +167,8 @@ def test_gemm_split_k(cuda_backend, M, K, N, split, bn):
 
 
 @pytest.mark.parametrize("bn", [64, 128, 160, 256])
-def test_gemm_block_n_and_inplace_residual(cuda_backend, bn):
+@pytest.mark.parametrize("epi", [1, 2])
+def test_gemm_block_n_and_inplace_residual(cuda_backend, bn, epi):
     # every tile width, N not a multiple of it, two residuals one of which aliases the output (t = t + ...)
     M, K, N = 1000, 640, 960
     x = _rand((M, K), 55)
@@ -156,7 +179,7 @@ def test_gemm_block_n_and_inplace_residual(cuda_backend, bn):
     t_ref, t_cu = t0.clone(), t0.clone()
     s_ref = ops.spec_linear(x, w, t_ref, bias=bias, res0=t_ref, res1=r1)
     s_cu = ops.spec_linear(x, w, t_cu, bias=bias, res0=t_cu, res1=r1)
-    s_cu.block_n, s_cu.split_k = bn, 1
+    s_cu.block_n, s_cu.split_k, s_cu.epilogue = bn, 1, epi
     SimBackend().gemm(s_ref)
     cuda_backend.gemm(s_cu)
     torch.cuda.synchronize()

@@ -122,7 +122,7 @@ def main():
     lines = [f"# asva_gemm census, workload {args.workload}: {len(recorded)} launches/step, summed {tot / 1e3:.3f} ms, "
              f"{totfl / 1e9:.1f} GFLOP executed -> {totfl / tot / 1e6:.1f} TFLOP/s average (back-to-back launches replayed "
              f"from a CUDA graph, CUDA events)", "",
-             "| M | N | K | taps | trav | box | epilogue | plan bn/split/cg/stages | launches | us/launch | TFLOP/s | step us | share | cuBLAS us |",
+             "| M | N | K | taps | trav | box | epilogue | plan bn/split/cg/stages/epi | launches | us/launch | TFLOP/s | step us | share | cuBLAS us |",
              "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for sig, cnt, us, tf, tt, lib, plan in sorted(rows, key=lambda r: -r[4]):
         lines.append(f"| {sig[0]} | {sig[1]} | {sig[2]} | {sig[3]} | {sig[4]} | {sig[5]} | {sig[6]} | {'/'.join(str(x) for x in plan)} | {cnt} | {us:.1f} | "

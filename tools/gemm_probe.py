@@ -126,28 +126,33 @@ def main():
                 for sp in ((1,) if spec.geglu else [int(x) for x in args.splits.split(",")]):
                     if bn > 64 and bn >= 2 * spec.N:
                         continue
-                    out = torch.zeros_like(spec.out)
-                    s = dataclasses.replace(spec, out=out, block_n=bn, split_k=sp, cta_group=cg)
-                    try:
-                        us = time_spec(be, s)
-                    except _lib.AsvaError as e:
-                        rows.append((cg, bn, sp, None, str(e)[:60]))
-                        continue
-                    err = float((out.float() - ref.float()).norm() / ref.float().norm())
-                    rows.append((cg, bn, sp, us, err))
+                    for epi in ((1,) if (spec.geglu or spec.out_fp32 or sp > 1) else (1, 2)):
+                        out = torch.zeros_like(spec.out)
+                        s = dataclasses.replace(spec, out=out, block_n=bn, split_k=sp, cta_group=cg, epilogue=epi)
+                        try:
+                            us = time_spec(be, s)
+                        except _lib.AsvaError as e:
+                            rows.append((cg, bn, sp, epi, None, str(e)[:60]))
+                            continue
+                        err = float((out.float() - ref.float()).norm() / ref.float().norm())
+                        rows.append((cg, bn, sp, epi, us, err))
         auto = time_spec(be, dataclasses.replace(spec, out=torch.zeros_like(spec.out)))
-        best = min((r for r in rows if r[3] is not None), key=lambda r: r[3])
+        ok = [r for r in rows if r[4] is not None]
+        best = min(ok, key=lambda r: r[4])
+        b1 = min((r for r in ok if r[3] == 1), key=lambda r: r[4])
+        b2 = min((r for r in ok if r[3] == 2), key=lambda r: r[4], default=None)
         lines.append(f"## {name}: M={spec.M} N={spec.N} K={spec.K} segs={len(spec.segs)} box={spec.box}  "
-                     f"auto {auto:.1f} us; best cg={best[0]} bn={best[1]} split={best[2]} {best[3]:.1f} us "
-                     f"({fl / best[3] / 1e6:.0f} TFLOP/s)")
-        lines.append("| cg | bn | split | us | TFLOP/s | rel-L2 vs sim |")
-        lines.append("|---|---|---|---|---|---|")
-        for cg, bn, sp, us, err in rows:
+                     f"auto {auto:.1f} us; best cg={best[0]} bn={best[1]} split={best[2]} epi={best[3]} {best[4]:.1f} us "
+                     f"({fl / best[4] / 1e6:.0f} TFLOP/s); best panel-epilogue {b1[4]:.1f} us, best per-warp "
+                     f"{'-' if b2 is None else format(b2[4], '.1f')} us")
+        lines.append("| cg | bn | split | epi | us | TFLOP/s | rel-L2 vs sim |")
+        lines.append("|---|---|---|---|---|---|---|")
+        for cg, bn, sp, epi, us, err in rows:
             if us is None:
-                lines.append(f"| {cg} | {bn} | {sp} | - | - | {err} |")
+                lines.append(f"| {cg} | {bn} | {sp} | {epi} | - | - | {err} |")
             else:
                 flag = "" if err < 5e-3 else "  **BAD**"
-                lines.append(f"| {cg} | {bn} | {sp} | {us:.1f} | {fl / us / 1e6:.0f} | {err:.2e}{flag} |")
+                lines.append(f"| {cg} | {bn} | {sp} | {epi} | {us:.1f} | {fl / us / 1e6:.0f} | {err:.2e}{flag} |")
         lines.append("")
         print("\n".join(lines[-(len(rows) + 4):]), flush=True)
     if args.out:
