@@ -39,7 +39,7 @@ struct AttnKParams {
   float scale_log2;   // scale * log2(e)
 };
 
-constexpr int kPolyOf8 = 3;  // of every 8 exponentials of an unmasked tile, this many avoid the MUFU pipe
+constexpr int kPolyOf8 = 2;  // of every 8 exponentials of an unmasked tile, this many avoid the MUFU pipe
 
 // NB = S buffers in TMEM and P buffers in shared memory per warpgroup. NB = 2 lets the tensor core compute S(j+1) while
 // the softmax works on S(j), and lets the softmax write P(j) while P V(j-1) still reads P(j-1): the per-tile critical
@@ -652,16 +652,18 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
         e = getenv("ASVA_ATTN_PIPE");
         pipe = !(e != nullptr && e[0] == '0');
       }
-      if (!pipe) {
+      // overlapping the second chunk's TMEM load pays once an item has several key tiles (self-attention: -3 %); the
+      // one- and two-tile items of the cross-attentions run ~4 % faster with the leaner serial form (measured)
+      if (!pipe || d->Nk < 256) {
         rc = launch_attn<1, 64, 2, 8, 2, false, kPolyOf8, false>(kp, stream);
         break;
       }
       switch (poly) {
         case 0: rc = launch_attn<1, 64, 2, 8, 2, false, 0>(kp, stream); break;
         case 1: rc = launch_attn<1, 64, 2, 8, 2, false, 1>(kp, stream); break;
-        case 2: rc = launch_attn<1, 64, 2, 8, 2, false, 2>(kp, stream); break;
         case 4: rc = launch_attn<1, 64, 2, 8, 2, false, 4>(kp, stream); break;
-        default: rc = launch_attn<1, 64, 2, 8, 2, false, 3>(kp, stream); break;
+        case 3: rc = launch_attn<1, 64, 2, 8, 2, false, 3>(kp, stream); break;
+        default: rc = launch_attn<1, 64, 2, 8, 2, false, kPolyOf8>(kp, stream); break;
       }
       break;
     }

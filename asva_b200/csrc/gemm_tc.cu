@@ -773,8 +773,10 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
   }
   GemmPlan best{128, 1, 2, 1, 1};
   // epilogue form: the per-warp one exists for bf16, non-GEGLU, non-split outputs; explicit request > env > default
-  int want_epi = d->epilogue ? d->epilogue : (env_epi ? env_epi : kDefaultEpi);
+  // default (measured, profiles/r1_gemm_probe_v9.md): the per-warp form wins whenever there is a residual to add
+  int want_epi = d->epilogue ? d->epilogue : (env_epi ? env_epi : (n_res > 0 ? 2 : kDefaultEpi));
   if (d->geglu || d->out_fp32) want_epi = 1;
+  if (want_epi != 2) want_epi = 1;
   const int bns[4] = {64, 128, 160, 256};
   const int splits[10] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
   const int want_bn = d->geglu ? 128 : (d->block_n ? d->block_n : env_bn);

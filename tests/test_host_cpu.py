@@ -42,6 +42,32 @@ def test_library_exports_every_header_symbol():
     assert lib.asva_version() >= 100
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in asva_b200/_lib.py must have the size and field offsets a C compiler gives the structs of
+    include/asva_b200.h (a drifted field would silently shift every pointer behind it)."""
+    import ctypes
+    import subprocess
+    from asva_b200 import _lib
+    structs = {"asva_gemm_seg": _lib.GemmSeg, "asva_rowadd": _lib.RowAdd, "asva_gemm_desc": _lib.GemmDesc,
+               "asva_attn_desc": _lib.AttnDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "asva_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        cname, field, val = line.split()
+        cls = structs[cname]
+        want = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(val) == want, (cname, field, int(val), want)
+
+
 def test_product_has_no_cpu_fallback():
     from asva_b200._lib import AsvaError
     from avgen.models.unets import AudioUNet3DConditionModel

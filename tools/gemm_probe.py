@@ -56,6 +56,7 @@ SHAPES = {
     "conv3": lambda: conv(24, 4, 4, 1280, 1280),
     "conv3b": lambda: conv(24, 4, 4, 2560, 1280),
     "lin0": lambda: lin(24576, 320, 320),
+    "lin0p": lambda: lin(24576, 320, 320, res=False),
     "lin1": lambda: lin(6144, 640, 640),
     "lin2": lambda: lin(1536, 1280, 1280),
     "lin3": lambda: lin(384, 1280, 1280),
