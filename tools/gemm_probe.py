@@ -95,22 +95,24 @@ def main():
     ap.add_argument("--shapes", default=",".join(SHAPES))
     ap.add_argument("--out", default="")
     ap.add_argument("--splits", default="1,2,4,8")
-    ap.add_argument("--timeplan", default="", help="cg,bn,split: time just this plan")
-    ap.add_argument("--single", default="", help="cg,bn,split: launch just this plan 3 times eagerly (for ncu)")
+    ap.add_argument("--timeplan", default="", help="cg,bn,split[,epilogue]: time just this plan")
+    ap.add_argument("--single", default="", help="cg,bn,split[,epilogue]: launch just this plan 3 times eagerly (for ncu)")
     args = ap.parse_args()
     be = ops.backend()
     if args.timeplan:
-        cg, bn, sp = (int(x) for x in args.timeplan.split(","))
+        cg, bn, sp, epi = ([int(x) for x in args.timeplan.split(",")] + [0])[:4]
         for name in args.shapes.split(","):
             spec = SHAPES[name]()
-            s = dataclasses.replace(spec, out=torch.zeros_like(spec.out), block_n=bn, split_k=sp, cta_group=cg)
+            s = dataclasses.replace(spec, out=torch.zeros_like(spec.out), block_n=bn, split_k=sp, cta_group=cg,
+                                    epilogue=epi)
             print(f"{name} cg={cg} bn={bn} split={sp}: {time_spec(be, s):.1f} us")
         return
     if args.single:
-        cg, bn, sp = (int(x) for x in args.single.split(","))
+        cg, bn, sp, epi = ([int(x) for x in args.single.split(",")] + [0])[:4]
         for name in args.shapes.split(","):
             spec = SHAPES[name]()
-            s = dataclasses.replace(spec, out=torch.zeros_like(spec.out), block_n=bn, split_k=sp, cta_group=cg)
+            s = dataclasses.replace(spec, out=torch.zeros_like(spec.out), block_n=bn, split_k=sp, cta_group=cg,
+                                    epilogue=epi)
             for _ in range(3):
                 be.gemm(s)
             torch.cuda.synchronize()
