@@ -356,19 +356,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           ready = mbar_test_wait_a(empty0 + 8u * s2, ph2);
           const uint32_t sa = smem_a0 + s * kSuperBytes + j * kStageBytes;
           const uint32_t fb = full0_l + 8u * s;
-          if (kb < tc.kb1 && !(p.dbg & 1)) {
-            const int ccol = sg.c0 + kin * 64, wcol = wbase + kin * 64;
-            // pair: both CTAs load their half; all bytes are credited to the even CTA's barrier, armed by its producers
-            mbar_arrive_expect_tx_p(el_arm, fb, tx_bytes);
-            if constexpr (CG == 2) {
-              tma_load_4d_pair_p(el, sa, tmA, fb, ccol, c1, c2, c3);
-              tma_load_2d_pair_p(el, sa + kABytes, &p.tmW, fb, wcol, wn0);
+          if constexpr (CG == 2) {
+            // CTA pairs: the stage's instructions are issued by ONE thread from inside a branch on elect.sync - ptxas
+            // then keeps the operands in uniform registers and emits the instructions back to back, where predicating
+            // each instruction on an elected lane costs a vote / elect / retry sequence (~15 instructions) per TMA or
+            // MMA instruction. With neither loads nor MMAs a stage then costs ~300 instead of ~590 cycles
+            // (profiles/r1_gemm_dbg_sweep_v12.md); single-CTA plans keep the predicated form, whose per-MMA overhead
+            // interleaves with the tensor core (back-to-back issue measured 3-7 % slower there).
+            if (kb < tc.kb1 && !(p.dbg & 1)) {
+              const int ccol = sg.c0 + kin * 64, wcol = wbase + kin * 64;
+              if (elect_one()) {
+                // both CTAs load their half; all bytes are credited to the even CTA's barrier, armed by its producers
+                if (rank == 0) mbar_arrive_expect_tx_a(fb, tx_bytes);
+                tma_load_4d_pair_a(sa, tmA, fb, ccol, c1, c2, c3);
+                tma_load_2d_pair_a(sa + kABytes, &p.tmW, fb, wcol, wn0);
+              }
             } else {
+              if (elect_one() && rank == 0) mbar_arrive_a(fb);  // odd K-block count: no second block in the last stage
+            }
+            __syncwarp();
+          } else {
+            if (kb < tc.kb1 && !(p.dbg & 1)) {
+              const int ccol = sg.c0 + kin * 64, wcol = wbase + kin * 64;
+              mbar_arrive_expect_tx_p(el_arm, fb, tx_bytes);
               tma_load_4d_p(el, sa, tmA, fb, ccol, c1, c2, c3);
               tma_load_2d_p(el, sa + kABytes, &p.tmW, fb, wcol, wn0);
+            } else {
+              mbar_arrive_p(el_arm, fb);  // odd K-block count: the last stage of the tile has no second block
             }
-          } else {
-            mbar_arrive_p(el_arm, fb);  // odd K-block count: the last stage of the tile has no second block
           }
           kb += 2;
           kin += 2;
@@ -416,27 +431,45 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           ready = mbar_test_wait_a(full0 + 8u * s2, ph2);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + s * (kSuperBytes >> 4);
-          const uint32_t el_mma = (p.dbg & 2) ? 0u : el;
+          if constexpr (CG == 2) {
+            if (elect_one()) {  // one thread issues the stage's MMAs and their commit (see the producer loop)
+              if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t el_h = (h == 1 && n < 2) ? 0u : el_mma;
-            const uint64_t adesc = desc_hi | (a_lo + h * (kStageBytes >> 4));
-            const uint64_t bdesc = desc_hi | (a_lo + h * (kStageBytes >> 4) + (kABytes >> 4));
+                for (int h = 0; h < 2; ++h) {
+                  if (h == 1 && n < 2) break;  // odd K-block count: the tile's last stage holds one block
+                  const uint64_t adesc = desc_hi | (a_lo + h * (kStageBytes >> 4));
+                  const uint64_t bdesc = desc_hi | (a_lo + h * (kStageBytes >> 4) + (kABytes >> 4));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t accf = (h == 0 && k == 0) ? accumulate : 1u;
-              if constexpr (CG == 2)
-                umma_bf16_ss_pair_p(el_h, tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
-              else
-                umma_bf16_ss_p(el_h, tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (h == 0 && k == 0) ? accumulate : 1u);
+                }
+              }
+              tc_commit_pair_a(empty0 + 8u * s, 3);
             }
+            __syncwarp();
+          } else {
+            const uint32_t el_mma = (p.dbg & 2) ? 0u : el;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t el_h = (h == 1 && n < 2) ? 0u : el_mma;
+              const uint64_t adesc = desc_hi | (a_lo + h * (kStageBytes >> 4));
+              const uint64_t bdesc = desc_hi | (a_lo + h * (kStageBytes >> 4) + (kABytes >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss_p(el_h, tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (h == 0 && k == 0) ? accumulate : 1u);
+            }
+            tc_commit_p(el, empty0 + 8u * s);
           }
           accumulate = 1u;
-          if constexpr (CG == 2) tc_commit_pair_p(el, empty0 + 8u * s, 3); else tc_commit_p(el, empty0 + 8u * s);
           s = s2;
           ph = ph2;
         }
-        if constexpr (CG == 2) tc_commit_pair_p(el, tfull0 + 8u * acc, 3); else tc_commit_p(el, tfull0 + 8u * acc);
+        if constexpr (CG == 2) {
+          if (elect_one()) tc_commit_pair_a(tfull0 + 8u * acc, 3);
+          __syncwarp();
+        } else {
+          tc_commit_p(el, tfull0 + 8u * acc);
+        }
       }
     }
     __syncwarp();
