@@ -1,5 +1,11 @@
+"""Ring depth vs launch time: fixed GEMM plans with the stage count capped by ASVA_GEMM_STAGES, normal and with
+ASVA_GEMM_DBG=3 (neither TMA loads nor MMAs).  If the protocol-only time does not move with the depth, the ring is
+paced by a single thread's loop iteration, not by a barrier round trip.
+
+    python tools/gemm_stages_sweep.py"""
 import dataclasses, os, sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tools")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch, gemm_probe
 from asva_b200 import ops
 be = ops.backend()
