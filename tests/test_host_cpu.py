@@ -68,6 +68,30 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(val) == want, (cname, field, int(val), want)
 
 
+def test_committed_bench_line_meets_the_contract():
+    """The newest committed bench line (profiles/r1_bench_v*.json, written by bench.py on a B200) carries every key the
+    driver's contract names, with self-consistent values."""
+    import json
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_bench_v*.json")),
+                   key=lambda q: int(re.search(r"_v(\d+)", q).group(1)))
+    paths = [q for q in paths if re.search(r"_v\d+\.json$", q)]
+    d = json.load(open(paths[-1]))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "steps/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["warmup"] >= 3
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] - 1e3 * d["n_gpus"] / d["ms_per_step"]) / d["value"] < 1e-3
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6 and 0 < r["frac"] < 1
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert d["gpu_launches"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown",
+                                                                         "sw_thermal_slowdown"}
+
+
 def test_product_has_no_cpu_fallback():
     from asva_b200._lib import AsvaError
     from avgen.models.unets import AudioUNet3DConditionModel
