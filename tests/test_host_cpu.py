@@ -102,6 +102,32 @@ def test_product_has_no_cpu_fallback():
           audio_encoder_hidden_states=torch.zeros(1, 2, 229, 768))
 
 
+def test_unet_module_boundary_api(tmp_path):
+    """The module-level seams of SURVEY.md 8(b): save_pretrained / from_pretrained round trip in the diffusers directory
+    format (config.json + weights; what scripts/animation_demo.py:80 loads), the attention-processor API with the
+    reference's error for a wrong-sized dict (audio_cond_unet_3d_condition.py:493-521), and the forward's input checks."""
+    from avgen.models.unets import AudioUNet3DConditionModel
+    torch.manual_seed(0)
+    m = AudioUNet3DConditionModel(sample_size=64, cross_attention_dim=768, block_out_channels=(64, 64, 64, 64))
+    assert m.config["block_out_channels"] == (64, 64, 64, 64) and m.config.in_channels == 4
+    for safe in (True, False):
+        d = str(tmp_path / f"ckpt_{int(safe)}")
+        m.save_pretrained(os.path.join(d, "unet"), safe_serialization=safe)
+        m2 = AudioUNet3DConditionModel.from_pretrained(d, subfolder="unet")
+        sd, sd2 = m.state_dict(), m2.state_dict()
+        assert list(sd) == list(sd2) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+        assert tuple(m2.config["block_out_channels"]) == (64, 64, 64, 64)
+    procs = m.attn_processors
+    assert len(procs) == 16 * 4 and all(k.endswith(".processor") for k in procs)  # 16 blocks x 4 Attention modules
+    with pytest.raises(ValueError, match="number of attention layers"):
+        m.set_attn_processor({k: None for k in list(procs)[:3]})
+    m.set_attn_processor({k: None for k in procs})
+    m.set_default_attn_processor()
+    with pytest.raises(Exception):  # 5-D sample assertion of the reference forward
+        m(torch.zeros(1, 4, 8, 8), 1, encoder_hidden_states=torch.zeros(1, 2, 77, 768),
+          audio_encoder_hidden_states=torch.zeros(1, 2, 229, 768))
+
+
 def test_product_never_imports_oracle():
     for d in ("asva_b200", "avgen"):
         for f in glob.glob(os.path.join(ROOT, d, "**", "*.py"), recursive=True):
