@@ -212,6 +212,24 @@ def test_ddim_matches_restatement_and_closed_form():
     assert len(plan) == 50 and abs(plan[-1].c_sample - float((ac[0] / ac[1]) ** 0.5)) < 1e-6
 
 
+def test_scheduler_known_answers_sd15():
+    """Known-answer values of the SD-1.5 noise schedule (scheduler_config.json: scaled_linear, beta 0.00085..0.012,
+    1000 train steps, steps_offset 1, skip_prk_steps) that the diffusers restatement and the product must reproduce:
+    alpha_bar[0] = 1 - 0.00085, alpha_bar[999] = 0.00466 (the widely quoted terminal signal level of SD-1.x), the
+    50-step DDIM grid 981, 961, .., 1 and the 51-call PLMS grid 981, 961, 961, 941, .., 1."""
+    ac = sampler_ref.alphas_cumprod()
+    assert len(ac) == 1000 and abs(float(ac[0]) - 0.99915) < 1e-6 and abs(float(ac[-1]) - 0.0046601) < 2e-6
+    assert all(float(ac[i + 1]) < float(ac[i]) for i in range(999))
+    for sched, ref, want in ((schedulers.DDIMScheduler(), sampler_ref.DDIMRef(50), list(range(981, 0, -20))),
+                             (schedulers.PNDMScheduler(), sampler_ref.PNDMRef(50),
+                              [981, 961] + list(range(961, 0, -20)))):
+        sched.set_timesteps(50)
+        assert sched.timesteps.tolist() == ref.timesteps.tolist() == want
+        assert float(sched.init_noise_sigma) == 1.0
+        x = torch.ones(1, 4, 2, 2, 2)
+        assert torch.equal(sched.scale_model_input(x, 981), x)  # identity for DDIM / PNDM (pipeline :337)
+
+
 def test_pndm_matches_restatement_including_alias_quirk():
     n = 7
     g = torch.Generator().manual_seed(1)
