@@ -33,7 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        # ASVA_NVCC_EXTRA: extra flags for experiments, e.g. "-DASVA_GEMM_LEAN_ISSUER" (use with force=True / --force)
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("ASVA_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
