@@ -545,25 +545,21 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-static int g_attn_sms = 0;
-
 template <int DKA, int KV, int NWG, int STAGES, int NB, bool TEMPORAL, int POLY = kPolyOf8, bool PIPE = true>
 static int launch_attn(const AttnKParams& kp, cudaStream_t stream) {
   using Cfg = AttnCfg<DKA, KV, NWG, STAGES, NB>;
   static_assert(Cfg::kSmemBytes <= 232448, "attention configuration exceeds the shared memory of an SM");
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};  // the opt-in shared-memory size is a per-device attribute
+  const int dev = current_device();
+  if (!configured[dev]) {
     ASVA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DKA, KV, NWG, STAGES, NB, TEMPORAL, POLY, PIPE>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured[dev] = true;
   }
-  if (g_attn_sms == 0) {
-    int dev = 0;
-    ASVA_CUDA_OK(cudaGetDevice(&dev));
-    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sms = device_sms();
+  ASVA_REQUIRE(sms > 0, "asva_attention: cannot query the device");
   int grid = (kp.total_items + NWG - 1) / NWG;
-  if (grid > g_attn_sms) grid = g_attn_sms;
+  if (grid > sms) grid = sms;
   ASVA_CUDA_OK(launch_k(attn_tc_kernel<DKA, KV, NWG, STAGES, NB, TEMPORAL, POLY, PIPE>, dim3(grid), dim3(Cfg::kThreads),
                         Cfg::kSmemBytes, stream, 1, kp));
   return 0;
@@ -585,11 +581,6 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
                (long long)d->ldq);
   ASVA_REQUIRE(d->mask == nullptr || d->mask_rows >= 1, "asva_attention: mask_rows must be >= 1");
   ASVA_REQUIRE(d->kv_rows_per_group >= d->Nk, "asva_attention: kv_rows_per_group < Nk");
-  if (g_attn_sms == 0) {
-    int dev = 0;
-    ASVA_CUDA_OK(cudaGetDevice(&dev));
-    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
 
   AttnKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -630,6 +621,7 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
     int rc = make_tmap_bf16(&kp.tmKV, d->kv, 3, dims, strides, box, el);
     if (rc != 0) return rc;
   }
+#ifdef ASVA_DEBUG_SWITCHES  // per-phase clock64 trace and A/B variants: experiment builds only
   static long long* trace_buf = nullptr;
   static int trace_on = -1;
   if (trace_on < 0) {
@@ -641,9 +633,11 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
     cudaMemsetAsync(trace_buf, 0, 8 * sizeof(long long), stream);
     kp.trace = trace_buf;
   }
+#endif
   int rc;
   switch (dka) {
     case 1: {
+#ifdef ASVA_DEBUG_SWITCHES
       static int poly = -1;  // ASVA_ATTN_POLY=0..4: exponentials per 8 computed on the FMA pipes (experiments)
       static bool pipe = true;  // ASVA_ATTN_PIPE=0: serial TMEM loads (the previous form, for A/B timing)
       if (poly < 0) {
@@ -652,12 +646,16 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
         e = getenv("ASVA_ATTN_PIPE");
         pipe = !(e != nullptr && e[0] == '0');
       }
+#else
+      constexpr bool pipe = true;
+#endif
       // overlapping the second chunk's TMEM load pays once an item has several key tiles (self-attention: -3 %); the
       // one- and two-tile items of the cross-attentions run ~4 % faster with the leaner serial form (measured)
       if (!pipe || d->Nk < 256) {
         rc = launch_attn<1, 64, 2, 8, 2, false, kPolyOf8, false>(kp, stream);
         break;
       }
+#ifdef ASVA_DEBUG_SWITCHES
       switch (poly) {
         case 0: rc = launch_attn<1, 64, 2, 8, 2, false, 0>(kp, stream); break;
         case 1: rc = launch_attn<1, 64, 2, 8, 2, false, 1>(kp, stream); break;
@@ -665,11 +663,15 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
         case 3: rc = launch_attn<1, 64, 2, 8, 2, false, 3>(kp, stream); break;
         default: rc = launch_attn<1, 64, 2, 8, 2, false, kPolyOf8>(kp, stream); break;
       }
+#else
+      rc = launch_attn<1, 64, 2, 8, 2, false, kPolyOf8>(kp, stream);
+#endif
       break;
     }
     case 2: rc = launch_attn<2, 64, 2, 4, 1, false>(kp, stream); break;
     default: rc = launch_attn<3, 64, 1, 3, 1, false>(kp, stream); break;
   }
+#ifdef ASVA_DEBUG_SWITCHES
   if (trace_on && rc == 0) {
     long long h[8];
     cudaStreamSynchronize(stream);
@@ -678,6 +680,7 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
       printf("[asva attn trace] tiles %lld: wait S %.0f | pass1 %.0f | wait PV + rescale %.0f | pass2 %.0f | arrive %.0f cycles per tile\n",
              h[5], (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5]);
   }
+#endif
   return rc;
 }
 

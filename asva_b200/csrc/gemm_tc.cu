@@ -33,6 +33,15 @@ constexpr int kSmemLimit = 232448;    // 227 KB opt-in maximum per CTA
 constexpr int kBarBytes = 512;
 constexpr int kDefaultEpi = 1;          // epilogue form when neither the descriptor nor ASVA_GEMM_EPI chooses
 
+// Experiment switches (ASVA_GEMM_DBG: skip TMA loads / MMAs for timing; ASVA_GEMM_BN / SPLIT / CG / EPI / STAGES / PF:
+// plan overrides) exist only in builds made with -DASVA_DEBUG_SWITCHES (ASVA_NVCC_EXTRA, tools/gemm_dbg_sweep.py).
+// The default library never reads the environment on the launch path and has no work-skipping branch.
+#ifdef ASVA_DEBUG_SWITCHES
+#define ASVA_DBG(p) ((p).dbg)
+#else
+#define ASVA_DBG(p) 0
+#endif
+
 struct SegK {
   int32_t src, c0, off1, off2, off3, num_kb, wk, wk_first, fix2;
 };
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             // MMA instruction. With neither loads nor MMAs a stage then costs ~300 instead of ~590 cycles
             // (profiles/r1_gemm_dbg_sweep_v12.md); single-CTA plans keep the predicated form, whose per-MMA overhead
             // interleaves with the tensor core (back-to-back issue measured 3-7 % slower there).
-            if (kb < tc.kb1 && !(p.dbg & 1)) {
+            if (kb < tc.kb1 && !(ASVA_DBG(p) & 1)) {
               const int ccol = sg.c0 + kin * 64, wcol = wbase + kin * 64;
               if (elect_one()) {
                 // both CTAs load their half; all bytes are credited to the even CTA's barrier, armed by its producers
@@ -376,7 +385,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
             __syncwarp();
           } else {
-            if (kb < tc.kb1 && !(p.dbg & 1)) {
+            if (kb < tc.kb1 && !(ASVA_DBG(p) & 1)) {
               const int ccol = sg.c0 + kin * 64, wcol = wbase + kin * 64;
               mbar_arrive_expect_tx_p(el_arm, fb, tx_bytes);
               tma_load_4d_p(el, sa, tmA, fb, ccol, c1, c2, c3);
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const uint32_t a_lo0 = ((smem_a0 & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t n_st = static_cast<uint32_t>(n_stages);
       const uint32_t tfull0 = smem_u32(tmem_full_bar);
-      const bool no_mma = (p.dbg & 2) != 0;
+      const bool no_mma = (ASVA_DBG(p) & 2) != 0;
       uint32_t s = 0, ph = 0, t = 0;
       bool ready = false;
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
@@ -486,7 +495,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           const uint32_t a_lo = a_lo0 + s * (kSuperBytes >> 4);
           if constexpr (CG == 2) {
             if (elect_one()) {  // one thread issues the stage's MMAs and their commit (see the producer loop)
-              if (!(p.dbg & 2)) {
+              if (!(ASVA_DBG(p) & 2)) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   if (h == 1 && n < 2) break;  // odd K-block count: the tile's last stage holds one block
@@ -501,7 +510,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
             __syncwarp();
           } else {
-            const uint32_t el_mma = (p.dbg & 2) ? 0u : el;
+            const uint32_t el_mma = (ASVA_DBG(p) & 2) ? 0u : el;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint32_t el_h = (h == 1 && n < 2) ? 0u : el_mma;
@@ -789,8 +798,6 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
   }
 }
 
-static int g_num_sms = 0;
-
 struct GemmPlan {
   int bn, split, stages, cg, epi;
 };
@@ -845,8 +852,13 @@ static double plan_cost(int bn, int cg, int split, int N, int64_t m_tiles, int n
 }
 
 static int env_int(const char* name) {
+#ifdef ASVA_DEBUG_SWITCHES
   const char* e = getenv(name);
   return e ? atoi(e) : 0;
+#else
+  (void)name;
+  return 0;
+#endif
 }
 
 static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, int num_kb, int n_res, int sms) {
@@ -908,8 +920,12 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
 
 template <int BN, bool GEGLU, int CG>
 static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t stream) {
-  static bool configured = false;
-  static int max_ctas = 0;
+  static bool configured_d[kMaxDevices] = {false};  // function attributes and occupancy are per device
+  static int max_ctas_d[kMaxDevices] = {0};
+  const int dev = current_device();
+  const int g_num_sms = device_sms();
+  bool& configured = configured_d[dev];
+  int& max_ctas = max_ctas_d[dev];
   if (!configured) {
     ASVA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kSmemLimit));
@@ -961,11 +977,8 @@ static int dispatch_gemm(const GemmKParams& kp, int bn, bool geglu, int smem, cu
 static int compute_plan(const asva_gemm_desc* d, asva::GemmPlan* out) {
   using namespace asva;
   if (d == nullptr || d->nseg < 1 || d->nseg > ASVA_GEMM_MAX_SEG) return fail(ASVA_ERR_INVALID, "bad descriptor");
-  if (g_num_sms == 0) {
-    int dev = 0;
-    ASVA_CUDA_OK(cudaGetDevice(&dev));
-    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_num_sms = device_sms();
+  ASVA_REQUIRE(g_num_sms > 0, "asva_gemm: cannot query the device");
   int64_t m_tiles = 1, M = 1;
   for (int i = 0; i < 3; ++i) {
     if (d->box[i] < 1 || d->out_dims[i] < 1) return fail(ASVA_ERR_INVALID, "bad box/out_dims");
@@ -1064,11 +1077,8 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
                (long long)d->ldw, d->wcols);
   ASVA_REQUIRE(d->ldo % (d->out_fp32 ? 4 : 8) == 0 && d->ldo >= (d->geglu ? d->N / 2 : d->N),
                "asva_gemm: ldo=%lld invalid", (long long)d->ldo);
-  if (g_num_sms == 0) {
-    int dev = 0;
-    ASVA_CUDA_OK(cudaGetDevice(&dev));
-    ASVA_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_num_sms = device_sms();
+  ASVA_REQUIRE(g_num_sms > 0, "asva_gemm: cannot query the device");
 
   GemmKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -1150,11 +1160,10 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   }
   kp.dbg = env_int("ASVA_GEMM_DBG");
   {
-    static int pf = -2;
-    if (pf == -2) {
-      const char* e = getenv("ASVA_GEMM_PF");
-      pf = e ? atoi(e) : 64;
-    }
+    int pf = 64;  // W blocks each CTA prefetches into L2 before the dependent-launch wait
+#ifdef ASVA_DEBUG_SWITCHES
+    if (const char* e = getenv("ASVA_GEMM_PF")) pf = atoi(e);
+#endif
     kp.pf_blocks = pf;
     kp.w_kblocks = d->wcols / 64;
   }

@@ -22,6 +22,22 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
+int device_sms() {
+  static int sms[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) sms[dev] = n;
+  }
+  return sms[dev];
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {

@@ -15,6 +15,12 @@ namespace asva {
 void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 
+// One-time launch state (opt-in shared-memory attributes, occupancy-derived grid caps, SM counts) is per DEVICE:
+// translation units keep it in arrays of kMaxDevices indexed by current_device().
+constexpr int kMaxDevices = 64;
+int current_device();   // cudaGetDevice, clamped to [0, kMaxDevices)
+int device_sms();       // multiprocessor count of the current device (cached per device; 0 on failure)
+
 // Builds a bf16 tiled tensor map with 128-byte swizzle. dims/box/elem_strides have `rank` entries (innermost
 // first); strides_bytes has rank-1 entries (dims 1..rank-1). Returns 0 or a negative asva_status.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

@@ -171,87 +171,11 @@ __global__ void timestep_features_kernel(const float* __restrict__ t, float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) temporal_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                            __nv_bfloat16* __restrict__ out, int B, int F, int N,
-                                                            int heads, int d, float scale, int64_t total_items) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pitch = d + 1;
-  const int per_warp = 3 * F * pitch + F * F;
-  float* sq = sm + warp * per_warp;
-  float* sk = sq + F * pitch;
-  float* sv = sk + F * pitch;
-  float* sp = sv + F * pitch;
-  const int C = heads * d;
-  const int dch = d >> 3;
-  for (int64_t item = static_cast<int64_t>(blockIdx.x) * 4 + warp; item < total_items;
-       item += static_cast<int64_t>(gridDim.x) * 4) {
-    const int head = static_cast<int>(item % heads);
-    const int n = static_cast<int>((item / heads) % N);
-    const int b = static_cast<int>(item / (static_cast<int64_t>(heads) * N));
-    // stage q, k, v : 3*F*dch chunks of 8 bf16
-    for (int i = lane; i < 3 * F * dch; i += 32) {
-      const int chn = i % dch;
-      const int f = (i / dch) % F;
-      const int part = i / (dch * F);
-      const __nv_bfloat16* src =
-          qkv + ((static_cast<int64_t>(b) * F + f) * N + n) * (3 * C) + part * C + head * d + chn * 8;
-      const uint4 u = *reinterpret_cast<const uint4*>(src);
-      const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), dd = unpack_bf16x2(u.w);
-      float* dst = sq + part * F * pitch + f * pitch + chn * 8;
-      dst[0] = a.x; dst[1] = a.y; dst[2] = bb.x; dst[3] = bb.y;
-      dst[4] = c.x; dst[5] = c.y; dst[6] = dd.x; dst[7] = dd.y;
-    }
-    __syncwarp();
-    // scores
-    for (int pr = lane; pr < F * F; pr += 32) {
-      const int fq = pr / F, fk = pr % F;
-      const float* qr = sq + fq * pitch;
-      const float* kr = sk + fk * pitch;
-      float acc = 0.f;
-      for (int j = 0; j < d; ++j) acc += qr[j] * kr[j];
-      sp[pr] = acc * scale;
-    }
-    __syncwarp();
-    // softmax per query row
-    for (int fq = lane; fq < F; fq += 32) {
-      float* pr = sp + fq * F;
-      float m = -INFINITY;
-      for (int k = 0; k < F; ++k) m = fmaxf(m, pr[k]);
-      float s = 0.f;
-      for (int k = 0; k < F; ++k) {
-        const float e = __expf(pr[k] - m);
-        pr[k] = e;
-        s += e;
-      }
-      const float inv = 1.f / s;
-      for (int k = 0; k < F; ++k) pr[k] *= inv;
-    }
-    __syncwarp();
-    // output: lane pairs (fq, 2 features)
-    const int dh = d >> 1;
-    for (int i = lane; i < F * dh; i += 32) {
-      const int fq = i / dh, j2 = (i % dh) * 2;
-      const float* pr = sp + fq * F;
-      float o0 = 0.f, o1 = 0.f;
-      for (int k = 0; k < F; ++k) {
-        const float pk = pr[k];
-        o0 += pk * sv[k * pitch + j2];
-        o1 += pk * sv[k * pitch + j2 + 1];
-      }
-      __nv_bfloat16* dst = out + ((static_cast<int64_t>(b) * F + fq) * N + n) * C + head * d + j2;
-      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o0, o1);
-    }
-    __syncwarp();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // CFG combine + sampler update (fp32, frames 1..F-1 only).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__ eps, int k,
+// eps [k][clips][C][F][hw] (CFG branch-major, the pipeline's torch.cat order), lat [clips][C][F][hw],
+// hist [4][clips][C][F][hw]; all clips of a launch are at the same sampler step (shared coef / slots).
+__global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__ eps, int k, int clips,
                                                        float* __restrict__ lat, float* __restrict__ hist,
                                                        const float* __restrict__ coef,
                                                        const int32_t* __restrict__ slots, int C, int F, int hw,
@@ -259,15 +183,18 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__
   pdl_trigger();
   pdl_wait();
   const int64_t per_c = static_cast<int64_t>(F - 1) * hw;
-  const int64_t total = per_c * C;
+  const int64_t per_clip = per_c * C;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = static_cast<int>(i / per_c);
-  const int64_t rem = i % per_c;  // (f-1)*hw + n
-  const int64_t idx = (static_cast<int64_t>(c) * F + 1) * hw + rem;
+  if (i >= per_clip * clips) return;
+  const int64_t clip = i / per_clip;
+  const int64_t ic = i - clip * per_clip;
+  const int c = static_cast<int>(ic / per_c);
+  const int64_t rem = ic % per_c;  // (f-1)*hw + n
   const int64_t stride_b = static_cast<int64_t>(C) * F * hw;
+  const int64_t idx = clip * stride_b + (static_cast<int64_t>(c) * F + 1) * hw + rem;
+  const int64_t stride_k = stride_b * clips;
   float e = 0.f;
-  for (int j = 0; j < k; ++j) e += coef[j] * eps[j * stride_b + idx];
+  for (int j = 0; j < k; ++j) e += coef[j] * eps[j * stride_k + idx];
   const float cs = coef[3], ce = coef[4];
   float ehat = e;
   if (plms) {
@@ -275,9 +202,9 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__
     ehat = coef[5] * e;
     for (int j = 1; j < 4; ++j) {
       const float a = coef[5 + j];
-      if (a != 0.f) ehat += a * hist[static_cast<int64_t>(slots[j]) * stride_b + idx];
+      if (a != 0.f) ehat += a * hist[static_cast<int64_t>(slots[j]) * stride_k + idx];
     }
-    if (slots[0] >= 0) hist[static_cast<int64_t>(slots[0]) * stride_b + idx] = e;
+    if (slots[0] >= 0) hist[static_cast<int64_t>(slots[0]) * stride_k + idx] = e;
   }
   lat[idx] = cs * lat[idx] + ce * ehat;
 }
@@ -352,10 +279,11 @@ extern "C" int asva_small_linear(const float* x, const void* w, const float* bia
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ASVA_REQUIRE(x && w && out, "asva_small_linear: null operand");
   ASVA_REQUIRE(M >= 1 && M <= 32 && N >= 1 && K >= 8 && K % 8 == 0 && K <= 8192, "asva_small_linear: bad shape");
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};  // per-device function attribute
+  const int dev = current_device();
+  if (!configured[dev]) {
     ASVA_CUDA_OK(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8192 * 4));
-    configured = true;
+    configured[dev] = true;
   }
   dim3 grid((N + 7) / 8, (M + 3) / 4);
   ASVA_CUDA_OK(launch_k(small_linear_kernel, dim3(grid), dim3(256), static_cast<size_t>(4) * K * sizeof(float), stream, 1, x, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N, K, act_in, act_out));
@@ -374,27 +302,29 @@ extern "C" int asva_timestep_features(const float* t, float* out, int32_t B, int
   return 0;
 }
 
-extern "C" int asva_cfg_ddim_step(const float* eps, int32_t k, float* latents, const float* coef, int32_t C,
-                                  int32_t F, int32_t hw, asva_stream_t stream_) {
+extern "C" int asva_cfg_ddim_step(const float* eps, int32_t k, int32_t clips, float* latents, const float* coef,
+                                  int32_t C, int32_t F, int32_t hw, asva_stream_t stream_) {
   using namespace asva;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ASVA_REQUIRE(eps && latents && coef && k >= 1 && k <= 3 && F >= 2, "asva_cfg_ddim_step: bad arguments");
-  const int64_t total = static_cast<int64_t>(C) * (F - 1) * hw;
-  ASVA_CUDA_OK(launch_k(cfg_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1, eps, k, latents, nullptr, coef,
-                                                                                  nullptr, C, F, hw, 0));
+  ASVA_REQUIRE(eps && latents && coef && k >= 1 && k <= 3 && clips >= 1 && F >= 2,
+               "asva_cfg_ddim_step: bad arguments");
+  const int64_t total = static_cast<int64_t>(clips) * C * (F - 1) * hw;
+  ASVA_CUDA_OK(launch_k(cfg_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1,
+                        eps, k, clips, latents, nullptr, coef, nullptr, C, F, hw, 0));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-extern "C" int asva_cfg_plms_step(const float* eps, int32_t k, float* latents, float* hist, const float* coef,
-                                  const int32_t* slots, int32_t C, int32_t F, int32_t hw, asva_stream_t stream_) {
+extern "C" int asva_cfg_plms_step(const float* eps, int32_t k, int32_t clips, float* latents, float* hist,
+                                  const float* coef, const int32_t* slots, int32_t C, int32_t F, int32_t hw,
+                                  asva_stream_t stream_) {
   using namespace asva;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ASVA_REQUIRE(eps && latents && hist && coef && slots && k >= 1 && k <= 3 && F >= 2,
+  ASVA_REQUIRE(eps && latents && hist && coef && slots && k >= 1 && k <= 3 && clips >= 1 && F >= 2,
                "asva_cfg_plms_step: bad arguments");
-  const int64_t total = static_cast<int64_t>(C) * (F - 1) * hw;
-  ASVA_CUDA_OK(launch_k(cfg_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1, eps, k, latents, hist, coef, slots,
-                                                                                  C, F, hw, 1));
+  const int64_t total = static_cast<int64_t>(clips) * C * (F - 1) * hw;
+  ASVA_CUDA_OK(launch_k(cfg_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 1,
+                        eps, k, clips, latents, hist, coef, slots, C, F, hw, 1));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -671,9 +671,13 @@ static GnClusterPlan gn_cluster_plan(int n_inst, int64_t rows, int Ctot, int gro
     while (pl.cs > 1 && units * pl.cs > 160) pl.cs >>= 1;
   }
   while (pl.cs > 1 && rows / pl.cs < 64) pl.cs >>= 1;
-  const char* e_cs = getenv("ASVA_GN_CS");  // experiments
+#ifdef ASVA_DEBUG_SWITCHES  // plan overrides for tools/norm_probe.py --sweep (experiment builds only)
+  const char* e_cs = getenv("ASVA_GN_CS");
   const char* e_t = getenv("ASVA_GN_T");
   const char* e_k = getenv("ASVA_GN_KMAX");
+#else
+  const char *e_cs = nullptr, *e_t = nullptr, *e_k = nullptr;
+#endif
   if (e_cs != nullptr) pl.cs = atoi(e_cs);
   const int64_t rows_cta = (rows + pl.cs - 1) / pl.cs;
   const int64_t chunks = rows_cta * bw;
@@ -692,7 +696,7 @@ static GnClusterPlan gn_cluster_plan(int n_inst, int64_t rows, int Ctot, int gro
   return pl;
 }
 
-static int g_gn_cap = 0;  // co-resident CTAs of gn_fused_kernel on this device
+static int g_gn_cap_d[kMaxDevices] = {0};  // co-resident CTAs of gn_fused_kernel, per device
 
 static GnStatsPlan gn_fused_plan(int n_inst, int64_t rows, int Ctot, int cap) {
   GnStatsPlan pl;
@@ -802,11 +806,15 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
   ASVA_REQUIRE((int64_t)n_inst * groups <= 4096, "asva_groupnorm: n_inst * groups = %lld exceeds the workspace",
                (long long)n_inst * groups);
   {
+#ifdef ASVA_DEBUG_SWITCHES
     static int no_cluster = -1;
     if (no_cluster < 0) {
       const char* e = getenv("ASVA_GN_NO_CLUSTER");
       no_cluster = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
+#else
+    constexpr int no_cluster = 0;
+#endif
     const GnClusterPlan cp = gn_cluster_plan(n_inst, rows, Ctot, groups);
     // few units x many rows (a whole clip per instance at the top resolution): 8 CTAs per unit cannot fill the GPU
     // and narrow column strips waste DRAM bursts - the grid-barrier kernel below reads full rows instead
@@ -831,15 +839,17 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
     }
   }
   // generic form (channel groups that do not bundle into 16-byte strips): grid-barrier kernel
+  int& g_gn_cap = g_gn_cap_d[current_device()];
   if (g_gn_cap == 0) {
-    int dev = 0, sms = 0, occ = 0;
-    ASVA_CUDA_OK(cudaGetDevice(&dev));
-    ASVA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int occ = 0;
+    const int sms = device_sms();
     ASVA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel, 256, 0));
-    ASVA_REQUIRE(occ >= 1, "asva_groupnorm: kernel does not fit an SM");
+    ASVA_REQUIRE(occ >= 1 && sms >= 1, "asva_groupnorm: kernel does not fit an SM");
     int per_sm = occ < kGnCtasPerSm ? occ : kGnCtasPerSm;
+#ifdef ASVA_DEBUG_SWITCHES
     const char* e = getenv("ASVA_GN_CTAS_PER_SM");
     if (e != nullptr && atoi(e) >= 1 && atoi(e) <= occ) per_sm = atoi(e);
+#endif
     g_gn_cap = per_sm * sms;
   }
   const int nchunk = Ctot / 8;

@@ -89,6 +89,9 @@ class UNetEngine:
         self.eps = float(c["norm_eps"])
         self.shape = None
         self.ctx, self.ctx_sig = None, None
+        # Buffer generation: bumped whenever prepare() / set_context() (re)allocates device buffers.  Anything that
+        # captured device addresses (CUDA graphs of the launch sequence) keys itself on it and re-captures on change.
+        self.gen = 0
         self._bufs: Dict[tuple, torch.Tensor] = {}
         self._ctx_bufs: Dict[tuple, torch.Tensor] = {}
         self._pack(sd)
@@ -209,6 +212,7 @@ class UNetEngine:
         self._frozen = False
         self._bufs.clear()
         self._ctx_bufs.clear()
+        self.gen += 1
         self.shape = (B, F, h, w)
         be = self.be
         ar = torch.arange(F, dtype=torch.float32, device=self.dev)
@@ -229,6 +233,7 @@ class UNetEngine:
         if t is None:
             t = torch.empty(shape, dtype=dtype, device=self.dev)
             self._ctx_bufs[key] = t
+            self.gen += 1
         return t
 
     def set_context(self, text: torch.Tensor, audio: torch.Tensor, audio_mask: Optional[torch.Tensor]) -> None:

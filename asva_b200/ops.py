@@ -214,7 +214,7 @@ class CudaBackend:
     def __init__(self) -> None:
         self.lib = _lib.load()
         self.launches = 0
-        self._gn_sync = None  # grid-barrier workspace of the fused GroupNorm
+        self._gn_sync = {}  # grid-barrier workspace of the fused GroupNorm, one per device
         self._prof = None
         self._ws = {}
         self.tuning = False
@@ -415,13 +415,14 @@ class CudaBackend:
     def groupnorm(self, x0, C0, x1, C1, n_inst, rows, groups, eps, gamma, beta, silu, out) -> None:
         """Fused statistics + apply (+SiLU) of one GroupNorm: out bf16 [n_inst*rows, C0+C1] (one launch)."""
         self._chk_dev(x0, x1, gamma, beta, out)
-        if self._gn_sync is None:  # zeroed once; the kernel leaves it zeroed
-            self._gn_sync = torch.zeros(int(self.lib.asva_groupnorm_sync_bytes()), dtype=torch.uint8,
-                                        device=x0.device)
+        sync = self._gn_sync.get(x0.device)
+        if sync is None:  # zeroed once per device; the kernel leaves it zeroed
+            sync = torch.zeros(int(self.lib.asva_groupnorm_sync_bytes()), dtype=torch.uint8, device=x0.device)
+            self._gn_sync[x0.device] = sync
         with self._timed('groupnorm'):
             _lib.check(self.lib.asva_groupnorm(x0.data_ptr(), C0, _ptr(x1), C1, n_inst, rows, groups, eps,
                                                gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
-                                               self._gn_sync.data_ptr(), self._stream()), "asva_groupnorm")
+                                               sync.data_ptr(), self._stream()), "asva_groupnorm")
         self.launches += 1
 
     def groupnorm_apply(self, x0, C0, x1, C1, stats, n_inst, n_img, h, w, silu, upsample, out) -> None:
@@ -468,18 +469,22 @@ class CudaBackend:
                    "asva_timestep_features")
         self.launches += 1
 
-    def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw) -> None:
+    def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw, clips: int = 1) -> None:
+        """eps fp32 (k*clips, C, F, hw) branch-major; lat fp32 (clips, C, F, hw)."""
         self._chk_dev(eps, lat, coef)
+        assert eps.numel() == k * clips * C * F * hw and lat.numel() == clips * C * F * hw
         with self._timed('cfg_step'):
-            _lib.check(self.lib.asva_cfg_ddim_step(eps.data_ptr(), k, lat.data_ptr(), coef.data_ptr(), C, F, hw,
+            _lib.check(self.lib.asva_cfg_ddim_step(eps.data_ptr(), k, clips, lat.data_ptr(), coef.data_ptr(), C, F, hw,
                                                self._stream()), "asva_cfg_ddim_step")
         self.launches += 1
 
-    def cfg_plms_step(self, eps, k, lat, hist, coef, slots, C, F, hw) -> None:
+    def cfg_plms_step(self, eps, k, lat, hist, coef, slots, C, F, hw, clips: int = 1) -> None:
         self._chk_dev(eps, lat, hist, coef, slots)
+        assert eps.numel() == k * clips * C * F * hw and hist.numel() == 4 * clips * C * F * hw
         with self._timed('cfg_step'):
-            _lib.check(self.lib.asva_cfg_plms_step(eps.data_ptr(), k, lat.data_ptr(), hist.data_ptr(), coef.data_ptr(),
-                                               slots.data_ptr(), C, F, hw, self._stream()), "asva_cfg_plms_step")
+            _lib.check(self.lib.asva_cfg_plms_step(eps.data_ptr(), k, clips, lat.data_ptr(), hist.data_ptr(),
+                                               coef.data_ptr(), slots.data_ptr(), C, F, hw, self._stream()),
+                       "asva_cfg_plms_step")
         self.launches += 1
 
 

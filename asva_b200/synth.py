@@ -51,7 +51,8 @@ def synth_inputs(F: int = 12, h: int = 32, w: int = 32, seed: int = 123, k: int 
                  n_text: int = 77):
     """One clip's synthetic conditioning in the pipeline's wire format (pipeline_audio_cond_animation.py:291-322):
     latents (1,4,F,h,w) fp32 (frame 0 stands in for the VAE latent of the conditioning image), and the CFG-batched
-    (k = 2: [text only, text+audio]) text (k,F,77,768), audio (k,F,229,768) contexts and audio masks (k,F,229)."""
+    (k = 2: [text only, text+audio]; k = 3: [uncond, text, text+audio] as encode_text / encode_audio order them,
+    :149-154,186-194) text (k,F,77,768), audio (k,F,229,768) contexts and audio masks (k,F,229)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     lat = torch.randn(1, 4, F, h, w, generator=g)
     text = torch.randn(1, n_text, ctx_dim, generator=g)
@@ -60,7 +61,11 @@ def synth_inputs(F: int = 12, h: int = 32, w: int = 32, seed: int = 123, k: int 
     mask = audio_segment_mask(F)  # (F,229)
     if k == 1:
         return lat, text.unsqueeze(1).expand(1, F, -1, -1), audio.unsqueeze(1).expand(1, F, -1, -1), mask[None]
-    text_k = text.expand(k, -1, -1).unsqueeze(1).expand(k, F, -1, -1)
+    if k == 3:  # dual CFG: branch 0 carries the unconditional (null-prompt) text encoding
+        uncond = torch.randn(1, n_text, ctx_dim, generator=torch.Generator(device="cpu").manual_seed(seed + 1000))
+        text_k = torch.cat([uncond, text, text]).unsqueeze(1).expand(k, F, -1, -1)
+    else:
+        text_k = text.expand(k, -1, -1).unsqueeze(1).expand(k, F, -1, -1)
     audio_k = torch.cat([null_audio] * (k - 1) + [audio]).unsqueeze(1).expand(k, F, -1, -1)
     mask_k = mask[None].expand(k, -1, -1).contiguous()
     return lat, text_k, audio_k, mask_k

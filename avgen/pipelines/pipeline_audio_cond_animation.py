@@ -129,18 +129,19 @@ class AudioCondAnimationPipeline(_ProgressMixin):
         else:
             mel = self.audio_processor(audios).to(device=device, dtype=dtype)
         _, enc, masks = self.audio_encoder(mel, normalize=False, return_dict=False)
-        enc = enc.unsqueeze(1).expand(-1, video_length, -1, -1)
         if do_audio_classifier_free_guidance:
             null_mel = torch.zeros(1, 1, *self.melspectrogram_shape, device=device, dtype=dtype)
             _, null_enc, null_masks = self.audio_encoder(null_mel, normalize=False, return_dict=False)
-            null_enc = null_enc.unsqueeze(1).expand(b, video_length, -1, -1)
-            null_masks = null_masks.expand(b, -1, -1)
+            null_enc, null_masks = null_enc.expand(b, -1, -1), null_masks.expand(b, -1, -1)
             if do_text_classifier_free_guidance:
-                return torch.cat([null_enc, null_enc, enc]), torch.cat([null_masks, null_masks, masks])
-            return torch.cat([null_enc, enc]), torch.cat([null_masks, masks])
-        if do_text_classifier_free_guidance:
-            return torch.cat([enc, enc]), torch.cat([masks, masks])
-        return enc, masks
+                enc, masks = torch.cat([null_enc, null_enc, enc]), torch.cat([null_masks, null_masks, masks])
+            else:
+                enc, masks = torch.cat([null_enc, enc]), torch.cat([null_masks, masks])
+        elif do_text_classifier_free_guidance:
+            enc, masks = torch.cat([enc, enc]), torch.cat([masks, masks])
+        # the frame axis stays a stride-0 view (the reference materialises the repeat, :177): the engine sees at a
+        # glance that the context is frame-invariant and projects keys / values once per clip
+        return enc.unsqueeze(1).expand(-1, video_length, -1, -1), masks
 
     def _preprocess_images(self, images) -> torch.Tensor:
         """PIL / array / tensor -> (b,3,H,W) in [-1,1], H and W rounded down to a multiple of the VAE factor
@@ -216,10 +217,8 @@ class AudioCondAnimationPipeline(_ProgressMixin):
         b, C, F, h, w = video_latents.shape
         assert text_encodings.shape[0] == k * b and audio_encodings.shape[0] == k * b, \
             (text_encodings.shape, audio_encodings.shape, k, b)
-        sess = None
-        if b == 1:
-            sess = self.open_session(text_encodings, audio_encodings, audio_masks, F, h, w, num_inference_steps,
-                                     audio_guidance_scale, text_guidance_scale)
+        sess = self.open_session(text_encodings, audio_encodings, audio_masks, F, h, w, num_inference_steps,
+                                 audio_guidance_scale, text_guidance_scale)
         if sess is None:
             self.scheduler.set_timesteps(num_inference_steps, device=video_latents.device)
             return self._denoise_generic(video_latents, text_encodings, audio_encodings, audio_masks, k, do_t, do_a,
@@ -234,8 +233,8 @@ class AudioCondAnimationPipeline(_ProgressMixin):
         return sess.latents.clone()
 
     def _denoise_generic(self, video_latents, text, audio, masks, k, do_t, do_a, s_a, s_t, generator):
-        """Any other scheduler (or b > 1): the reference's loop verbatim in structure - our UNet module per step,
-        CFG combine and scheduler.step() as tensor ops."""
+        """Any other scheduler: the reference's loop in structure - our UNet module per step, CFG combine and
+        scheduler.step() as tensor ops."""
         extra = self.prepare_extra_step_kwargs(generator, eta=0.0)
         video_latents = video_latents.clone()
         for t in self.progress_bar(self.scheduler.timesteps):
@@ -283,9 +282,12 @@ class AudioCondAnimationPipeline(_ProgressMixin):
 
 
 class DenoiseSession:
-    """One clip on one GPU: static fp32 latents (1,C,F,h,w) on the device, the per-step coefficient tables, and a
-    CUDA-graph runner whose body is  UNet forward (k CFG branches) -> fused CFG combine + DDIM/PLMS update of
-    frames 1.. in place.  `step(i)` is one graph replay plus three tiny device-to-device table-row copies."""
+    """b clips on one GPU (b = 1 in the reference's own use; more clips per GPU batch along the token
+    axis and fill the deep, small-M levels of the UNet): static fp32 latents (b,C,F,h,w) on the device, the per-step
+    parameter table, and a CUDA-graph runner whose body is  UNet forward (k CFG branches x b clips, branch-major like
+    the reference's torch.cat([latents] * k)) -> fused CFG combine + DDIM/PLMS update of frames 1.. in place.
+    `step(i)` is one graph replay plus ONE small device-to-device copy of that step's parameter row
+    (timesteps | CFG weights and sampler coefficients | PLMS history slots)."""
 
     def __init__(self, pipe, plans, text, audio, masks, F, h, w, audio_scale, text_scale):
         do_t, do_a = text_scale > 1.0, audio_scale > 1.0
@@ -303,39 +305,48 @@ class DenoiseSession:
         eng = unet.engine()
         dev = unet.device
         C, Co = unet.config.in_channels, unet.config.out_channels
-        assert text.shape[0] == k and audio.shape[0] == k, "the fused session handles one clip (b = 1) per GPU"
-        self.plans, self.num_steps, self.k, self.dev = plans, len(plans), k, dev
+        if C != Co:
+            raise ValueError(f"the fused CFG + sampler step needs in_channels == out_channels (got {C}, {Co})")
+        kb = text.shape[0]
+        assert kb % k == 0 and audio.shape[0] == kb, \
+            f"contexts must hold k = {k} CFG branches per clip, branch-major (got {tuple(text.shape)}, {tuple(audio.shape)})"
+        b = kb // k
+        self.plans, self.num_steps, self.k, self.clips, self.dev = plans, len(plans), k, b, dev
         self.plms = any(p.slots[0] >= 0 or tuple(p.a) != (1.0, 0.0, 0.0, 0.0) for p in plans)
         with torch.cuda.device(dev):
-            if eng.shape != (k, F, h, w):
-                eng.prepare(k, F, h, w)
+            if eng.shape != (kb, F, h, w):
+                eng.prepare(kb, F, h, w)
                 unet._runner, unet._ctx_key, pipe._loop = None, None, None
             unet.bind_context(text, audio, masks)
-            key = (k, C, F, h, w, self.plms, id(eng), eng.ctx_sig)
+            # eng.gen changes whenever the engine (re)allocates buffers (prepare(), new context geometry), also when
+            # that happens behind this pipeline's back (unet.forward with another batch, a second pipeline on the
+            # same unet): a cached graph is only replayed against the buffers it was captured on
+            key = (k, b, C, F, h, w, self.plms, id(eng), eng.ctx_sig, eng.gen)
             if pipe._loop is None or pipe._loop["key"] != key:
-                L = dict(key=key,
-                         lat=torch.empty(1, C, F, h, w, dtype=torch.float32, device=dev),
-                         ts=torch.empty(k, dtype=torch.float32, device=dev),
-                         eps=torch.empty(k, Co, F, h, w, dtype=torch.float32, device=dev),
-                         coef=torch.empty(9, dtype=torch.float32, device=dev),
-                         slots=torch.zeros(4, dtype=torch.int32, device=dev),
-                         hist=torch.zeros(4, C, F, h, w, dtype=torch.float32, device=dev) if self.plms else None)
+                par = torch.zeros(kb + 13, dtype=torch.float32, device=dev)  # [timesteps kb | coef 9 | slots 4 (int32)]
+                L = dict(key=key, par=par, ts=par[:kb], coef=par[kb:kb + 9], slots=par[kb + 9:].view(torch.int32),
+                         lat=torch.empty(b, C, F, h, w, dtype=torch.float32, device=dev),
+                         eps=torch.empty(kb, Co, F, h, w, dtype=torch.float32, device=dev),
+                         hist=torch.zeros(4, b, C, F, h, w, dtype=torch.float32, device=dev) if self.plms else None)
                 be, plms = eng.be, self.plms
 
                 def step_fn():
                     eng.forward(L["lat"], L["ts"], L["eps"])
                     if plms:
-                        be.cfg_plms_step(L["eps"], k, L["lat"], L["hist"], L["coef"], L["slots"], C, F, h * w)
+                        be.cfg_plms_step(L["eps"], k, L["lat"], L["hist"], L["coef"], L["slots"], C, F, h * w, b)
                     else:
-                        be.cfg_ddim_step(L["eps"], k, L["lat"], L["coef"], C, F, h * w)
+                        be.cfg_ddim_step(L["eps"], k, L["lat"], L["coef"], C, F, h * w, b)
 
                 L["runner"] = _engine.GraphRunner(step_fn, be)
                 pipe._loop = L
             self.L = pipe._loop
-            self.coef_all = torch.tensor([[*wts, p.c_sample, p.c_eps, *p.a] for p in plans],
-                                         dtype=torch.float32).to(dev)
-            self.slots_all = torch.tensor([list(p.slots) for p in plans], dtype=torch.int32).to(dev)
-            self.ts_all = torch.tensor([[float(p.timestep)] * k for p in plans], dtype=torch.float32).to(dev)
+            tab = torch.zeros(len(plans), kb + 13, dtype=torch.float32)
+            tab_i = tab.view(torch.int32)  # the slot indices are int32 bit patterns in the same rows
+            for i, p in enumerate(plans):
+                tab[i, :kb] = float(p.timestep)
+                tab[i, kb:kb + 9] = torch.tensor([*wts, p.c_sample, p.c_eps, *p.a], dtype=torch.float32)
+                tab_i[i, kb + 9:] = torch.tensor(list(p.slots), dtype=torch.int32)
+            self.table = tab.to(dev)
 
     @property
     def latents(self) -> torch.Tensor:
@@ -346,7 +357,7 @@ class DenoiseSession:
         return self.L["runner"].total_launches
 
     def load_latents(self, latents: torch.Tensor) -> None:
-        """Host (pinned) or device tensor (1,C,F,h,w) -> the session's static fp32 latents."""
+        """Host (pinned) or device tensor (b,C,F,h,w) -> the session's static fp32 latents."""
         self.L["lat"].copy_(latents, non_blocking=True)
 
     def read_latents(self, out: torch.Tensor) -> None:
@@ -355,10 +366,7 @@ class DenoiseSession:
     def step(self, i: int) -> None:
         L = self.L
         with torch.cuda.device(self.dev):
-            L["ts"].copy_(self.ts_all[i])
-            L["coef"].copy_(self.coef_all[i])
-            if self.plms:
-                L["slots"].copy_(self.slots_all[i])
+            L["par"].copy_(self.table[i])
             L["runner"]()
 
 

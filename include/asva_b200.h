@@ -138,7 +138,8 @@ typedef struct asva_attn_desc {
 
 int asva_attention(const asva_attn_desc* d, asva_stream_t stream);
 
-/* Temporal self-attention core over the frame axis (F x F per pixel and head), CUDA cores.
+/* Temporal self-attention core over the frame axis (F x F per pixel and head) on tcgen05: blocks of floor(KV/F)
+ * pixels x F frames are queries and keys of one block-diagonal tile, gathered by 5-D TMA boxes (attn_tc.cu).
  * Replaces the SDPA inside attn_temp (ff_spatio_audio_temp_transformer_3d.py:352-358).
  *   qkv : bf16 [B][F][N][3C] (q | k | v), out: bf16 [B][F][N][C] */
 int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
@@ -210,17 +211,18 @@ int asva_timestep_features(const float* t, float* out, int32_t B, int32_t dim, i
                            asva_stream_t stream);
 
 /* Classifier-free guidance + sampler update on frames 1..F-1 (frame 0 is the conditioning image and is never
- * written, pipeline_audio_cond_animation.py:363-364).  eps: fp32 [k][C][F][h][w] UNet outputs (k <= 3 CFG
- * branches); latents: fp32 [C][F][h][w] updated in place.  All scalars live in DEVICE memory so the launch can
- * sit inside a replayed CUDA graph:  coef fp32[9] = {w0, w1, w2, c_sample, c_eps, a0, a1, a2, a3}
+ * written, pipeline_audio_cond_animation.py:363-364).  eps: fp32 [k][clips][C][F][h][w] UNet outputs (k <= 3 CFG
+ * branches, branch-major like the pipeline's torch.cat([latents] * k), :331-336); latents: fp32 [clips][C][F][h][w]
+ * updated in place; every clip of a launch is at the same sampler step.  All scalars live in DEVICE memory so the
+ * launch can sit inside a replayed CUDA graph:  coef fp32[9] = {w0, w1, w2, c_sample, c_eps, a0, a1, a2, a3}
  *   e = w0*eps[0] + w1*eps[1] + w2*eps[2]                                   (CFG combine, :349-361)
  *   DDIM (eta = 0, epsilon prediction):  x <- c_sample * x + c_eps * e
  *   PLMS (PNDMScheduler.step_plms):      e_hat = a0*e + a1*hist[slots[1]] + a2*hist[slots[2]] + a3*hist[slots[3]];
  *                                        if slots[0] >= 0: hist[slots[0]] <- e;   x <- c_sample * x + c_eps * e_hat
- * hist: fp32 [4][C][F][h][w] ring of past e; slots: int32[4] in device memory. */
-int asva_cfg_ddim_step(const float* eps, int32_t k, float* latents, const float* coef, int32_t C, int32_t F,
-                       int32_t hw, asva_stream_t stream);
-int asva_cfg_plms_step(const float* eps, int32_t k, float* latents, float* hist, const float* coef,
+ * hist: fp32 [4][clips][C][F][h][w] ring of past e; slots: int32[4] in device memory. */
+int asva_cfg_ddim_step(const float* eps, int32_t k, int32_t clips, float* latents, const float* coef, int32_t C,
+                       int32_t F, int32_t hw, asva_stream_t stream);
+int asva_cfg_plms_step(const float* eps, int32_t k, int32_t clips, float* latents, float* hist, const float* coef,
                        const int32_t* slots, int32_t C, int32_t F, int32_t hw, asva_stream_t stream);
 
 const char* asva_last_error(void);

@@ -1,7 +1,7 @@
 """oracle/unet_ref.py — TEST INFRASTRUCTURE.  Clean-room CPU restatement (plain torch, fp32 by default) of ASVA's
 audio-conditioned video UNet forward, driven by a reference-format state dict.  It travels to the GPU box (the
 reference tree does not) and is the checker for the CUDA path; it is itself pinned against the reference's own
-files executed through oracle/ref_loader.py (tests/test_oracle_vs_reference.py, tests/golden/).
+files executed through oracle/ref_loader.py (tests/test_host_cpu.py::test_oracle_vs_reference_live, tests/golden/).
 
 Each function cites the reference lines it follows (paths relative to /root/reference/avgen/models/unets/).
 The restatement is functional and applies the result-preserving hoists the product uses:
@@ -35,12 +35,22 @@ def sinusoid(t: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, shift: flo
     return torch.cat([c, s], 1) if flip_sin_to_cos else torch.cat([s, c], 1)
 
 
+def conv2d(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], **kw) -> torch.Tensor:
+    """F.conv2d; low-precision inputs are multiplied in fp32 and the result rounded back (what a bf16 conv with fp32
+    accumulation computes) - torch's CPU bf16 convolution returns NaN on few-pixel images (4x2 -> 2x1, stride 2)."""
+    if x.dtype == torch.float32:
+        return F.conv2d(x, w, b, **kw)
+    return F.conv2d(x.float(), w.float(), None if b is None else b.float(), **kw).to(x.dtype)
+
+
 def lin(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
     return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
 
 
 def time_mlp(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
-    """diffusers TimestepEmbedding: linear_1 -> SiLU -> linear_2."""
+    """diffusers TimestepEmbedding: linear_1 -> SiLU -> linear_2.  The sinusoid is fp32 and is cast to the model
+    dtype before the first linear (audio_cond_unet_3d_condition.py:679)."""
+    x = x.to(sd[p + ".linear_1.weight"].dtype)
     return lin(sd, p + ".linear_2", F.silu(lin(sd, p + ".linear_1", x)))
 
 
@@ -50,7 +60,7 @@ def ff_conv(sd: SD, p: str, x: torch.Tensor, stride: int = 1) -> torch.Tensor:
     B, C, Fr, h, w = x.shape
     wt = sd[p + ".weight"]
     pad = (wt.shape[-1] - 1) // 2
-    y = F.conv2d(x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, h, w), wt, sd[p + ".bias"], stride=stride, padding=pad)
+    y = conv2d(x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, h, w), wt, sd[p + ".bias"], stride=stride, padding=pad)
     Co, ho, wo = y.shape[1:]
     y = y.view(B, Fr, Co, ho, wo).permute(0, 1, 3, 4, 2)  # (B,F,h,w,C)
     W = sd[p + ".conv_temp.weight"]
@@ -96,7 +106,7 @@ def transformer(sd: SD, p: str, x: torch.Tensor, text: torch.Tensor, audio: torc
     N = h * w
     xf = x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, h, w)
     t = F.group_norm(xf, groups, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)  # per frame, eps 1e-6 (:61)
-    t = F.conv2d(t, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
+    t = conv2d(t, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
     t = t.permute(0, 2, 3, 1).reshape(B, Fr, N, C)
     b = p + ".transformer_blocks.0"
 
@@ -135,15 +145,20 @@ def transformer(sd: SD, p: str, x: torch.Tensor, text: torch.Tensor, audio: torc
     t = t + lin(sd, b + ".ff.net.2", hval * F.gelu(gate))
     # proj_out + residual (:142-153)
     o = t.reshape(B * Fr, h, w, C).permute(0, 3, 1, 2)
-    o = F.conv2d(o, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"]) + xf
+    o = conv2d(o, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"]) + xf
     return o.view(B, Fr, C, h, w).permute(0, 2, 1, 3, 4)
 
 
 def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, text: torch.Tensor, audio: torch.Tensor,
-                 audio_mask: Optional[torch.Tensor]) -> torch.Tensor:
+                 audio_mask: Optional[torch.Tensor], dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """AudioUNet3DConditionModel.forward, audio_cond_unet_3d_condition.py:598-798 with the block sequencing of
     unet_3d_blocks.py:285-302 (res down), :904-938 (attn down), :789-819 (mid), :354-369 (res up), :1019-1064
-    (attn up).  sample (B,4,F,h,w) -> (B,4,F,h,w)."""
+    (attn up).  sample (B,4,F,h,w) -> (B,4,F,h,w).
+    dtype = torch.bfloat16 runs the same restatement with weights and activations in bfloat16 - "torch's own bf16
+    eager" of this model, the yardstick the GPU tolerances are anchored to (SURVEY.md section 8(c))."""
+    if dtype != torch.float32:
+        sd = {k: v.to(dtype) for k, v in sd.items()}
+        sample, text, audio = sample.to(dtype), text.to(dtype), audio.to(dtype)
     c = dict(DEFAULT_CONFIG)
     c.update(cfg or {})
     chans, groups, eps, heads = tuple(c["block_out_channels"]), c["norm_num_groups"], c["norm_eps"], c["attention_head_dim"]

@@ -227,21 +227,21 @@ class SimBackend:
             e = e + coef[j] * eps[j]
         return e
 
-    def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw) -> None:
+    def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw, clips: int = 1) -> None:
         self.launches += 1
-        e = self._cfg(eps.view(k, C, F, hw), k, coef)
-        lv = lat.view(C, F, hw)
-        lv[:, 1:] = coef[3] * lv[:, 1:] + coef[4] * e[:, 1:]
+        e = self._cfg(eps.view(k, clips, C, F, hw), k, coef)
+        lv = lat.view(clips, C, F, hw)
+        lv[:, :, 1:] = coef[3] * lv[:, :, 1:] + coef[4] * e[:, :, 1:]
 
-    def cfg_plms_step(self, eps, k, lat, hist, coef, slots, C, F, hw) -> None:
+    def cfg_plms_step(self, eps, k, lat, hist, coef, slots, C, F, hw, clips: int = 1) -> None:
         self.launches += 1
-        e = self._cfg(eps.view(k, C, F, hw), k, coef)
-        hv = hist.view(4, C, F, hw)
+        e = self._cfg(eps.view(k, clips, C, F, hw), k, coef)
+        hv = hist.view(4, clips, C, F, hw)
         ehat = coef[5] * e
         for j in range(1, 4):
             if float(coef[5 + j]) != 0.0:
                 ehat = ehat + coef[5 + j] * hv[int(slots[j])]
         if int(slots[0]) >= 0:
-            hv[int(slots[0]), :, 1:] = e[:, 1:]
-        lv = lat.view(C, F, hw)
-        lv[:, 1:] = coef[3] * lv[:, 1:] + coef[4] * ehat[:, 1:]
+            hv[int(slots[0]), :, :, 1:] = e[:, :, 1:]
+        lv = lat.view(clips, C, F, hw)
+        lv[:, :, 1:] = coef[3] * lv[:, :, 1:] + coef[4] * ehat[:, :, 1:]

@@ -367,3 +367,36 @@ def test_tconv_spec_single_frame_tiles():
     assert [(g.off, g.wk, g.wk_first, g.fix2) for g in sp.segs] == [((0, 0, 0), 0, -1, -1), ((0, -1, 0), C, -1, -1),
                                                                      ((0, 0, 0), 2 * C, 3 * C, 0)]
     assert sp.K == 3 * C and sp.wcols == 4 * C
+
+
+# ------------------------------------------------------------------------------------------------ pipeline plumbing
+def test_pipeline_conditioning_branch_order_cpu():
+    """encode_text / encode_audio build the CFG batches in the reference's branch-major order
+    (pipeline_audio_cond_animation.py:149-154, 186-194): dual [uncond, text, text] x [null, null, audio], text-only
+    [uncond, text] x [audio, audio], audio-only [text, text] x [null, audio]; b > 1 repeats the null masks (F8)."""
+    import stubs
+    from avgen.pipelines.pipeline_audio_cond_animation import AudioCondAnimationPipeline
+    F = 4
+    pipe = AudioCondAnimationPipeline(stubs.StubTextEncoder(), stubs.StubTokenizer(), None, schedulers.PNDMScheduler(),
+                                      stubs.StubVAE(), stubs.StubAudioEncoder(F))
+    pipe._audio_processor = stubs.StubMelExtractor()
+    cpu, f32 = torch.device("cpu"), torch.float32
+    texts = ["a dog", "rain"]
+    txt = stubs.StubTextEncoder()(stubs.StubTokenizer()(texts).input_ids)[0]
+    unc = stubs.StubTextEncoder()(stubs.StubTokenizer()("").input_ids)[0].expand(2, -1, -1)
+    audios = [torch.randn(1, 5000, generator=torch.Generator().manual_seed(i)) for i in range(2)]
+    _, a_enc, a_mask = stubs.StubAudioEncoder(F)(stubs.StubMelExtractor()(audios))
+    _, n_enc, n_mask = stubs.StubAudioEncoder(F)(torch.zeros(1, 1, 128, 204))
+    n_enc, n_mask = n_enc.expand(2, -1, -1), n_mask.expand(2, -1, -1)
+    for do_t, do_a, t_exp, a_exp, m_exp in (
+            (True, True, [unc, txt, txt], [n_enc, n_enc, a_enc], [n_mask, n_mask, a_mask]),
+            (True, False, [unc, txt], [a_enc, a_enc], [a_mask, a_mask]),
+            (False, True, [txt, txt], [n_enc, a_enc], [n_mask, a_mask]),
+            (False, False, [txt], [a_enc], [a_mask])):
+        t = pipe.encode_text(texts, cpu, f32, do_t, do_a)
+        assert torch.equal(t, torch.cat(t_exp)), (do_t, do_a)
+        a, m = pipe.encode_audio(audios, F, do_t, do_a, cpu, f32)
+        assert a.shape == (2 * len(a_exp), F, 229, 768) and a.stride(1) == 0  # frame axis is an expand
+        assert torch.equal(a[:, 0], torch.cat(a_exp)) and torch.equal(m, torch.cat(m_exp)), (do_t, do_a)
+    lat = pipe.prepare_video_latents(torch.zeros(2, 4, 8, 8), 4, F, 64, 64, cpu, f32, torch.Generator().manual_seed(1))
+    assert lat.shape == (2, 4, F, 8, 8) and float(lat[:, :, 0].abs().max()) == 0.0 and float(lat[:, :, 1:].std()) > 0.5

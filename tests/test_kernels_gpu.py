@@ -240,6 +240,29 @@ def test_attention(cuda_backend, d, R, Nk, masked):
     _attn_case(cuda_backend, 2, 8, R, Nk, d, masked, 30 + d)
 
 
+def test_attention_config4_first_frame_shape(cuda_backend):
+    """BASELINE config 4's level-0 first-frame attention: per CFG branch 24 frames x 4 096 queries against the 4 096
+    keys of frame 0 (G 2, R 98 304, Nk 4 096, d 40) - 64 key tiles per query tile, 12 288 query tiles.  The reference
+    is evaluated in fp32 in row chunks (the full score tensor would be 26 GB)."""
+    G, heads, R, Nk, d = 2, 8, 98304, 4096, 40
+    C = heads * d
+    q = _rand((G * R, C), 45)
+    kv = _rand((G * Nk, 2 * C), 46)
+    out = torch.zeros(G * R, C, dtype=torch.bfloat16, device=DEV)
+    spec = ops.AttnSpec(q=q, kv=kv, out=out, G=G, heads=heads, R=R, Nk=Nk, d=d, dpad=64, ldq=C, ldkv=2 * C, ldo=C,
+                        kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d))
+    cuda_backend.attention(spec)
+    torch.cuda.synchronize()
+    ref = torch.empty_like(out)
+    k = kv.view(G, Nk, 2 * C)[:, :, :C].reshape(G, Nk, heads, d).permute(0, 2, 1, 3).float()
+    v = kv.view(G, Nk, 2 * C)[:, :, C:].reshape(G, Nk, heads, d).permute(0, 2, 1, 3).float()
+    for r0 in range(0, R, 8192):
+        qc = q.view(G, R, heads, d)[:, r0:r0 + 8192].permute(0, 2, 1, 3).float()
+        oc = torch.nn.functional.scaled_dot_product_attention(qc, k, v)
+        ref.view(G, R, heads, d)[:, r0:r0 + 8192] = oc.permute(0, 2, 1, 3).to(torch.bfloat16)
+    _report("attention config-4 level 0", out, ref, 1e-2)
+
+
 def test_attention_large_scores(cuda_backend):
     # online-softmax rescale path: later key tiles carry the maxima
     G, heads, R, Nk, d = 1, 2, 128, 512, 40
@@ -353,7 +376,8 @@ def test_groupnorm_fused(cuda_backend, n_inst, rows, C0, C1, silu):
     _report("gn fused vs F.group_norm", outs[0], want, 4e-3)
     _report("gn fused vs sim", outs[0], o_sim, 4e-3)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
-    assert int(cuda_backend._gn_sync.view(torch.int32).abs().sum()) == 0  # counters and accumulators back to zero
+    for sync in cuda_backend._gn_sync.values():  # counters and accumulators back to zero (one workspace per device)
+        assert int(sync.view(torch.int32).abs().sum()) == 0
 
 
 # ------------------------------------------------------------------------------------------------ small kernels
@@ -411,25 +435,32 @@ def test_timestep_features(cuda_backend):
     assert (o_cu - o_ref).abs().max() < 2e-4  # sin/cos of arguments up to ~1e3 in fp32
 
 
-@pytest.mark.parametrize("k", [1, 2, 3])
-def test_cfg_steps(cuda_backend, k):
+@pytest.mark.parametrize("k,clips", [(1, 1), (2, 1), (3, 1), (2, 3), (3, 2)])
+def test_cfg_steps(cuda_backend, k, clips):
+    """eps (k, clips, C, F, hw) branch-major; latents (clips, C, F, hw); the clips of a launch share the step."""
     C, F, hw = 4, 6, 80
-    eps = _rand((k, C, F, hw), 100, dtype=torch.float32)
-    lat0 = _rand((C, F, hw), 101, dtype=torch.float32)
+    eps = _rand((k * clips, C, F, hw), 100, dtype=torch.float32)
+    lat0 = _rand((clips, C, F, hw), 101, dtype=torch.float32)
     coef = torch.tensor([-3.0, 4.0, 0.5, 1.01, -0.07, 23 / 12, -16 / 12, 5 / 12, 0.0], device=DEV)
     if k < 3:
         coef[2] = 0.0
     a, b = lat0.clone(), lat0.clone()
-    SimBackend().cfg_ddim_step(eps, k, a, coef, C, F, hw)
-    cuda_backend.cfg_ddim_step(eps, k, b, coef, C, F, hw)
+    SimBackend().cfg_ddim_step(eps, k, a, coef, C, F, hw, clips)
+    cuda_backend.cfg_ddim_step(eps, k, b, coef, C, F, hw, clips)
     torch.cuda.synchronize()
-    assert torch.equal(a[:, 0], lat0[:, 0]) and torch.equal(b[:, 0], lat0[:, 0])
+    assert torch.equal(a[:, :, 0], lat0[:, :, 0]) and torch.equal(b[:, :, 0], lat0[:, :, 0])
     _report("cfg ddim", b.view(-1, hw), a.view(-1, hw), 1e-6)
-    hist0 = _rand((4, C, F, hw), 102, dtype=torch.float32)
+    if clips > 1:  # clip j of a batched launch == the same clip stepped alone
+        j = clips - 1
+        alone = lat0[j].clone()
+        cuda_backend.cfg_ddim_step(eps.view(k, clips, C, F, hw)[:, j].contiguous(), k, alone, coef, C, F, hw, 1)
+        torch.cuda.synchronize()
+        assert torch.equal(alone, b[j])
+    hist0 = _rand((4, clips, C, F, hw), 102, dtype=torch.float32)
     slots = torch.tensor([2, 0, 1, 3], dtype=torch.int32, device=DEV)
     a, b, ha, hb = lat0.clone(), lat0.clone(), hist0.clone(), hist0.clone()
-    SimBackend().cfg_plms_step(eps, k, a, ha, coef, slots, C, F, hw)
-    cuda_backend.cfg_plms_step(eps, k, b, hb, coef, slots, C, F, hw)
+    SimBackend().cfg_plms_step(eps, k, a, ha, coef, slots, C, F, hw, clips)
+    cuda_backend.cfg_plms_step(eps, k, b, hb, coef, slots, C, F, hw, clips)
     torch.cuda.synchronize()
     _report("cfg plms", b.view(-1, hw), a.view(-1, hw), 1e-6)
-    _report("cfg plms hist", hb[:, :, 1:].reshape(-1, hw), ha[:, :, 1:].reshape(-1, hw), 1e-6)
+    _report("cfg plms hist", hb[:, :, :, 1:].reshape(-1, hw), ha[:, :, :, 1:].reshape(-1, hw), 1e-6)

@@ -1,13 +1,15 @@
 """Whole-path parity on the B200 through the PUBLIC API (avgen.models.unets / avgen.pipelines): the CUDA engine vs
 (1) tests/golden/ fixtures produced by executing the reference's own UNet files on CPU in fp32
 (oracle/make_goldens.py) and (2) the clean-room CPU oracle on fresh seeds.
-Stated tolerance (reference fp32 vs bf16-storage / fp32-accumulate kernels; SURVEY.md section 8(c) calibrates torch's
-own bf16 eager run of the reference at rel-L2 1.45e-2): one UNet forward at the SD-1.5 geometry rel-L2 <= 2e-2 and
-cosine >= 0.9995 (measured 1.3e-2 .. 1.4e-2); the 64..256-channel toy geometries (fewer channels to average the
-rounding over) rel-L2 <= 4e-2 and N-step sampler latents on the toy geometry rel-L2 <= 4e-2.  The toy numbers are
-noisy by construction: which bf16 roundings flip depends on the fp32 summation order inside a GEMM, and that order
-changes with the tile plan the tuner picks (split-K or not) - measured 2.3e-2 .. 3.0e-2 across boxes for the same
-seed, hence the margin.  The cosine bound (>= 0.9995) is the same everywhere."""
+Stated tolerance (reference fp32 vs bf16-storage / fp32-accumulate kernels), SURVEY.md section 8(c):
+  * SD-1.5 geometry (configs 2 and 4): one UNet forward rel-L2 <= 2e-2, cosine >= 0.9995 (measured 1.3e-2 .. 1.4e-2);
+    latents after steps 1, 2, 3 and N of a 50-step DDIM / 51-call PNDM run rel-L2 <= 2e-2;
+  * ANCHOR: every fixture records `bf16_eager_rel`, the error of torch's own eager run of the reference model in pure
+    bfloat16 against its fp32 run on the same inputs (oracle/make_goldens.py: 1.48e-2 at SD-1.5, 1.9e-2 .. 2.5e-2 on
+    the 64..256-channel toy nets, 2.5e-2 .. 3.6e-2 along the toy sampler traces); the CUDA path must stay within
+    1.5 x that number.  Tests against the CPU oracle on fresh seeds compute the same anchor live (the oracle run in
+    bfloat16).  The toy numbers are larger than SD-1.5's because fewer channels average the rounding.
+The cosine bound (>= 0.9995) is the same everywhere."""
 import glob
 import os
 
@@ -17,7 +19,8 @@ import torch
 from asva_b200 import schedulers, synth
 
 pytestmark = pytest.mark.gpu
-TOL_TOY = 4e-2
+ANCHOR_X = 1.5   # err(ours) <= ANCHOR_X * err(torch bf16 eager of the reference), SURVEY.md 8(c)
+TOL_SD15 = 2e-2
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _MODELS = {}
 
@@ -41,8 +44,19 @@ def _check(name, got, ref, tol):
     rel = float((got - ref).norm() / ref.norm())
     cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
     print(f"[parity] {name}: rel-L2 {rel:.3e} cos {cos:.6f} max|d| {float((got - ref).abs().max()):.3e}")
-    assert rel <= tol and cos >= 0.9995, (name, rel, cos)
+    assert rel <= tol and cos >= 0.9995, (name, rel, cos, tol)
     return rel
+
+
+def _oracle_pair(sd, chans, x, t, text, audio, mask):
+    """fp32 oracle output and the live anchor tolerance: ANCHOR_X x the error of the same oracle run in bfloat16."""
+    from oracle import unet_ref
+    cfg = dict(block_out_channels=chans)
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, cfg, x, t, text, audio, mask)
+        low = unet_ref.unet_forward(sd, cfg, x, t, text, audio, mask, dtype=torch.bfloat16)
+    anchor = float((low.float() - ref).norm() / ref.norm())
+    return ref, ANCHOR_X * anchor
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "unet_tiny_*.pt"))), ids=os.path.basename)
@@ -54,7 +68,7 @@ def test_unet_vs_reference_golden_tiny(cuda_backend, path):
     for rep in range(3):  # eager, graph capture, graph replay must all agree
         y = m(x, g["t"], encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
               audio_attention_mask=mask.cuda()).sample
-        _check(f"{os.path.basename(path)} call {rep}", y, g["out"], TOL_TOY if "tiny" in path else 2e-2)
+        _check(f"{os.path.basename(path)} call {rep}", y, g["out"], ANCHOR_X * g["bf16_eager_rel"])
 
 
 def test_unet_vs_reference_golden_sd15(cuda_backend):
@@ -65,7 +79,20 @@ def test_unet_vs_reference_golden_sd15(cuda_backend):
     for rep in range(3):
         y = m(x, torch.tensor(g["t"]), encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
               audio_attention_mask=mask.cuda()).sample
-        _check(f"sd15 12x32x32 call {rep}", y, g["out"], 2e-2)
+        _check(f"sd15 12x32x32 call {rep}", y, g["out"], min(TOL_SD15, ANCHOR_X * g["bf16_eager_rel"]))
+
+
+def test_unet_vs_reference_golden_sd15_config4(cuda_backend):
+    """BASELINE config 4 at full channel width: 24 frames x 64x64 latents (196 608 tokens at level 0, 4 096-key
+    first-frame attention), against the reference's own fp32 output."""
+    g = torch.load(os.path.join(GOLD, "unet_sd15_cfg4.pt"))
+    m, _ = _model(g["chans"])
+    lat, text, audio, mask = synth.synth_inputs(F=g["F"], h=g["h"], w=g["w"], k=g["k"], seed=g["input_seed"])
+    x = lat.expand(g["k"], -1, -1, -1, -1).contiguous().cuda()
+    for rep in range(2):
+        y = m(x, g["t"], encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
+              audio_attention_mask=mask.cuda()).sample
+        _check(f"sd15 24x64x64 call {rep}", y, g["out"], TOL_SD15)
 
 
 def test_unet_vs_oracle_fresh_seed_and_frame_varying_context(cuda_backend):
@@ -79,16 +106,14 @@ def test_unet_vs_oracle_fresh_seed_and_frame_varying_context(cuda_backend):
     text = torch.randn(B, F, 77, 768, generator=g)
     audio = torch.randn(B, F, 229, 768, generator=g)
     mask = synth.audio_segment_mask(F)[None].expand(B, -1, -1).contiguous()
-    with torch.no_grad():
-        ref = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, 37, text, audio, mask)
+    ref, tol = _oracle_pair(sd, chans, x, 37, text, audio, mask)
     y = m(x.cuda(), 37, encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
           audio_attention_mask=mask.cuda(), return_dict=False)[0]
-    _check("fresh seed, per-frame contexts", y, ref, TOL_TOY)
+    _check("fresh seed, per-frame contexts", y, ref, tol)
     y2 = m(x.cuda(), 37, encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
            audio_attention_mask=None).sample
-    with torch.no_grad():
-        ref2 = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, 37, text, audio, None)
-    _check("no audio mask", y2, ref2, TOL_TOY)
+    ref2, tol2 = _oracle_pair(sd, chans, x, 37, text, audio, None)
+    _check("no audio mask", y2, ref2, tol2)
 
 
 @pytest.mark.parametrize("B,F,h,w,n_text,masked", [(1, 8, 24, 40, 77, True), (3, 4, 8, 16, 77, True),
@@ -107,34 +132,94 @@ def test_unet_geometry_sweep(cuda_backend, B, F, h, w, n_text, masked):
     audio = torch.randn(B, 1, 229, 768, generator=g).expand(B, F, 229, 768).contiguous()
     mask = synth.audio_segment_mask(F)[None].expand(B, -1, -1).contiguous() if masked else None
     t = 11 + 40 * F
-    with torch.no_grad():
-        ref = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, t, text, audio, mask)
+    ref, tol = _oracle_pair(sd, chans, x, t, text, audio, mask)
     for rep in range(2):  # first call (tuning pass + capture) and the replay
         y = m(x.cuda(), t, encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
               audio_attention_mask=mask.cuda() if masked else None).sample
-        _check(f"B{B} F{F} {h}x{w} text{n_text} mask{int(masked)} call {rep}", y, ref, TOL_TOY)
+        _check(f"B{B} F{F} {h}x{w} text{n_text} mask{int(masked)} call {rep}", y, ref, tol)
 
 
-@pytest.mark.parametrize("name", ["ddim", "pndm"])
+def _sched(name):
+    return schedulers.DDIMScheduler() if name.startswith("ddim") else schedulers.PNDMScheduler()
+
+
+@pytest.mark.parametrize("name", ["ddim", "pndm", "ddim_dual", "pndm_dual"])
 def test_sampler_trace_vs_golden(cuda_backend, name):
+    """6-step DDIM / 7-call PLMS on a toy geometry through pipeline.denoise (fused session): audio-only CFG (k = 2)
+    and dual text + audio CFG (k = 3, weights (1 - s_t, s_t - s_a, s_a), reference :349-353), every step against the
+    reference-UNet trace within ANCHOR_X x the bf16-eager error of that step."""
     from avgen.pipelines.pipeline_audio_cond_animation import AudioCondAnimationPipeline
     g = torch.load(os.path.join(GOLD, f"sampler_{name}.pt"))
     m, _ = _model(g["chans"])
-    sched = schedulers.DDIMScheduler() if name == "ddim" else schedulers.PNDMScheduler()
-    pipe = AudioCondAnimationPipeline(None, None, m, sched, None, None)
+    pipe = AudioCondAnimationPipeline(None, None, m, _sched(name), None, None)
     pipe.set_progress_bar_config(disable=True)
-    lat, text, audio, mask = synth.synth_inputs(F=g["F"], h=g["h"], w=g["w"], k=2)
+    lat, text, audio, mask = synth.synth_inputs(F=g["F"], h=g["h"], w=g["w"], k=g["k"])
     trace = []
     for run in range(2):  # second run replays the captured graph and must reproduce the first
         trace.clear()
         out = pipe.denoise(lat.cuda(), text.cuda(), audio.cuda(), mask.cuda(), g["steps"],
-                           audio_guidance_scale=g["audio_scale"],
+                           audio_guidance_scale=g["audio_scale"], text_guidance_scale=g["text_scale"],
                            callback=lambda i, t, l: trace.append(l.clone().cpu()))
-        assert len(trace) == g["trace"].shape[0]
+        assert len(trace) == g["calls"]
         assert torch.equal(out.cpu()[:, :, 0], lat[:, :, 0]), "conditioning frame must never change"
-        for i in (0, 1, 2, len(trace) - 1):
-            _check(f"{name} run {run} after step {i + 1}", trace[i], g["trace"][i], TOL_TOY)
+        for j, i in enumerate(g["kept"]):
+            _check(f"{name} run {run} after step {i + 1}", trace[i], g["trace"][j], ANCHOR_X * g["bf16_eager_rel"][j])
     assert pipe.last_launches > 0
+
+
+@pytest.mark.parametrize("name", ["ddim", "pndm"])
+def test_sampler_trace_sd15_50_steps(cuda_backend, name):
+    """BASELINE config 2 end to end on the hot path: 50-step DDIM / 51-call PNDM (what scripts/animation_demo.py
+    runs) at the full SD-1.5 geometry, audio guidance 4.0; latents after steps 1, 2, 3 and N against the trace of
+    the reference's own UNet (fp32 CPU) - bf16 error must not compound over the loop (<= 2e-2)."""
+    from avgen.pipelines.pipeline_audio_cond_animation import AudioCondAnimationPipeline
+    g = torch.load(os.path.join(GOLD, f"sampler_{name}_sd15.pt"))
+    m, _ = _model(g["chans"])
+    pipe = AudioCondAnimationPipeline(None, None, m, _sched(name), None, None)
+    pipe.set_progress_bar_config(disable=True)
+    lat, text, audio, mask = synth.synth_inputs(F=g["F"], h=g["h"], w=g["w"], k=g["k"])
+    trace = {}
+    out = pipe.denoise(lat.cuda(), text.cuda(), audio.cuda(), mask.cuda(), g["steps"],
+                       audio_guidance_scale=g["audio_scale"], text_guidance_scale=g["text_scale"],
+                       callback=lambda i, t, l: trace.__setitem__(i, l.clone().cpu()) if i in g["kept"] else None)
+    assert torch.equal(out.cpu()[:, :, 0], lat[:, :, 0])
+    for j, i in enumerate(g["kept"]):
+        _check(f"sd15 {name} after call {i + 1} of {g['calls']}", trace[i], g["trace"][j], TOL_SD15)
+
+
+def test_two_clips_per_gpu_session(cuda_backend):
+    """b = 2 clips batched in one fused session (k*b = 4 UNet rows, branch-major): clip 0 reproduces the golden
+    single-clip trace, clip 1 matches its own single-clip run, and neither clip's frame 0 changes."""
+    from avgen.pipelines.pipeline_audio_cond_animation import AudioCondAnimationPipeline
+    g = torch.load(os.path.join(GOLD, "sampler_pndm.pt"))
+    m, _ = _model(g["chans"])
+    F, h, w, k = g["F"], g["h"], g["w"], g["k"]
+    clips = [synth.synth_inputs(F=F, h=h, w=w, k=k, seed=s) for s in (123, 124)]
+
+    def branch_major(i):  # [branch 0 of every clip, branch 1 of every clip, ...] like torch.cat([x] * k)
+        return torch.cat([torch.stack([c[i][j] for c in clips]) for j in range(k)])
+
+    pipe = AudioCondAnimationPipeline(None, None, m, schedulers.PNDMScheduler(), None, None)
+    pipe.set_progress_bar_config(disable=True)
+    lat2 = torch.cat([c[0] for c in clips])
+    both = pipe.denoise(lat2.cuda(), branch_major(1).cuda(), branch_major(2).cuda(), branch_major(3).cuda(),
+                        g["steps"], audio_guidance_scale=g["audio_scale"]).cpu()
+    assert torch.equal(both[:, :, 0], lat2[:, :, 0])
+    _check("clip 0 of 2 vs golden", both[:1], g["trace"][-1], ANCHOR_X * g["bf16_eager_rel"][-1])
+    # clip 1 has no golden: its truth is the CPU oracle UNet under the restated PNDM loop (fp32)
+    from oracle import sampler_ref, unet_ref
+    _, sd = _model(g["chans"])
+    lat1, text1, audio1, mask1 = clips[1]
+    want = lat1.clone()
+    with torch.no_grad():
+        sampler_ref.denoise_loop(lambda x, t, a, b, c: unet_ref.unet_forward(sd, dict(block_out_channels=g["chans"]),
+                                                                             x, t, a, b, c),
+                                 sampler_ref.PNDMRef(g["steps"]), want, text1, audio1, mask1,
+                                 audio_scale=g["audio_scale"])
+    _check("clip 1 of 2 vs CPU oracle loop", both[1:], want, ANCHOR_X * g["bf16_eager_rel"][-1])
+    solo = pipe.denoise(lat1.cuda(), text1.cuda(), audio1.cuda(), mask1.cuda(), g["steps"],
+                        audio_guidance_scale=g["audio_scale"]).cpu()
+    _check("clip 1 alone vs CPU oracle loop", solo, want, ANCHOR_X * g["bf16_eager_rel"][-1])
 
 
 def test_generic_scheduler_path_matches_fused(cuda_backend):
@@ -168,12 +253,11 @@ def test_context_swap_after_graph_capture(cuda_backend):
     x = torch.randn(B, 4, F, h, w, generator=g)
 
     def run(text, audio, mask, name, reps):
-        with torch.no_grad():
-            ref = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, 500, text, audio, mask)
+        ref, tol = _oracle_pair(sd, chans, x, 500, text, audio, mask)
         for r in range(reps):
             y = m(x.cuda(), 500, encoder_hidden_states=text.cuda(), audio_encoder_hidden_states=audio.cuda(),
                   audio_attention_mask=mask.cuda()).sample
-            _check(f"{name} rep {r}", y, ref, TOL_TOY)
+            _check(f"{name} rep {r}", y, ref, tol)
 
     rule = synth.audio_segment_mask(F)[None].expand(B, -1, -1).contiguous()
     t1 = torch.randn(B, 1, 77, 768, generator=g).expand(B, F, 77, 768)
