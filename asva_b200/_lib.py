@@ -117,7 +117,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    # ASVA_LIB: an experiment build (tools/build_debug.sh: -DASVA_DEBUG_SWITCHES, traces) instead of the shipped library
+    p = path or os.environ.get("ASVA_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise AsvaError(
             f"{p} not found: build it with `python -m asva_b200.build` (or __graft_entry__.build()); "

@@ -24,17 +24,26 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """debug=True builds lib/libasva_b200_dbg.so with -DASVA_DEBUG_SWITCHES (environment-driven plan overrides,
+    work-skipping timing modes, in-kernel traces) next to the shipped library; select it with ASVA_LIB=<path>."""
+    if debug:
+        return _build(LIB.replace(".so", "_dbg.so"), ["-DASVA_DEBUG_SWITCHES"], "dbg_", verbose)
     if not force and not _stale():
         return LIB
+    return _build(LIB, [], "", verbose)
+
+
+def _build(lib_path: str, extra: list, obj_prefix: str, verbose: bool) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        obj = os.path.join(LIBDIR, obj_prefix + src.replace(".cu", ".o"))
         # ASVA_NVCC_EXTRA: extra flags for experiments, e.g. "-DASVA_GEMM_LEAN_ISSUER" (use with force=True / --force)
-        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("ASVA_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *os.environ.get("ASVA_NVCC_EXTRA", "").split(), "-c",
+               os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -45,12 +54,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out:
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

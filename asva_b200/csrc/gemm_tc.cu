@@ -38,8 +38,18 @@ constexpr int kDefaultEpi = 1;          // epilogue form when neither the descri
 // The default library never reads the environment on the launch path and has no work-skipping branch.
 #ifdef ASVA_DEBUG_SWITCHES
 #define ASVA_DBG(p) ((p).dbg)
+// ASVA_GEMM_TRACE=1: CTA 0 stamps %globaltimer at the marked points into a [warp][event] table (see asva_gemm)
+#define ASVA_TR(p, w, e)                                                                      \
+  do {                                                                                        \
+    if ((p).trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (e) < 64) {     \
+      unsigned long long _t;                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                  \
+      (p).trace[(w) * 64 + (e)] = static_cast<long long>(_t);                                 \
+    }                                                                                         \
+  } while (0)
 #else
 #define ASVA_DBG(p) 0
+#define ASVA_TR(p, w, e) do { } while (0)
 #endif
 
 struct SegK {
@@ -48,16 +58,20 @@ struct SegK {
 
 struct GemmKParams {
   CUtensorMap tmA0, tmA1, tmW, tmR0, tmR1, tmO;
+  CUtensorMap tmO2;  // epi == 3, bf16: the 32-column tail panel of a tile whose width is not a multiple of 64
   SegK seg[ASVA_GEMM_MAX_SEG];
   int32_t box[3], trav[3], out_dims[3], tiles[3];
   int32_t rows_per_tile, N, n_out, num_kb, n_tiles_n, mn_tiles, total_tiles, split_k, kb_per_split;
   int32_t n_stages, n_res, n_res_slots, out_fp32, dbg;
+  long long* trace;  // debug builds only (ASVA_GEMM_TRACE)
+  int32_t sub_rows;  // epi == 3: rows of a warp's slice of the tile (32, or the whole tile when it has fewer)
   int32_t pf_blocks, w_kblocks;  // W prefetch: blocks per CTA (0 = off), 64-column blocks of W that exist  // dbg (ASVA_GEMM_DBG): 1 = skip TMA loads, 2 = skip MMAs (timing only)
   const float* bias;
   const float* add_ptr;
   int64_t add_ld;
   int32_t add_div;
-  int32_t epi;  // 1 = panel epilogue (TMA residual ring, TMA stores), 2 = per-warp epilogue (direct loads / stores)
+  int32_t epi;  // 1 = panel epilogue (TMA residual ring, TMA stores), 2 = per-warp epilogue (direct loads / stores),
+                // 3 = warp-private TMA epilogue (every warp moves its own 32-row slice of a panel with its own TMA ops)
   __nv_bfloat16* out_ptr;  // epi == 2 only
   int64_t ldo;
   const __nv_bfloat16* res_ptr[2];
@@ -244,6 +258,451 @@ __device__ __forceinline__ void epilogue_direct(const GemmKParams& p, int warp, 
   }
 }
 
+// Warp-private TMA epilogue (epi == 3). Measured with a %globaltimer trace (profiles/r2_gemm_trace.md): a panel of the
+// panel epilogue costs a warp ~1.5 us of which ~350 instructions are issued by only two warps per scheduler - bias loads
+// that miss the (almost absent) L1, bf16 unpack + fp32 adds for the residual, one lane decoding tiles and issuing the
+// residual TMA loads, 64-byte rows on both the residual and the output side. Every short-K launch runs at that pace.
+// This form removes work from the chain instead of overlapping it:
+//   * each of the eight epilogue warps owns the 32 rows of its TMEM lane quadrant: private staging, private TMA
+//     stores through a tensor map whose row box is the quadrant's slice of the tile (host: sub_box) - no block barrier;
+//   * bf16 outputs move 64-column panels (128-byte rows: whole lines in, whole lines out, half the per-panel fixed cost);
+//   * residual panels arrive through a ring shared by both groups and are issued by warp 2, which has nothing else to
+//     do, so no epilogue lane decodes tiles or issues loads; they are added in fp32 before the single bf16 rounding
+//     (a packed bf16x2 add was 5 % faster but cost 8 % of the whole-UNet error budget: measured, not shipped);
+//   * bias loads are issued before the wait for the TMEM load, so their L2 latency hides under it.
+// GEGLU and fp32 outputs keep 32-column panels (epilogue_warp_tma_narrow).
+template <int BN, int CG>
+__device__ __forceinline__ int wide_chunks(const GemmKParams& p, int n0) {  // 32-column chunks of the tile that exist
+  const int left = p.n_out - n0;
+  return ((left < BN ? left : BN) + 31) >> 5;
+}
+
+// warp 2, one lane: residual panels in the order the epilogue consumes them (tile, panel, residual).
+// The D slots are split into one private ring per epilogue group (group 0: ceil(D/2) slots, group 1: the rest): a slot is
+// then always consumed by the same four warps, in order, and the parity of its barriers cannot alias. (With one ring
+// shared by both groups a group could reach "slot s, phase p+1" before phase p had even landed - mbarrier parity waits
+// tell adjacent phases apart, not phases two apart - read stale data, release the slot early and desynchronise the ring:
+// seen as a hang when the loads came from DRAM in a different order, profiles/r2_gemm_trace.md.)
+template <int BN, int CG>
+__device__ __forceinline__ void residual_issuer_wide(const GemmKParams& p, int rank, int tile0, int tile_step,
+                                                     uint64_t* res_full, uint64_t* res_empty, uint8_t* res_ring) {
+  const uint32_t D = static_cast<uint32_t>(p.n_res_slots);
+  const uint32_t dg[2] = {(D + 1u) >> 1, D >> 1}, base[2] = {0u, (D + 1u) >> 1};
+  const uint32_t tx = static_cast<uint32_t>(p.rows_per_tile) * 128u;
+  uint32_t pos[2] = {0u, 0u};  // entries issued into each group's ring
+  uint32_t pc = 0;
+  for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+    const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
+    const int np = (wide_chunks<BN, CG>(p, tc.n0) + 1) >> 1;
+    for (int q = 0; q < np; ++q) {
+      const uint32_t g = (pc + static_cast<uint32_t>(q)) & 1u;
+      for (int i = 0; i < p.n_res; ++i) {
+        const uint32_t slot = base[g] + pos[g] % dg[g];
+        mbar_wait(&res_empty[slot], ((pos[g] / dg[g]) & 1u) ^ 1u);  // fresh barriers count as released
+        mbar_arrive_expect_tx(&res_full[slot], tx);
+        tma_load_4d(res_ring + slot * 16384u, i ? &p.tmR1 : &p.tmR0, &res_full[slot], tc.n0 + q * 64, tc.o1, tc.o2,
+                    tc.o3);
+        ++pos[g];
+      }
+    }
+    pc += static_cast<uint32_t>(np);
+  }
+}
+
+template <int BN, int CG>
+__device__ __forceinline__ void epilogue_warp_tma_wide(const GemmKParams& p, int warp, int lane, int rank, int tile0,
+                                                       int tile_step, uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                                       uint64_t* tmem_empty_bar, uint64_t* res_full,
+                                                       uint64_t* res_empty, uint8_t* res_ring, uint8_t* out_ring) {
+  const int ew = warp - 4;
+  const uint32_t g = static_cast<uint32_t>(ew) >> 2;
+  const int qd = warp & 3;
+  const int r0 = qd * 32;
+  const bool has_rows = r0 < p.rows_per_tile;
+  const int q1 = r0 % p.box[0], q2 = (r0 / p.box[0]) % p.box[1], q3 = r0 / (p.box[0] * p.box[1]);
+  const int r = r0 + lane;
+  const int r1 = r % p.box[0], r2 = (r / p.box[0]) % p.box[1], r3 = r / (p.box[0] * p.box[1]);
+  const uint32_t stage = smem_u32(out_ring) + static_cast<uint32_t>(ew) * 4096u;  // 32 rows x 128 B, one slot
+  const uint32_t my_row = stage + static_cast<uint32_t>(lane) * 128u;
+  const uint32_t res_row = static_cast<uint32_t>(r) * 128u;                          // this row inside a residual slot
+  const uint32_t swz = static_cast<uint32_t>(lane & 7);                              // r & 7 == lane & 7
+  const uint32_t D = static_cast<uint32_t>(p.n_res_slots);
+  const uint32_t nres = static_cast<uint32_t>(p.n_res);
+  const uint32_t ring_d = g ? (D >> 1) : ((D + 1u) >> 1), ring_base = g ? ((D + 1u) >> 1) : 0u;  // this group's ring
+  uint32_t rpos = 0;  // residual entries this group has consumed
+  auto release_acc = [](uint64_t* bar) {
+    if constexpr (CG == 2) mbar_arrive_pair_leader(bar); else mbar_arrive(bar);
+  };
+  uint32_t pc = 0, t = 0;  // pc = panels of all earlier tiles (panel parity -> group)
+  for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
+    const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
+    const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
+    const int chunks = wide_chunks<BN, CG>(p, tc.n0);
+    const int n_panels = (chunks + 1) >> 1;
+    const float* addp = nullptr;
+    if (p.add_ptr != nullptr) {
+      const int a1 = tc.o1 + r1, a2 = tc.o2 + r2, a3 = tc.o3 + r3;
+      const bool valid = (r < p.rows_per_tile) && (a1 < p.out_dims[0]) && (a2 < p.out_dims[1]) && (a3 < p.out_dims[2]);
+      const int64_t row = valid ? (static_cast<int64_t>(a3) * p.out_dims[1] + a2) * p.out_dims[0] + a1 : 0;
+      addp = p.add_ptr + (row / p.add_div) * p.add_ld;
+    }
+    int q_last = n_panels - 1;
+    if (((pc + q_last) & 1u) != g) --q_last;
+    mbar_wait(&tmem_full_bar[acc], acc_ph);
+    tc_fence_after();
+    ASVA_TR(p, warp, 3 + 20 * t);
+    int trp = 0;
+    if (q_last < 0 || !has_rows) {  // nothing of this tile is ours: hand the accumulator back right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) release_acc(&tmem_empty_bar[acc]);
+      pc += n_panels;
+      continue;
+    }
+    const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(r0) << 16);
+#pragma unroll 1
+    for (int q = 0; q < n_panels; ++q) {
+      if (((pc + q) & 1u) != g) continue;
+      const bool two = (2 * q + 1) < chunks;  // the panel has its second 32-column half
+      const int acol = tc.n0 + q * 64;
+      uint32_t v0[32], v1[32];
+      tmem_ld_x32(taddr + q * 64, v0);
+      if (two) tmem_ld_x32(taddr + q * 64 + 32, v1);
+      // bias (+ per-row addend) of one 32-column half at a time: the first half's loads fly under the TMEM load, the
+      // second half's under the first half's arithmetic - both halves at once would not fit the register file
+      float4 b[8];
+      auto load_bias = [&](int col0, bool on) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (on && p.bias != nullptr && col0 + j * 4 < p.N) b[j] = ldg4(p.bias + col0 + j * 4);
+        }
+        if (on && addp != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (col0 + j * 4 < p.N) {
+              const float4 a = ldg4(addp + col0 + j * 4);
+              b[j].x += a.x; b[j].y += a.y; b[j].z += a.z; b[j].w += a.w;
+            }
+          }
+        }
+      };
+      load_bias(acol, true);
+      tmem_ld_wait();
+      if (q == q_last) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release_acc(&tmem_empty_bar[acc]);
+      }
+      ASVA_TR(p, warp, 4 + 20 * t + 6 * trp);
+      // accumulator + bias (+ row addend) in fp32, in place
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v0[4 * j + 0] = __float_as_uint(__uint_as_float(v0[4 * j + 0]) + b[j].x);
+        v0[4 * j + 1] = __float_as_uint(__uint_as_float(v0[4 * j + 1]) + b[j].y);
+        v0[4 * j + 2] = __float_as_uint(__uint_as_float(v0[4 * j + 2]) + b[j].z);
+        v0[4 * j + 3] = __float_as_uint(__uint_as_float(v0[4 * j + 3]) + b[j].w);
+      }
+      if (two) {
+        load_bias(acol + 32, true);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v1[4 * j + 0] = __float_as_uint(__uint_as_float(v1[4 * j + 0]) + b[j].x);
+          v1[4 * j + 1] = __float_as_uint(__uint_as_float(v1[4 * j + 1]) + b[j].y);
+          v1[4 * j + 2] = __float_as_uint(__uint_as_float(v1[4 * j + 2]) + b[j].z);
+          v1[4 * j + 3] = __float_as_uint(__uint_as_float(v1[4 * j + 3]) + b[j].w);
+        }
+      }
+      ASVA_TR(p, warp, 5 + 20 * t + 6 * trp);
+      // residual panels: added in fp32 (the stored value is rounded to bf16 exactly once)
+      for (uint32_t i = 0; i < nres; ++i) {
+        const uint32_t slot = ring_base + rpos % ring_d, ph = (rpos / ring_d) & 1u;
+        ++rpos;
+        mbar_wait(&res_full[slot], ph);
+        const uint32_t rp = smem_u32(res_ring) + slot * 16384u + res_row;
+        auto add_half = [&](uint32_t (&v)[32], int c0) {  // 32 columns = 4 chunks of 8 bf16
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(rp + ((static_cast<uint32_t>(c0 + c) ^ swz) << 4))
+                         : "memory");
+            v[8 * c + 0] = __float_as_uint(__uint_as_float(v[8 * c + 0]) + __uint_as_float(w0 << 16));
+            v[8 * c + 1] = __float_as_uint(__uint_as_float(v[8 * c + 1]) + __uint_as_float(w0 & 0xffff0000u));
+            v[8 * c + 2] = __float_as_uint(__uint_as_float(v[8 * c + 2]) + __uint_as_float(w1 << 16));
+            v[8 * c + 3] = __float_as_uint(__uint_as_float(v[8 * c + 3]) + __uint_as_float(w1 & 0xffff0000u));
+            v[8 * c + 4] = __float_as_uint(__uint_as_float(v[8 * c + 4]) + __uint_as_float(w2 << 16));
+            v[8 * c + 5] = __float_as_uint(__uint_as_float(v[8 * c + 5]) + __uint_as_float(w2 & 0xffff0000u));
+            v[8 * c + 6] = __float_as_uint(__uint_as_float(v[8 * c + 6]) + __uint_as_float(w3 << 16));
+            v[8 * c + 7] = __float_as_uint(__uint_as_float(v[8 * c + 7]) + __uint_as_float(w3 & 0xffff0000u));
+          }
+        };
+        add_half(v0, 0);
+        if (two) add_half(v1, 4);
+        __syncwarp();  // every lane of this warp has read its rows of the slot
+        if (lane == 0) mbar_arrive(&res_empty[slot]);
+      }
+      uint32_t pk[32];  // the row's 64 bf16 outputs, packed
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[16 + j] = pack_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+      }
+      ASVA_TR(p, warp, 6 + 20 * t + 6 * trp);
+      if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging slot
+      __syncwarp();
+      ASVA_TR(p, warp, 7 + 20 * t + 6 * trp);
+      if (two) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(my_row + ((static_cast<uint32_t>(c) ^ swz) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      } else {
+        // 32-column tail panel: rows of 64 B under the 64B swizzle of its own tensor map (tmO2)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t lin = static_cast<uint32_t>(lane) * 64u + static_cast<uint32_t>(c) * 16u;
+          st_shared_v4(stage + (lin ^ (((lin >> 7) & 3u) << 4)), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+      }
+      ASVA_TR(p, warp, 8 + 20 * t + 6 * trp);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(two ? &p.tmO : &p.tmO2)), "r"(stage), "r"(acol), "r"(tc.o1 + q1),
+                     "r"(tc.o2 + q2), "r"(tc.o3 + q3), "r"(tc.split)
+                     : "memory");
+        bulk_commit();
+      }
+      ASVA_TR(p, warp, 9 + 20 * t + 6 * trp);
+      ++trp;
+    }
+    pc += n_panels;
+  }
+  if (lane == 0) bulk_wait_read<0>();
+  ASVA_TR(p, warp, 63);
+}
+
+// Narrow form of the warp-private TMA epilogue (GEGLU and fp32 outputs: 32-column panels).
+// (original text) The panel epilogue above moves a 128-row x 32-column panel per GROUP of four
+// warps: two named barriers and one elected thread's TMA store per panel, one lane feeding the group's residual ring -
+// two serial latency chains per CTA, which is what bounds every short-K launch. Here each of the
+// eight epilogue warps owns the 32 rows of its TMEM lane quadrant outright: its own staging slots, its own residual
+// ring and mbarriers, its own TMA loads and stores through tensor maps whose row box is the quadrant's 32-row slice of
+// the tile (host: sub-box feasibility). No block-level barrier is left in the epilogue - eight independent chains per
+// CTA keep the TMA / TMEM / L2 latencies of one panel under the work of the others.
+template <int BN, bool GEGLU, int CG>
+__device__ __forceinline__ void epilogue_warp_tma_narrow(const GemmKParams& p, int warp, int lane, int rank, int tile0,
+                                                  int tile_step, uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                                  uint64_t* tmem_empty_bar, uint64_t* res_full_bar, uint8_t* res_ring,
+                                                  uint8_t* out_ring) {
+  const int ew = warp - 4;
+  const uint32_t g = static_cast<uint32_t>(ew) >> 2;
+  const int qd = warp & 3;
+  const int r0 = qd * 32;                       // first tile row of this warp's slice
+  const bool has_rows = r0 < p.rows_per_tile;   // short tiles: the upper quadrants hold no rows
+  const int q1 = r0 % p.box[0], q2 = (r0 / p.box[0]) % p.box[1], q3 = r0 / (p.box[0] * p.box[1]);
+  const int r = r0 + lane;                      // this thread's row in the tile (== its TMEM lane)
+  const int r1 = r % p.box[0], r2 = (r / p.box[0]) % p.box[1], r3 = r / (p.box[0] * p.box[1]);
+  const uint32_t slot_bytes = p.out_fp32 ? 4096u : 2048u;  // 32 rows x 32 columns
+  uint8_t* my_out = out_ring + static_cast<uint32_t>(ew) * 2u * slot_bytes;
+  const uint32_t D = static_cast<uint32_t>(p.n_res_slots);
+  uint8_t* my_res = res_ring + static_cast<uint32_t>(ew) * D * 2048u;
+  uint64_t* my_bar = res_full_bar + ew * kMaxResSlots;
+  auto release_acc = [](uint64_t* bar) {
+    if constexpr (CG == 2) mbar_arrive_pair_leader(bar); else mbar_arrive(bar);
+  };
+  // residual prefetch, D panels ahead of the warp's own position (across tile boundaries); lane 0 issues
+  const bool pf_lane = has_rows && (lane == 0) && (p.n_res > 0);
+  uint32_t rslot = 0, rph = 0;
+  int pf_tile = tile0, pf_q = 0, pf_i = 0;
+  uint32_t pf_pc = 0, pf_slot = 0;
+  TileCoord pf_tc = decode_tile<BN, CG>(p, tile0 < p.total_tiles ? tile0 : 0, rank);
+  int pf_np = tile_panels<BN, GEGLU>(p, pf_tc.n0);
+  auto pf_issue = [&]() {
+    while (pf_tile < p.total_tiles) {
+      while (pf_q < pf_np && (((pf_pc + pf_q) & 1u) != g)) ++pf_q;
+      if (pf_q < pf_np) break;
+      pf_pc += pf_np;
+      pf_tile += tile_step;
+      pf_q = 0;
+      if (pf_tile < p.total_tiles) {
+        pf_tc = decode_tile<BN, CG>(p, pf_tile, rank);
+        pf_np = tile_panels<BN, GEGLU>(p, pf_tc.n0);
+      }
+    }
+    if (pf_tile >= p.total_tiles) return;
+    mbar_arrive_expect_tx(&my_bar[pf_slot], static_cast<uint32_t>(p.sub_rows) * 64u);
+    tma_load_4d(my_res + pf_slot * 2048u, pf_i ? &p.tmR1 : &p.tmR0, &my_bar[pf_slot], pf_tc.n0 + pf_q * 32,
+                pf_tc.o1 + q1, pf_tc.o2 + q2, pf_tc.o3 + q3);
+    if (++pf_slot == D) pf_slot = 0;
+    if (++pf_i == p.n_res) {
+      pf_i = 0;
+      ++pf_q;
+    }
+  };
+  if (pf_lane)
+    for (uint32_t i = 0; i < D; ++i) pf_issue();
+  uint32_t pc = 0, ocnt = 0, t = 0;
+  for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
+    const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
+    const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
+    const int n_panels = tile_panels<BN, GEGLU>(p, tc.n0);
+    const int n0_out = GEGLU ? (tc.n0 >> 1) : tc.n0;
+    const float* addp = nullptr;
+    if (p.add_ptr != nullptr) {
+      const int a1 = tc.o1 + r1, a2 = tc.o2 + r2, a3 = tc.o3 + r3;
+      const bool valid = (r < p.rows_per_tile) && (a1 < p.out_dims[0]) && (a2 < p.out_dims[1]) && (a3 < p.out_dims[2]);
+      const int64_t row = valid ? (static_cast<int64_t>(a3) * p.out_dims[1] + a2) * p.out_dims[0] + a1 : 0;
+      addp = p.add_ptr + (row / p.add_div) * p.add_ld;
+    }
+    int q_last = n_panels - 1;
+    if (((pc + q_last) & 1u) != g) --q_last;
+    mbar_wait(&tmem_full_bar[acc], acc_ph);
+    tc_fence_after();
+    ASVA_TR(p, warp, 3 + 20 * t);
+    int trp = 0;
+    if (q_last < 0 || !has_rows) {  // nothing of this tile is ours: hand the accumulator back right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) release_acc(&tmem_empty_bar[acc]);
+      pc += n_panels;
+      continue;
+    }
+    const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(r0) << 16);
+#pragma unroll 1
+    for (int q = 0; q < n_panels; ++q) {
+      if (((pc + q) & 1u) != g) continue;
+      uint32_t v[32];
+      if constexpr (!GEGLU) {
+        tmem_ld_x32(taddr + q * 32, v);
+        tmem_ld_wait();
+        ASVA_TR(p, warp, 4 + 20 * t + 6 * trp);
+        if (q == q_last) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc(&tmem_empty_bar[acc]);
+        }
+        const int acol = tc.n0 + q * 32;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (acol + j * 4 < p.N) {
+              const float4 b = ldg4(p.bias + acol + j * 4);
+              v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+            }
+          }
+        }
+        if (addp != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (acol + j * 4 < p.N) {
+              const float4 b = ldg4(addp + acol + j * 4);
+              v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+            }
+          }
+        }
+        ASVA_TR(p, warp, 5 + 20 * t + 6 * trp);
+        for (int i = 0; i < p.n_res; ++i) {
+          mbar_wait(&my_bar[rslot], rph);
+          const uint8_t* rp = my_res + rslot * 2048u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t lin = static_cast<uint32_t>(lane) * 64u + j * 16u;
+            const uint4 w = *reinterpret_cast<const uint4*>(rp + (lin ^ (((lin >> 7) & 3u) << 4)));
+            const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z),
+                         f3 = unpack_bf16x2(w.w);
+            v[8 * j + 0] = __float_as_uint(__uint_as_float(v[8 * j + 0]) + f0.x);
+            v[8 * j + 1] = __float_as_uint(__uint_as_float(v[8 * j + 1]) + f0.y);
+            v[8 * j + 2] = __float_as_uint(__uint_as_float(v[8 * j + 2]) + f1.x);
+            v[8 * j + 3] = __float_as_uint(__uint_as_float(v[8 * j + 3]) + f1.y);
+            v[8 * j + 4] = __float_as_uint(__uint_as_float(v[8 * j + 4]) + f2.x);
+            v[8 * j + 5] = __float_as_uint(__uint_as_float(v[8 * j + 5]) + f2.y);
+            v[8 * j + 6] = __float_as_uint(__uint_as_float(v[8 * j + 6]) + f3.x);
+            v[8 * j + 7] = __float_as_uint(__uint_as_float(v[8 * j + 7]) + f3.y);
+          }
+          if (++rslot == D) {
+            rslot = 0;
+            rph ^= 1u;
+          }
+        }
+      } else {
+        // tile columns [0,64) = value h, [64,128) = gate g; output = (h + bh) * gelu(g + bg)
+        uint32_t gv[32];
+        tmem_ld_x32(taddr + q * 32, v);
+        tmem_ld_x32(taddr + 64 + q * 32, gv);
+        tmem_ld_wait();
+        if (q == q_last) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc(&tmem_empty_bar[acc]);
+        }
+        const int acol = tc.n0 + q * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+          if (p.bias != nullptr) {
+            bh = ldg4(p.bias + acol + j * 4);
+            bg = ldg4(p.bias + acol + 64 + j * 4);
+          }
+          v[4 * j + 0] = __float_as_uint((__uint_as_float(v[4 * j + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gv[4 * j + 0]) + bg.x));
+          v[4 * j + 1] = __float_as_uint((__uint_as_float(v[4 * j + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gv[4 * j + 1]) + bg.y));
+          v[4 * j + 2] = __float_as_uint((__uint_as_float(v[4 * j + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gv[4 * j + 2]) + bg.z));
+          v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gv[4 * j + 3]) + bg.w));
+        }
+      }
+      ASVA_TR(p, warp, 6 + 20 * t + 6 * trp);
+      // every lane is past its reads of this panel's residual slots (and of the staging slot's previous content)
+      uint8_t* op = my_out + (ocnt & 1u) * slot_bytes;
+      if (lane == 0) bulk_wait_read<1>();  // the store that last used this staging slot has finished reading it
+      __syncwarp();
+      ASVA_TR(p, warp, 7 + 20 * t + 6 * trp);
+      if (pf_lane)
+        for (int i = 0; i < p.n_res; ++i) pf_issue();
+      if (!p.out_fp32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+          w.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+          w.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+          w.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+          const uint32_t lin = static_cast<uint32_t>(lane) * 64u + j * 16u;
+          *reinterpret_cast<uint4*>(op + (lin ^ (((lin >> 7) & 3u) << 4))) = w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t lin = static_cast<uint32_t>(lane) * 128u + j * 16u;
+          *reinterpret_cast<uint4*>(op + (lin ^ (((lin >> 7) & 7u) << 4))) =
+              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      ASVA_TR(p, warp, 8 + 20 * t + 6 * trp);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_5d(&p.tmO, op, n0_out + q * 32, tc.o1 + q1, tc.o2 + q2, tc.o3 + q3, tc.split);
+        bulk_commit();
+      }
+      ASVA_TR(p, warp, 9 + 20 * t + 6 * trp);
+      ++trp;
+      ++ocnt;
+    }
+    pc += n_panels;
+  }
+  if (lane == 0) bulk_wait_read<0>();
+  ASVA_TR(p, warp, 63);
+}
+
 template <int BN, bool GEGLU, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
   constexpr int kABytes = 128 * 128;
@@ -262,12 +721,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2 groups][kMaxResSlots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 2 * kMaxResSlots);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2 groups][kMaxResSlots] (epi 1) / [8 warps][kMaxResSlots] (epi 3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 8 * kMaxResSlots);
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  ASVA_TR(p, warp, 0);
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
@@ -280,7 +740,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 8 * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
-    for (int s = 0; s < 2 * kMaxResSlots; ++s) mbar_init(&res_full_bar[s], 1);
+    // epi 3 (wide): [0..3] = residual slot full, [8..11] = slot released by every quadrant warp that holds rows
+    const int nq = (p.rows_per_tile + 31) / 32;
+    for (int s = 0; s < 8 * kMaxResSlots; ++s)
+      mbar_init(&res_full_bar[s], (p.epi == 3 && s >= 8 && s < 12) ? static_cast<uint32_t>(nq < 4 ? nq : 4) : 1u);
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmW);
@@ -312,7 +775,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       tma_prefetch_l2_2d(&p.tmW, kbx * 64, rbx * (BN / CG));
     }
   }
+  ASVA_TR(p, warp, 1);
   pdl_wait();  // everything above overlapped the previous kernel's tail; its results are read from here on
+  ASVA_TR(p, warp, 2);
 
   // The producer and MMA loops run in one thread each and are paced by their own instruction and mbarrier latency,
   // so they are written for a minimal dependent-instruction count: ring position kept as (stage, phase) counters,
@@ -481,10 +946,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const TileCoord tc = decode_tile<BN, CG>(p, tile, 0);
         const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
+        ASVA_TR(p, warp, 4 + 3 * t);
         const uint32_t tmem_d = tmem_u + acc * BN;
         uint32_t accumulate = 0;
         for (int n = tc.kb1 - tc.kb0; n > 0; n -= 2) {
           if (!ready) mbar_wait_a(full0 + 8u * s, ph);
+          if (n == tc.kb1 - tc.kb0) ASVA_TR(p, warp, 5 + 3 * t);
           uint32_t s2 = s + 1, ph2 = ph;
           if (s2 == n_st) {
             s2 = 0;
@@ -532,11 +999,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         } else {
           tc_commit_p(el, tfull0 + 8u * acc);
         }
+        ASVA_TR(p, warp, 6 + 3 * t);
       }
     }
     __syncwarp();
   } else if (warp >= 4 && !GEGLU && p.epi == 2) {
     epilogue_direct<BN, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar, tmem_empty_bar, out_ring);
+  } else if (warp == 2) {
+    if constexpr (!GEGLU) {
+      if (p.epi == 3 && !p.out_fp32 && p.n_res > 0 && lane == 0)
+        residual_issuer_wide<BN, CG>(p, rank, tile0, tile_step, res_full_bar, res_full_bar + 8, res_ring);
+    }
+    __syncwarp();
+  } else if (warp >= 4 && p.epi == 3) {
+    if constexpr (!GEGLU) {
+      if (!p.out_fp32)
+        epilogue_warp_tma_wide<BN, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar, tmem_empty_bar,
+                                       res_full_bar, res_full_bar + 8, res_ring, out_ring);
+      else
+        epilogue_warp_tma_narrow<BN, GEGLU, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar,
+                                                tmem_empty_bar, res_full_bar, res_ring, out_ring);
+    } else {
+      epilogue_warp_tma_narrow<BN, GEGLU, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar,
+                                              tmem_empty_bar, res_full_bar, res_ring, out_ring);
+    }
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const uint32_t g = static_cast<uint32_t>(warp - 4) >> 2;
@@ -851,6 +1337,33 @@ static double plan_cost(int bn, int cg, int split, int N, int64_t m_tiles, int n
   return cost;
 }
 
+// Warp-private TMA epilogue: the 32 tile rows of TMEM lane quadrant q (linear tile rows 32q .. 32q+31, first box
+// dimension fastest) must themselves be a (d1, d2, d3) box. Returns false when the tile's row box does not split so.
+static bool sub_box(const asva_gemm_desc* d, int sub[3]) {
+  const int b1 = d->box[0], b2 = d->box[1], b3 = d->box[2];
+  const int rows = b1 * b2 * b3;
+  if (rows <= 32) {
+    sub[0] = b1; sub[1] = b2; sub[2] = b3;
+    return true;
+  }
+  if (b1 >= 32) {
+    // a single line of rows may be ragged: the rows past it lie past the tensor and the TMA clips them
+    const bool one_line = (b2 == 1 && b3 == 1 && b1 >= d->out_dims[0]);
+    if (b1 % 32 != 0 && !one_line) return false;
+    sub[0] = 32; sub[1] = 1; sub[2] = 1;
+    return true;
+  }
+  if (32 % b1 != 0 || rows % 32 != 0) return false;
+  if (b1 * b2 >= 32) {
+    if ((b1 * b2) % 32 != 0) return false;
+    sub[0] = b1; sub[1] = 32 / b1; sub[2] = 1;
+    return true;
+  }
+  if (32 % (b1 * b2) != 0) return false;
+  sub[0] = b1; sub[1] = b2; sub[2] = 32 / (b1 * b2);
+  return true;
+}
+
 static int env_int(const char* name) {
 #ifdef ASVA_DEBUG_SWITCHES
   const char* e = getenv(name);
@@ -872,9 +1385,13 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
   GemmPlan best{128, 1, 2, 1, 1};
   // epilogue form: the per-warp one exists for bf16, non-GEGLU, non-split outputs; explicit request > env > default
   // default (measured, profiles/r1_gemm_probe_v9.md): the per-warp form wins whenever there is a residual to add
+  // 3 (warp-private TMA) serves every output type but needs a tile whose quadrants are boxes (sub_box)
+  int sub[3];
+  const bool sub_ok = sub_box(d, sub);
   int want_epi = d->epilogue ? d->epilogue : (env_epi ? env_epi : (n_res > 0 ? 2 : kDefaultEpi));
-  if (d->geglu || d->out_fp32) want_epi = 1;
-  if (want_epi != 2) want_epi = 1;
+  if (want_epi == 2 && (d->geglu || d->out_fp32)) want_epi = 1;
+  if (want_epi == 3 && (!sub_ok || (n_res > 0 && d->out_fp32))) want_epi = 1;
+  if (want_epi != 2 && want_epi != 3) want_epi = 1;
   const int bns[4] = {64, 128, 160, 256};
   const int splits[10] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
   const int want_bn = d->geglu ? 128 : (d->block_n ? d->block_n : env_bn);
@@ -910,7 +1427,7 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
       }
     }
   }
-  best.epi = best.split > 1 ? 1 : want_epi;
+  best.epi = best.split > 1 ? (want_epi == 3 ? 3 : 1) : want_epi;
   const int nr = (best.split > 1 || best.epi == 2) ? 0 : n_res;
   best.stages = stages_for(best.bn, best.cg, nr, best.split > 1 ? 1 : d->out_fp32, (num_kb + best.split - 1) / best.split);
   const int cap = env_int("ASVA_GEMM_STAGES");
@@ -1018,8 +1535,8 @@ extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, in
   const int splits[6] = {1, 2, 3, 4, 6, 8};
   float best = 1e30f;
   int rc = 0, bb = 0, bs = 0, bc = 0, be = 0;
-  for (int ce = 0; ce < 2 * 2 && rc == 0; ++ce) {
-    const int cg = 1 + (ce >> 1), epi = 1 + (ce & 1);
+  for (int ce = 0; ce < 2 * 3 && rc == 0; ++ce) {
+    const int cg = 1 + ce / 3, epi = 1 + ce % 3;
     for (int bi = 0; bi < 4 && rc == 0; ++bi) {
       for (int si = 0; si < 6 && rc == 0; ++si) {
         asva_gemm_desc c = *d;
@@ -1031,6 +1548,12 @@ extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, in
         GemmPlan pl;
         if (compute_plan(&c, &pl) != 0) continue;
         if (pl.bn != c.block_n || pl.split != c.split_k || pl.cg != c.cta_group || pl.epi != epi) continue;  // not feasible
+#ifdef ASVA_DEBUG_SWITCHES
+        if (getenv("ASVA_TUNE_LOG")) {
+          printf("[tune] cg=%d bn=%d split=%d epi=%d stages=%d\n", cg, c.block_n, c.split_k, epi, pl.stages);
+          fflush(stdout);
+        }
+#endif
         if ((rc = asva_gemm(&c, stream_)) != 0) break;  // warm-up (also first-use kernel attribute setup)
         cudaEventRecord(e0, stream);
         for (int r = 0; r < reps && rc == 0; ++r) rc = asva_gemm(&c, stream_);
@@ -1203,7 +1726,16 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
     if (rc != 0) return rc;
   }
   // output (or split-K scratch) and residuals: (cols, d1, d2, d3[, split]) boxes of 32 columns x the row box
-  const uint32_t rbox[5] = {32u, (uint32_t)d->box[0], (uint32_t)d->box[1], (uint32_t)d->box[2], 1u};
+  uint32_t rbox[5] = {32u, (uint32_t)d->box[0], (uint32_t)d->box[1], (uint32_t)d->box[2], 1u};
+  uint32_t obox[5] = {32u, (uint32_t)d->box[0], (uint32_t)d->box[1], (uint32_t)d->box[2], 1u};
+  kp.sub_rows = rows < 32 ? rows : 32;
+  const bool wide = plan.epi == 3 && !kp.out_fp32 && !d->geglu;  // bf16 panels of 64 columns
+  if (plan.epi == 3) {  // every epilogue warp stores its own quadrant of a panel
+    int sub[3];
+    ASVA_REQUIRE(sub_box(d, sub), "asva_gemm: epilogue 3 needs a tile whose 32-row quadrants are boxes");
+    for (int i = 0; i < 3; ++i) obox[i + 1] = (uint32_t)sub[i];
+    if (wide) obox[0] = rbox[0] = 64u;  // residual panels keep the whole-tile row box (one load per panel)
+  }
   const uint32_t rel[5] = {1u, 1u, 1u, 1u, 1u};
   {
     const bool f32 = kp.out_fp32 != 0;
@@ -1214,20 +1746,40 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
                         (uint64_t)d->out_dims[2], (uint64_t)plan.split};
     uint64_t strides[4] = {ld * es, ld * es * dims[1], ld * es * dims[1] * dims[2],
                            ld * es * dims[1] * dims[2] * dims[3]};
-    int rc = make_tmap(&kp.tmO, base, f32 ? TMAP_F32 : TMAP_BF16, f32 ? TMAP_SW128 : TMAP_SW64, 5, dims, strides,
-                       rbox, rel);
+    int rc = make_tmap(&kp.tmO, base, f32 ? TMAP_F32 : TMAP_BF16, (f32 || wide) ? TMAP_SW128 : TMAP_SW64, 5, dims,
+                       strides, obox, rel);
     if (rc != 0) return rc;
+    kp.tmO2 = kp.tmO;
+    if (wide) {
+      obox[0] = 32u;
+      rc = make_tmap(&kp.tmO2, base, TMAP_BF16, TMAP_SW64, 5, dims, strides, obox, rel);
+      if (rc != 0) return rc;
+    }
   }
   for (int i = 0; i < (direct ? 0 : kp.n_res); ++i) {
     uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->out_dims[0], (uint64_t)d->out_dims[1], (uint64_t)d->out_dims[2]};
     const uint64_t ld = (uint64_t)res_ld[i] * 2u;
     uint64_t strides[3] = {ld, ld * dims[1], ld * dims[1] * dims[2]};
-    int rc = make_tmap(i == 0 ? &kp.tmR0 : &kp.tmR1, res[i], TMAP_BF16, TMAP_SW64, 4, dims, strides, rbox, rel);
+    int rc = make_tmap(i == 0 ? &kp.tmR0 : &kp.tmR1, res[i], TMAP_BF16, wide ? TMAP_SW128 : TMAP_SW64, 4, dims, strides,
+                       rbox, rel);
     if (rc != 0) return rc;
   }
   if (kp.n_res < 2) kp.tmR1 = kp.tmR0;
   if (kp.n_res < 1 || direct) kp.tmR0 = kp.tmR1 = kp.tmO;
 
+#ifdef ASVA_DEBUG_SWITCHES
+  static long long* trace_buf = nullptr;
+  static int trace_on = -1;
+  if (trace_on < 0) {
+    const char* e = getenv("ASVA_GEMM_TRACE");
+    trace_on = (e != nullptr && e[0] == '1') ? 1 : 0;
+    if (trace_on) cudaMalloc(&trace_buf, 12 * 64 * sizeof(long long));
+  }
+  if (trace_on) {
+    cudaMemsetAsync(trace_buf, 0, 12 * 64 * sizeof(long long), stream);
+    kp.trace = trace_buf;
+  }
+#endif
   kp.n_tiles_n = (d->N + bn - 1) / bn;
   ASVA_REQUIRE(m_tiles * kp.n_tiles_n * plan.split < (1ll << 31), "asva_gemm: too many tiles");
   kp.mn_tiles = (int)(((m_tiles + plan.cg - 1) / plan.cg) * kp.n_tiles_n);  // pairs of m tiles when cg == 2
@@ -1235,6 +1787,24 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   const int smem = smem_for(bn, plan.cg, plan.stages, kp.n_res_slots, kp.out_fp32);
   const int rc = plan.cg == 2 ? dispatch_gemm<2>(kp, bn, d->geglu != 0, smem, stream)
                               : dispatch_gemm<1>(kp, bn, d->geglu != 0, smem, stream);
+#ifdef ASVA_DEBUG_SWITCHES
+  if (trace_on && rc == 0) {
+    static long long h[12 * 64];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    long long t0 = 0;
+    for (int w = 0; w < 12; ++w)
+      if (h[w * 64] != 0 && (t0 == 0 || h[w * 64] < t0)) t0 = h[w * 64];
+    printf("[asva gemm trace] M tiles %lld N=%d K=%d bn=%d cg=%d epi=%d stages=%d (ns since CTA 0 entry)\n",
+           (long long)m_tiles, d->N, d->K, bn, plan.cg, plan.epi, plan.stages);
+    for (int w = 0; w < 12; ++w) {
+      printf("  warp %2d:", w);
+      for (int e = 0; e < 64; ++e)
+        if (h[w * 64 + e] != 0) printf(" e%d=%lld", e, h[w * 64 + e] - t0);
+      printf("\n");
+    }
+  }
+#endif
   if (rc != 0 || !split) return rc;
   const int64_t chunks = M * (d->N / 8);
   int64_t blocks = (chunks + 255) / 256;

@@ -307,7 +307,7 @@ class CudaBackend:
             if plan is None and self.tuning:
                 d = self._gemm_desc(s)
                 bn, sp, cg, ep, us = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_float(0.0)
-                _lib.check(self.lib.asva_gemm_tune(d, self._stream(), 3, C.byref(bn), C.byref(sp), C.byref(cg),
+                _lib.check(self.lib.asva_gemm_tune(d, self._stream(), 8, C.byref(bn), C.byref(sp), C.byref(cg),
                                                    C.byref(ep), C.byref(us)), "asva_gemm_tune")
                 plan = (bn.value, sp.value, cg.value, ep.value)
                 self.plan_cache[sig] = plan

@@ -93,7 +93,10 @@ typedef struct asva_gemm_desc {
   int64_t ws_bytes;
   int32_t epilogue; /* 0 = auto; 1 = panel epilogue (residual panels arrive by TMA, output leaves by TMA store);
                        2 = per-warp epilogue (each warp finishes its own 32 x 32 sub-panels: direct residual loads
-                       and 16-byte stores; bf16, non-GEGLU, non-split outputs only - otherwise 1 is used) */
+                       and 16-byte stores; bf16, non-GEGLU, non-split outputs only - otherwise 1 is used);
+                       3 = warp-private TMA epilogue (each of the eight epilogue warps moves the 32 rows of its TMEM
+                       quadrant with its own TMA loads / stores, no block-level barrier; any output type; needs a
+                       row box whose 32-row quadrants are themselves boxes - otherwise 1 is used) */
   int32_t reserved;
 } asva_gemm_desc;
 

@@ -50,7 +50,7 @@ def _run_gemm_pair(be, spec, out_shape, out_dtype, fill=0.0):
     (256, 768, 640, 64), (256, 768, 640, 128), (200, 1280, 2560, 0), (24576, 320, 320, 0), (77, 768, 2560, 0),
     (16, 1280, 1280, 0),
 ])
-@pytest.mark.parametrize("epi", [1, 2])
+@pytest.mark.parametrize("epi", [1, 2, 3])
 def test_gemm_linear(cuda_backend, M, K, N, bn, epi):
     x = _rand((M, K), 1)
     w = _rand((N, K), 2, 1.0 / math.sqrt(K))
@@ -97,11 +97,14 @@ def test_gemm_two_sources(cuda_backend):
 
 
 @pytest.mark.parametrize("M,C", [(256, 320), (384, 640), (200, 1280)])
-def test_gemm_geglu(cuda_backend, M, C):
+@pytest.mark.parametrize("epi", [1, 3])
+def test_gemm_geglu(cuda_backend, M, C, epi):
     x = _rand((M, C), 10)
     w = _rand((8 * C, C), 11, 1.0 / math.sqrt(C))
     bias = _rand((8 * C,), 12, dtype=torch.float32)
     spec = ops.spec_linear(x, w, torch.empty(M, 4 * C, dtype=torch.bfloat16, device=DEV), bias=bias, geglu=True)
+    spec.epilogue = epi
+    assert cuda_backend.gemm_plan(spec)[4] == epi
     got, ref = _run_gemm_pair(cuda_backend, spec, (M, 4 * C), torch.bfloat16)
     _report(f"geglu {M}x{C}", got, ref, 4e-3)
 
@@ -111,7 +114,7 @@ def test_gemm_geglu(cuda_backend, M, C):
     (2, 16, 32, 320, 640, 1), (3, 32, 32, 320, 320, 2), (4, 8, 8, 1280, 1280, 2), (2, 6, 10, 128, 64, 1),
     (2, 16, 16, 960, 320, 1),
 ])
-@pytest.mark.parametrize("epi", [1, 2])
+@pytest.mark.parametrize("epi", [1, 2, 3])
 def test_gemm_conv3x3(cuda_backend, n_img, h, w, Cin, Cout, stride, epi):
     x = _rand((n_img * h * w, Cin), 13)
     wt = _rand((Cout, 9 * Cin), 14, 1.0 / math.sqrt(9 * Cin))
@@ -131,7 +134,7 @@ def test_gemm_conv3x3(cuda_backend, n_img, h, w, Cin, Cout, stride, epi):
 
 @pytest.mark.parametrize("B,F,N,C", [(2, 12, 64, 320), (1, 8, 16, 1280), (2, 5, 100, 640), (2, 3, 256, 320),
                                      (3, 4, 16, 640)])
-@pytest.mark.parametrize("epi", [1, 2])
+@pytest.mark.parametrize("epi", [1, 2, 3])
 def test_gemm_tconv(cuda_backend, B, F, N, C, epi):
     y = _rand((B * F * N, C), 16)
     w3 = _rand((C, 3 * C), 17, 0.02)
@@ -155,19 +158,20 @@ def test_gemm_tconv(cuda_backend, B, F, N, C, epi):
 
 @pytest.mark.parametrize("M,K,N,split,bn", [(384, 11520, 1280, 5, 128), (1536, 5760, 1280, 2, 128), (384, 2560, 1280, 4, 64),
                                             (200, 1280, 640, 3, 0), (130, 640, 320, 2, 160), (384, 2304, 1280, 0, 0)])
-def test_gemm_split_k(cuda_backend, M, K, N, split, bn):
+@pytest.mark.parametrize("epi", [1, 3])
+def test_gemm_split_k(cuda_backend, M, K, N, split, bn, epi):
     x = _rand((M, K), 51)
     w = _rand((N, K), 52, 1.0 / math.sqrt(K))
     bias = _rand((N,), 53, dtype=torch.float32)
     res = _rand((M, N), 54)
     spec = ops.spec_linear(x, w, torch.empty(M, N, dtype=torch.bfloat16, device=DEV), bias=bias, res0=res)
-    spec.block_n, spec.split_k = bn, split
+    spec.block_n, spec.split_k, spec.epilogue = bn, split, epi
     got, ref = _run_gemm_pair(cuda_backend, spec, (M, N), torch.bfloat16)
-    _report(f"split-k {M}x{K}x{N} /{split}", got, ref, 4e-3)
+    _report(f"split-k {M}x{K}x{N} /{split} epi{epi}", got, ref, 4e-3)
 
 
 @pytest.mark.parametrize("bn", [64, 128, 160, 256])
-@pytest.mark.parametrize("epi", [1, 2])
+@pytest.mark.parametrize("epi", [1, 2, 3])
 def test_gemm_block_n_and_inplace_residual(cuda_backend, bn, epi):
     # every tile width, N not a multiple of it, two residuals one of which aliases the output (t = t + ...)
     M, K, N = 1000, 640, 960

@@ -129,7 +129,7 @@ def main():
                 for sp in ((1,) if spec.geglu else [int(x) for x in args.splits.split(",")]):
                     if bn > 64 and bn >= 2 * spec.N:
                         continue
-                    for epi in ((1,) if (spec.geglu or spec.out_fp32 or sp > 1) else (1, 2)):
+                    for epi in ((1, 3) if (spec.geglu or spec.out_fp32 or sp > 1) else (1, 2, 3)):
                         out = torch.zeros_like(spec.out)
                         s = dataclasses.replace(spec, out=out, block_n=bn, split_k=sp, cta_group=cg, epilogue=epi)
                         try:
@@ -144,10 +144,12 @@ def main():
         best = min(ok, key=lambda r: r[4])
         b1 = min((r for r in ok if r[3] == 1), key=lambda r: r[4])
         b2 = min((r for r in ok if r[3] == 2), key=lambda r: r[4], default=None)
+        b3 = min((r for r in ok if r[3] == 3), key=lambda r: r[4], default=None)
         lines.append(f"## {name}: M={spec.M} N={spec.N} K={spec.K} segs={len(spec.segs)} box={spec.box}  "
                      f"auto {auto:.1f} us; best cg={best[0]} bn={best[1]} split={best[2]} epi={best[3]} {best[4]:.1f} us "
                      f"({fl / best[4] / 1e6:.0f} TFLOP/s); best panel-epilogue {b1[4]:.1f} us, best per-warp "
-                     f"{'-' if b2 is None else format(b2[4], '.1f')} us")
+                     f"{'-' if b2 is None else format(b2[4], '.1f')} us, best warp-TMA "
+                     f"{'-' if b3 is None else format(b3[4], '.1f')} us")
         lines.append("| cg | bn | split | epi | us | TFLOP/s | rel-L2 vs sim |")
         lines.append("|---|---|---|---|---|---|---|")
         for cg, bn, sp, epi, us, err in rows:
