@@ -232,7 +232,70 @@ __global__ void __launch_bounds__(256) tconv_gather_kernel(const __nv_bfloat16* 
   *reinterpret_cast<uint4*>(out + row * 3 * C + part * C + c) = u;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row softmax for attention whose head dimension exceeds what attn_tc.cu tiles (the VAE's single 512-wide head):
+// scores come out of asva_gemm in fp32, probabilities go back into asva_gemm as bf16.  One CTA per row; the row is
+// read three times (max, sum, write) - it is a few KB and L2 resident.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int64_t lds,
+                                                           __nv_bfloat16* __restrict__ p, int64_t ldp, int cols,
+                                                           float scale_log2) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8];
+  const float* row = s + static_cast<int64_t>(blockIdx.x) * lds;
+  __nv_bfloat16* out = p + static_cast<int64_t>(blockIdx.x) * ldp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  const float off = m * scale_log2;
+  float sum = 0.f;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    sum += exp2f(fmaf(v.x, scale_log2, -off)) + exp2f(fmaf(v.y, scale_log2, -off)) +
+           exp2f(fmaf(v.z, scale_log2, -off)) + exp2f(fmaf(v.w, scale_log2, -off));
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    uint2 u;
+    u.x = pack_bf16x2(exp2f(fmaf(v.x, scale_log2, -off)) * inv, exp2f(fmaf(v.y, scale_log2, -off)) * inv);
+    u.y = pack_bf16x2(exp2f(fmaf(v.z, scale_log2, -off)) * inv, exp2f(fmaf(v.w, scale_log2, -off)) * inv);
+    *reinterpret_cast<uint2*>(out + c) = u;
+  }
+}
+
 }  // namespace asva
+
+extern "C" int asva_softmax_rows(const float* scores, int64_t lds, void* probs, int64_t ldp, int64_t rows,
+                                 int32_t cols, float scale, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(scores && probs, "asva_softmax_rows: null operand");
+  ASVA_REQUIRE(rows >= 1 && rows < (1ll << 31) && cols >= 4 && cols % 4 == 0, "asva_softmax_rows: bad shape");
+  ASVA_REQUIRE(lds % 4 == 0 && ldp % 4 == 0 && lds >= cols && ldp >= cols, "asva_softmax_rows: bad leading dimension");
+  ASVA_REQUIRE(scale > 0.f, "asva_softmax_rows: scale must be positive");
+  ASVA_CUDA_OK(launch_k(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, 1, scores, lds,
+                        reinterpret_cast<__nv_bfloat16*>(probs), ldp, cols, scale * 1.4426950408889634f));
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int asva_tconv_gather(const void* y, void* out, int32_t B, int32_t F, int32_t N, int32_t C,
                                  asva_stream_t stream_) {

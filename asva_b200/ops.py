@@ -469,6 +469,15 @@ class CudaBackend:
                    "asva_timestep_features")
         self.launches += 1
 
+    def softmax_rows(self, scores, probs, rows, cols, scale) -> None:
+        """probs bf16 [rows, cols] = softmax(scale * scores fp32 [rows, cols]) (row views with contiguous columns)."""
+        self._chk_dev(scores, probs)
+        assert scores.dtype == torch.float32 and probs.dtype == torch.bfloat16
+        with self._timed('misc'):
+            _lib.check(self.lib.asva_softmax_rows(scores.data_ptr(), scores.stride(0), probs.data_ptr(), probs.stride(0),
+                                                  rows, cols, scale, self._stream()), "asva_softmax_rows")
+        self.launches += 1
+
     def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw, clips: int = 1) -> None:
         """eps fp32 (k*clips, C, F, hw) branch-major; lat fp32 (clips, C, F, hw)."""
         self._chk_dev(eps, lat, coef)

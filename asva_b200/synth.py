@@ -21,7 +21,7 @@ def _gen(key: str, seed: int) -> torch.Generator:
 def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0) -> torch.Tensor:
     g = _gen(key, seed)
     leaf = key.rsplit(".", 1)[-1]
-    is_norm = ".norm" in key or key.startswith("conv_norm_out")
+    is_norm = ".norm" in key or "conv_norm_out" in key or "group_norm" in key
     if leaf == "weight" and is_norm and len(shape) == 1:
         return 1.0 + 0.1 * torch.randn(shape, generator=g)
     if leaf == "bias":

@@ -169,6 +169,12 @@ class AudioCondAnimationPipeline(_ProgressMixin):
 
     @torch.no_grad()
     def decode_latents(self, latents):
+        """(b f) c h w latents -> images in [0, 1] on the CPU (:205-213).  A diffusers AutoencoderKL on a CUDA device is
+        decoded by the B200 engine (asva_b200.vae: same state dict, tcgen05 convs); ASVA_STOCK_VAE=1 keeps the module's
+        own decode."""
+        if latents.is_cuda and os.environ.get("ASVA_STOCK_VAE", "0") != "1":
+            from asva_b200 import vae as _vae
+            self.vae = _vae.wrap_vae(self.vae)
         latents = latents.to(dtype=next(self.vae.parameters()).dtype) / self.vae.config.scaling_factor
         image = self.vae.decode(latents).sample
         return (image / 2 + 0.5).clamp(0, 1).cpu().float()

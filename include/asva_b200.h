@@ -213,6 +213,13 @@ int asva_small_linear(const float* x, const void* w, const float* bias, float* o
 int asva_timestep_features(const float* t, float* out, int32_t B, int32_t dim, int32_t flip_sin_to_cos,
                            asva_stream_t stream);
 
+/* Row softmax  probs[r][c] = softmax_c(scale * scores[r][c]): fp32 scores (an asva_gemm output) -> bf16 probabilities
+ * (an asva_gemm operand).  Serves attention whose single head is wider than asva_attention tiles: the mid-block
+ * attention of the SD-1.5 VAE decoder (diffusers Attention, heads 1, dim_head 512) behind
+ * pipeline_audio_cond_animation.py:205-213 `decode_latents`.  cols % 4 == 0. */
+int asva_softmax_rows(const float* scores, int64_t lds, void* probs, int64_t ldp, int64_t rows, int32_t cols,
+                      float scale, asva_stream_t stream);
+
 /* Classifier-free guidance + sampler update on frames 1..F-1 (frame 0 is the conditioning image and is never
  * written, pipeline_audio_cond_animation.py:363-364).  eps: fp32 [k][clips][C][F][h][w] UNet outputs (k <= 3 CFG
  * branches, branch-major like the pipeline's torch.cat([latents] * k), :331-336); latents: fp32 [clips][C][F][h][w]

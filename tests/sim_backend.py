@@ -227,6 +227,10 @@ class SimBackend:
             e = e + coef[j] * eps[j]
         return e
 
+    def softmax_rows(self, scores, probs, rows, cols, scale) -> None:
+        self.launches += 1
+        probs[:rows, :cols] = torch.softmax(scores[:rows, :cols].float() * scale, dim=-1).to(probs.dtype)
+
     def cfg_ddim_step(self, eps, k, lat, coef, C, F, hw, clips: int = 1) -> None:
         self.launches += 1
         e = self._cfg(eps.view(k, clips, C, F, hw), k, coef)

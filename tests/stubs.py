@@ -151,3 +151,37 @@ def data_utils_stub(n_samples=32000):
 
     return types.SimpleNamespace(load_image=load_image, load_audio_clips_uniformly=load_audio_clips_uniformly,
                                  AudioMelspectrogramExtractor=StubMelExtractor)
+
+
+class StubAutoencoderKL(torch.nn.Module):
+    """Shaped like diffusers.AutoencoderKL for the calls the pipeline makes: a parameter tree whose state_dict() has the
+    library's decoder keys (`post_quant_conv.*`, `decoder.*`), `.config`, `.dtype`, `encode(x).latent_dist.sample()`
+    (StubVAE's pooling) and `decode(z).sample` computed by the restated decoder (oracle/vae_ref.py) on whatever device
+    the parameters live on - it plays the stock module that asva_b200.vae.FastDecodeVAE wraps."""
+
+    def __init__(self, block_out_channels=(128, 256, 512, 512), seed=7):
+        super().__init__()
+        from oracle import vae_ref
+        self.cfg = dict(block_out_channels=tuple(block_out_channels))
+        self.config = _Cfg(block_out_channels=tuple(block_out_channels), scaling_factor=0.18215, latent_channels=4,
+                           layers_per_block=2, out_channels=3, norm_num_groups=32)
+        sd = synth.synth_state_dict(vae_ref.state_dict_shapes(self.cfg), seed=seed)
+        for key, val in sd.items():
+            mod = self
+            parts = key.split(".")
+            for name in parts[:-1]:
+                if not hasattr(mod, name):
+                    mod.add_module(name, torch.nn.Module())
+                mod = getattr(mod, name)
+            mod.register_parameter(parts[-1], torch.nn.Parameter(val, requires_grad=False))
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    def encode(self, x):
+        return StubVAE.encode(self, x)
+
+    def decode(self, z, return_dict=True):
+        from oracle import vae_ref
+        return types.SimpleNamespace(sample=vae_ref.decode(dict(self.state_dict()), z, self.cfg))

@@ -400,3 +400,21 @@ def test_pipeline_conditioning_branch_order_cpu():
         assert torch.equal(a[:, 0], torch.cat(a_exp)) and torch.equal(m, torch.cat(m_exp)), (do_t, do_a)
     lat = pipe.prepare_video_latents(torch.zeros(2, 4, 8, 8), 4, F, 64, 64, cpu, f32, torch.Generator().manual_seed(1))
     assert lat.shape == (2, 4, F, 8, 8) and float(lat[:, :, 0].abs().max()) == 0.0 and float(lat[:, :, 1:].std()) > 0.5
+
+
+# ------------------------------------------------------------------------------------------------ VAE decoder
+def test_vae_decoder_engine_logic_vs_oracle_cpu():
+    """asva_b200.vae.VAEDecoderEngine (weight packing, op sequencing, attention-as-GEMMs with the folded v bias,
+    upsample + conv) interpreted in fp32 on the CPU == the restated AutoencoderKL decoder (oracle/vae_ref.py)."""
+    from asva_b200 import vae
+    from oracle import vae_ref
+    cfg = dict(block_out_channels=(64, 64, 128, 128))
+    sd = synth.synth_state_dict(vae_ref.state_dict_shapes(cfg), seed=3)
+    z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        want = vae_ref.decode(sd, z, cfg)
+    eng = vae.VAEDecoderEngine(sd, cfg, device="cpu", backend=SimBackend(), act_dtype=torch.float32)
+    got = eng.decode(z)
+    assert got.shape == want.shape == (2, 3, 64, 64)
+    assert _rel(got, want) < 2e-5, _rel(got, want)
+    assert vae.is_autoencoder_kl_state_dict(sd) and not vae.is_autoencoder_kl_state_dict({"x": 1})
