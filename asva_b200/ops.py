@@ -216,6 +216,7 @@ class CudaBackend:
         self.launches = 0
         self._gn_sync = {}  # grid-barrier workspace of the fused GroupNorm, one per device
         self._prof = None
+        self._nvtx = os.environ.get("ASVA_NVTX", "0") == "1"
         self._ws = {}
         self.tuning = False
         self.plan_cache = {}
@@ -274,11 +275,15 @@ class CudaBackend:
 
         class _T:
             def __enter__(self):
+                if be._nvtx:  # ASVA_NVTX=1: one NVTX range per C-ABI call, named by kernel family (nsys / ncu --nvtx)
+                    torch.cuda.nvtx.range_push("asva:" + fam)
                 if be._prof is not None:
                     self.e0 = torch.cuda.Event(enable_timing=True)
                     self.e0.record()
 
             def __exit__(self, *a):
+                if be._nvtx:
+                    torch.cuda.nvtx.range_pop()
                 if be._prof is not None:
                     e1 = torch.cuda.Event(enable_timing=True)
                     e1.record()

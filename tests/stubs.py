@@ -185,3 +185,21 @@ class StubAutoencoderKL(torch.nn.Module):
     def decode(self, z, return_dict=True):
         from oracle import vae_ref
         return types.SimpleNamespace(sample=vae_ref.decode(dict(self.state_dict()), z, self.cfg))
+
+
+def dataset_data_utils_stub(filenames, categories, n_samples=8000):
+    """avgen.data.utils protocol used by generate_videos_for_dataset (:494-551): get_evaluation_data(dataset) ->
+    (video_root, filenames, categories, _); load_av_clips_uniformly(...) -> (videos [(F,3,H,W) in [0,1]], audios)."""
+
+    def get_evaluation_data(dataset):
+        return "/videos/" + dataset, list(filenames), list(categories), None
+
+    def load_av_clips_uniformly(video_path, video_fps, video_num_frame, image_size, num_clips,
+                                load_audio_as_melspectrogram=False):
+        g = torch.Generator().manual_seed(sum(map(ord, video_path)))
+        vids = [torch.rand(video_num_frame, 3, image_size[0], image_size[1], generator=g) for _ in range(num_clips)]
+        auds = [torch.randn(1, n_samples, generator=g) * 0.1 for _ in range(num_clips)]
+        return vids, auds
+
+    return types.SimpleNamespace(get_evaluation_data=get_evaluation_data, load_av_clips_uniformly=load_av_clips_uniformly,
+                                 AudioMelspectrogramExtractor=StubMelExtractor)

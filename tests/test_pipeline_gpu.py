@@ -5,6 +5,8 @@ reference's I/O helpers) and the REAL hot path (CUDA UNet engine + fused CFG/sam
 computed independently on the CPU: stub encoders -> reference-ordered CFG batches -> oracle UNet (oracle/unet_ref.py)
 + restated diffusers sampler (oracle/sampler_ref.py) -> stub VAE decode.
 Reference: /root/reference/avgen/pipelines/pipeline_audio_cond_animation.py:264-375 (__call__), :379-468."""
+import os
+
 import numpy as np
 import PIL.Image
 import pytest
@@ -139,3 +141,64 @@ def test_generate_videos_contract(cuda_backend, monkeypatch):
     assert torch.equal(vids[0][0], vids[1][0]), "same conditioning image -> same first frame"
     assert not torch.equal(vids[0][1:], vids[1][1:]), "different audio clips must give different videos"
     assert pipe.scheduler.step_calls == 0
+
+
+def test_generate_videos_for_dataset_sharded(cuda_backend, monkeypatch, tmp_path):
+    """generate_videos_for_dataset (:472-551, scripts/animation_gen.py:32-45) end to end with every external piece
+    stubbed at its import site (diffusers AutoencoderKL / PNDMScheduler, transformers CLIP, ImageBind encoder, the
+    reference's data helpers, torchvision.io.write_video) and the REAL UNet checkpoint path
+    (AudioUNet3DConditionModel.from_pretrained on a directory written by save_pretrained).  Two ranks of a
+    world_size-2 job must together write every <file>_clip-XX.mp4 exactly once (clip-level sharding)."""
+    import json
+    import sys
+    import types
+
+    import torchvision
+    import transformers
+
+    from avgen.models.unets import AudioUNet3DConditionModel
+    from avgen.pipelines import pipeline_audio_cond_animation as P
+    unet, _ = _unet()
+    exp = tmp_path / "exp"
+    unet.save_pretrained(str(exp / "ckpts" / "checkpoint-7" / "modules" / "unet"))
+    files = [f"vid{i}.mp4" for i in range(5)]
+    cats = ["dog", "rain", "dog", "drum", "rain"]
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "datasets" / "AVSync15").mkdir(parents=True)
+    (tmp_path / "pretrained").mkdir()
+    json.dump({c: c for c in set(cats)}, open(tmp_path / "datasets" / "AVSync15" / "class_mapping.json", "w"))
+    enc = stubs.StubTextEncoder()
+    tok = stubs.StubTokenizer()
+    torch.save({c: enc(tok([c]).input_ids)[0] for c in set(cats)},
+               tmp_path / "datasets" / "AVSync15" / "class_clip_text_encodings_stable-diffusion-v1-5.pt")
+    torch.save(enc(tok("").input_ids)[0], tmp_path / "pretrained" / "openai-clip-l_null_text_encoding.pt")
+
+    def from_pretrained_of(factory):
+        return types.SimpleNamespace(from_pretrained=staticmethod(lambda *a, **k: factory()))
+
+    fake_diffusers = types.ModuleType("diffusers")
+    fake_models = types.ModuleType("diffusers.models")
+    fake_models.AutoencoderKL = from_pretrained_of(stubs.StubVAE)
+    fake_sched = types.ModuleType("diffusers.schedulers")
+    fake_sched.PNDMScheduler = from_pretrained_of(stubs.PNDMScheduler)
+    fake_audio = types.ModuleType("avgen.models.audio_encoders")
+    fake_audio.ImageBindSegmaskAudioEncoder = lambda n_segment=12: stubs.StubAudioEncoder(n_segment)
+    for name, mod in (("diffusers", fake_diffusers), ("diffusers.models", fake_models),
+                      ("diffusers.schedulers", fake_sched), ("avgen.models.audio_encoders", fake_audio)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    monkeypatch.setattr(transformers.CLIPTextModel, "from_pretrained", staticmethod(lambda *a, **k: stubs.StubTextEncoder()))
+    monkeypatch.setattr(transformers.CLIPTokenizer, "from_pretrained", staticmethod(lambda *a, **k: stubs.StubTokenizer()))
+    monkeypatch.setattr(P, "_data_utils", lambda: stubs.dataset_data_utils_stub(files, cats))
+    written = []
+    monkeypatch.setattr(torchvision.io, "write_video",
+                        lambda filename, video_array, fps, **kw: written.append((filename, tuple(video_array.shape))))
+    for rank in (0, 1):
+        P.generate_videos_for_dataset(str(exp), 7, dataset="AVSync15", image_size=(H, W), video_fps=6,
+                                      video_num_frame=F, num_clips_per_video=2, audio_guidance_scale=4.0,
+                                      text_guidance_scale=1.0, random_seed=0, device=torch.device("cuda"),
+                                      dtype=torch.float32, rank=rank, world_size=2)
+    names = sorted(os.path.basename(f) for f, _ in written)
+    assert names == sorted(f"vid{i}_clip-{k:02d}.mp4" for i in range(5) for k in range(2)), names
+    assert all(shape == (F, H, W, 3) for _, shape in written)
+    root = os.path.dirname(written[0][0])
+    assert root.endswith(os.path.join("evaluations", "checkpoint-7", "AG-4.0_TG-1.0", "seed-0", "videos")), root

@@ -43,15 +43,22 @@ def make(name):
                         kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d))
 
 
-def sweep(out_path):
+def sweep(out_path, once=False):
     """BASELINE.json config 5: spatial 32^2..64^2 tokens x head dims, temporal 8..24 frames, cross-attention 1..256 keys.
-    Core FLOPs = 4 Nq Nk d per (group, head); bytes = Q + O + K + V in bf16."""
+    Core FLOPs = 4 Nq Nk d per (group, head); bytes = Q + O + K + V in bf16.
+    once=True: every shape is launched exactly twice, eagerly (warm-up + one), for an `ncu --metrics ...` pass whose
+    launch list is then joined with the labels written here (tools/join_attn_sweep.py)."""
     import math as _m
     be = ops.backend()
     H = 8
     lines = ["| kind | tokens / frames / keys | C | d | us | core TFLOP/s | Q+O+KV GB/s |", "|---|---|---|---|---|---|---|"]
 
     def timeit(fn):
+        if once:
+            fn()
+            fn()
+            torch.cuda.synchronize()
+            return float("nan")
         fn()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -109,12 +116,13 @@ def sweep(out_path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep", action="store_true", help="the BASELINE.json config-5 attention microbenchmark sweep")
+    ap.add_argument("--once", action="store_true", help="with --sweep: two eager launches per shape (for ncu)")
     ap.add_argument("--shapes", default=",".join(k for k in SHAPES if not k.endswith("_hr")))
     ap.add_argument("--single", default="")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     if args.sweep:
-        sweep(args.out)
+        sweep(args.out, args.once)
         return
     be = ops.backend()
     if args.single:
