@@ -416,6 +416,10 @@ def generate_videos(pipeline, image_path: str = "", audio_path: str = "", video_
         if save_template:
             path = f"{save_template}_clip-{k:02d}.mp4"
             os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+            if not hasattr(torchvision.io, "write_video"):
+                raise ImportError("torchvision.io.write_video is gone from this torchvision (removed with the video "
+                                  "IO deprecation); install the version the reference pins, or call generate_videos "
+                                  "without save_template and write the returned uint8 frames yourself")
             torchvision.io.write_video(filename=path, video_array=video, fps=video_fps, audio_array=audio,
                                        audio_fps=16000, audio_codec="aac")
         else:

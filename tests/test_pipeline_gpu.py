@@ -190,12 +190,14 @@ def test_generate_videos_for_dataset_sharded(cuda_backend, monkeypatch, tmp_path
     monkeypatch.setattr(transformers.CLIPTokenizer, "from_pretrained", staticmethod(lambda *a, **k: stubs.StubTokenizer()))
     monkeypatch.setattr(P, "_data_utils", lambda: stubs.dataset_data_utils_stub(files, cats))
     written = []
+    # (torchvision >= 0.24 no longer ships write_video; the reference pins an older one - the attribute is injected)
     monkeypatch.setattr(torchvision.io, "write_video",
-                        lambda filename, video_array, fps, **kw: written.append((filename, tuple(video_array.shape))))
+                        lambda filename, video_array, fps, **kw: written.append((filename, tuple(video_array.shape))),
+                        raising=False)
     for rank in (0, 1):
         P.generate_videos_for_dataset(str(exp), 7, dataset="AVSync15", image_size=(H, W), video_fps=6,
                                       video_num_frame=F, num_clips_per_video=2, audio_guidance_scale=4.0,
-                                      text_guidance_scale=1.0, random_seed=0, device=torch.device("cuda"),
+                                      text_guidance_scale=1.0, random_seed=0, device=torch.device("cuda", 0),
                                       dtype=torch.float32, rank=rank, world_size=2)
     names = sorted(os.path.basename(f) for f, _ in written)
     assert names == sorted(f"vid{i}_clip-{k:02d}.mp4" for i in range(5) for k in range(2)), names
