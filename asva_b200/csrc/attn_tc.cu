@@ -39,7 +39,7 @@ struct AttnKParams {
   float scale_log2;   // scale * log2(e)
 };
 
-constexpr int kPolyOf8 = 2;  // of every 8 exponentials of an unmasked tile, this many avoid the MUFU pipe
+constexpr int kPolyOf8 = 4;  // of every 8 exponentials of an unmasked tile, this many avoid the MUFU pipe (packed FFMA2 form)
 
 // NB = S buffers in TMEM and P buffers in shared memory per warpgroup. NB = 2 lets the tensor core compute S(j+1) while
 // the softmax works on S(j), and lets the softmax write P(j) while P V(j-1) still reads P(j-1): the per-tile critical
@@ -79,6 +79,45 @@ __device__ __forceinline__ float poly_exp2(float x) {
   q = fmaf(q, f, 0.69327623f);
   q = fmaf(q, f, 0.99992895f);
   return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2: two fp32 lanes of a 64-bit register pair per instruction). The
+// exponential pass issues at the rate of the FMA / ALU pipes (two softmax warps per scheduler, ~310 instructions per
+// 64-key tile and warp): the scale FFMA and the polynomial's FMAs / ADDs run on pairs, halving their issue slots.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// poly_exp2 on a pair
+__device__ __forceinline__ void poly_exp2_x2(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x2 = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t2 = add_f32x2(x2, pack_f32x2(12582912.f, 12582912.f));
+  const uint64_t r2 = add_f32x2(t2, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma_f32x2(r2, pack_f32x2(-1.f, -1.f), x2);  // x - round(x)
+  uint64_t q2 = fma_f32x2(pack_f32x2(0.05508868f, 0.05508868f), f2, pack_f32x2(0.24260405f, 0.24260405f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.69327623f, 0.69327623f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.99992895f, 0.99992895f));
+  float q0, q1, t0, t1;
+  unpack_f32x2(q2, q0, q1);
+  unpack_f32x2(t2, t0, t1);
+  e0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
 // idesc for P(bf16, K-major, from smem) x V(bf16, MN-major): b_major bit 16 set
@@ -407,7 +446,23 @@ __global__ void __launch_bounds__(64 + 128 * NWG + (NWG > 1 ? 32 : 0), 1) attn_t
         // one 32-column chunk: exponentiate, pack to bf16, store into the swizzled P tile
         auto exp_chunk = [&](const uint32_t (&sv)[32], int c, float m_off, float& mt) {
           float pv[32];
-          if (plain) {
+          if (plain && (POLY % 2 == 0)) {
+            const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), off2 = pack_f32x2(-m_off, -m_off);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
+              mt = fmaxf(mt, fmaxf(s0, s1));
+              const uint64_t x2 = fma_f32x2(pack_f32x2(s0, s1), sc2, off2);
+              if ((i & 7) < POLY) {  // balance the MUFU and FMA pipes
+                poly_exp2_x2(x2, pv[i], pv[i + 1]);
+              } else {
+                float x0, x1;
+                unpack_f32x2(x2, x0, x1);
+                pv[i] = fast_exp2(x0);
+                pv[i + 1] = fast_exp2(x1);
+              }
+            }
+          } else if (plain) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               mt = fmaxf(mt, __uint_as_float(sv[i]));
