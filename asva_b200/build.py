@@ -41,7 +41,7 @@ def _build(lib_path: str, extra: list, obj_prefix: str, verbose: bool) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, obj_prefix + src.replace(".cu", ".o"))
-        # ASVA_NVCC_EXTRA: extra flags for experiments, e.g. "-DASVA_GEMM_LEAN_ISSUER" (use with force=True / --force)
+        # ASVA_NVCC_EXTRA: extra nvcc flags for experiments (use with force=True / --force)
         cmd = [nvcc, *NVCC_FLAGS, *extra, *os.environ.get("ASVA_NVCC_EXTRA", "").split(), "-c",
                os.path.join(CSRC, src), "-o", obj]
         if verbose:

@@ -876,59 +876,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     __syncwarp();
   } else if (warp == 1) {
     // ---------------- MMA issuer (warp-uniform loop, instructions predicated on one elected lane) ----------------
-#ifdef ASVA_GEMM_LEAN_ISSUER
-    // STAGED FOR ROUND 2 - not compiled unless -DASVA_GEMM_LEAN_ISSUER, never validated on a GPU. Single-CTA plans:
-    // the whole issuer loop runs in ONE thread (a branch on elect.sync around the loop, so ptxas emits back-to-back
-    // UTCHMMA with operands in uniform registers and no vote is needed to share a barrier probe's result), and because
-    // a UTCHMMA issue holds the thread for the ~64 cycles a 128 x 128 x 16 MMA runs, the ring
-    // bookkeeping and the probe of the next stage's barrier sit in the gaps BETWEEN the eight MMAs of a stage.
-    if (CG == 1 && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
-      constexpr uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
-      const uint32_t a_lo0 = ((smem_a0 & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t n_st = static_cast<uint32_t>(n_stages);
-      const uint32_t tfull0 = smem_u32(tmem_full_bar);
-      const bool no_mma = (ASVA_DBG(p) & 2) != 0;
-      uint32_t s = 0, ph = 0, t = 0;
-      bool ready = false;
-      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
-        const TileCoord tc = decode_tile<BN, CG>(p, tile, 0);
-        const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
-        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        uint32_t accumulate = 0;
-        for (int n = tc.kb1 - tc.kb0; n > 0; n -= 2) {
-          if (!ready) mbar_wait_a(full0 + 8u * s, ph);
-          tc_fence_after();
-          const uint32_t a_lo = a_lo0 + s * (kSuperBytes >> 4);
-          const uint64_t a0 = desc_hi | a_lo, b0 = desc_hi | (a_lo + (kABytes >> 4));
-          const uint64_t a1 = desc_hi | (a_lo + (kStageBytes >> 4)), b1 = desc_hi | (a_lo + (kStageBytes >> 4) + (kABytes >> 4));
-          if (!no_mma) umma_bf16_ss(tmem_d, a0, b0, idesc, accumulate);
-          uint32_t s2 = s + 1, ph2 = ph;  // (gap) next ring position
-          if (s2 == n_st) {
-            s2 = 0;
-            ph2 ^= 1u;
-          }
-          if (!no_mma) umma_bf16_ss(tmem_d, a0 + 2u, b0 + 2u, idesc, 1u);
-          if (!no_mma) umma_bf16_ss(tmem_d, a0 + 4u, b0 + 4u, idesc, 1u);
-          ready = mbar_test_wait_a(full0 + 8u * s2, ph2);  // (gap) probe the next stage while this one multiplies
-          if (!no_mma) umma_bf16_ss(tmem_d, a0 + 6u, b0 + 6u, idesc, 1u);
-          if (n >= 2 && !no_mma) {  // odd K-block count: the tile's last stage holds one block
-            umma_bf16_ss(tmem_d, a1, b1, idesc, 1u);
-            umma_bf16_ss(tmem_d, a1 + 2u, b1 + 2u, idesc, 1u);
-            umma_bf16_ss(tmem_d, a1 + 4u, b1 + 4u, idesc, 1u);
-            umma_bf16_ss(tmem_d, a1 + 6u, b1 + 6u, idesc, 1u);
-          }
-          tc_commit_a(empty0 + 8u * s);
-          accumulate = 1u;
-          s = s2;
-          ph = ph2;
-        }
-        tc_commit_a(tfull0 + 8u * acc);
-      }
-    }
-    if (CG == 2)
-#endif
     if (rank == 0) {
       const uint32_t el = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN);
