@@ -69,19 +69,19 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
 
 
 def test_committed_bench_line_meets_the_contract():
-    """The newest committed bench line (profiles/r1_bench_v*.json, written by bench.py on a B200) carries every key the
-    driver's contract names, with self-consistent values."""
+    """The newest committed bench line (profiles/r<round>_bench_v<n>.json, written by bench.py on a B200) carries every
+    key the driver's contract names, with self-consistent values."""
     import json
-    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_bench_v*.json")),
-                   key=lambda q: int(re.search(r"_v(\d+)", q).group(1)))
-    paths = [q for q in paths if re.search(r"_v\d+\.json$", q)]
+    paths = [q for q in glob.glob(os.path.join(ROOT, "profiles", "r*_bench_v*.json")) if re.search(r"r\d+_bench_v\d+\.json$", q)]
+    paths.sort(key=lambda q: tuple(int(x) for x in re.search(r"r(\d+)_bench_v(\d+)\.json$", q).groups()))
     d = json.load(open(paths[-1]))
+    assert d["config"].get("clips_per_gpu") == 1  # the headline line is BASELINE's configuration
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in d, k
     assert d["unit"] == "steps/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["warmup"] >= 3
     assert "workload" in d["config"] and "model" not in d["config"]
-    assert abs(d["value"] - 1e3 * d["n_gpus"] / d["ms_per_step"]) / d["value"] < 1e-3
+    assert abs(d["value"] - 1e3 * d["n_gpus"] * d["config"]["clips_per_gpu"] / d["ms_per_step"]) / d["value"] < 1e-3
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"]
     r = d["roofline"]
