@@ -157,14 +157,17 @@ def spec_rows3(x: AView, box_dims: Tuple[int, int, int], w: torch.Tensor, out: t
 
 
 def spec_conv3x3(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n_img: int, h: int, wd: int,
-                 stride: int = 1, bias: Optional[torch.Tensor] = None, out_fp32: bool = False) -> GemmSpec:
-    """Implicit-GEMM 3x3 conv, padding 1.  x: [n_img*h*wd, Cin] channels-last; w: [Cout, 9*Cin] with K index
-    (ky*3 + kx)*Cin + c; out: [n_img*ho*wo, >=Cout]."""
+                 stride: int = 1, bias: Optional[torch.Tensor] = None, out_fp32: bool = False,
+                 pad_lo: int = 1) -> GemmSpec:
+    """Implicit-GEMM 3x3 conv.  x: [n_img*h*wd, Cin] channels-last; w: [Cout, 9*Cin] with K index
+    (ky*3 + kx)*Cin + c; out: [n_img*ho*wo, >=Cout].  Padding 1 on every side, or - pad_lo = 0 - only on the
+    right / bottom (diffusers' VAE Downsample2D: F.pad(x, (0, 1, 0, 1)) then a stride-2 conv without padding); the
+    out-of-range taps are TMA zero fill either way."""
     Cin = x.shape[1]
     N, K = w.shape
-    assert K == 9 * Cin and Cin % 64 == 0 and x.stride(1) == 1 and x.stride(0) == Cin
-    ho, wo = (h + 2 - 3) // stride + 1, (wd + 2 - 3) // stride + 1
-    segs = [Seg(0, 0, (kx - 1, ky - 1, 0), Cin // 64) for ky in range(3) for kx in range(3)]
+    assert K == 9 * Cin and Cin % 64 == 0 and x.stride(1) == 1 and x.stride(0) == Cin and pad_lo in (0, 1)
+    ho, wo = (h + pad_lo + 1 - 3) // stride + 1, (wd + pad_lo + 1 - 3) // stride + 1
+    segs = [Seg(0, 0, (kx - pad_lo, ky - pad_lo, 0), Cin // 64) for ky in range(3) for kx in range(3)]
     av = AView(x, (Cin, wd, h, n_img), (Cin, wd * Cin, h * wd * Cin))
     return GemmSpec(a=[av, None], box=pick_box((wo, ho, n_img)), trav=(stride, stride, 1),
                     out_dims=(wo, ho, n_img), segs=segs, w=w, ldw=w.stride(0), N=N, K=K, out=out, bias=bias,

@@ -162,19 +162,23 @@ class AudioCondAnimationPipeline(_ProgressMixin):
             out.append(torch.from_numpy(a).permute(2, 0, 1) * 2.0 - 1.0)
         return torch.stack(out)
 
+    def _maybe_fast_vae(self, on_cuda: bool) -> None:
+        """A diffusers AutoencoderKL on a CUDA device is run by the B200 engine (asva_b200.vae: same state dict, tcgen05
+        convs, both encode and decode); ASVA_STOCK_VAE=1 keeps the module's own code."""
+        if on_cuda and os.environ.get("ASVA_STOCK_VAE", "0") != "1":
+            from asva_b200 import vae as _vae
+            self.vae = _vae.wrap_vae(self.vae)
+
     @torch.no_grad()
     def encode_latents(self, image: torch.Tensor):
+        self._maybe_fast_vae(torch.device(self.device).type == "cuda")
         image = image.to(device=self.device, dtype=self.vae.dtype)
         return self.vae.encode(image).latent_dist.sample() * self.vae.config.scaling_factor
 
     @torch.no_grad()
     def decode_latents(self, latents):
-        """(b f) c h w latents -> images in [0, 1] on the CPU (:205-213).  A diffusers AutoencoderKL on a CUDA device is
-        decoded by the B200 engine (asva_b200.vae: same state dict, tcgen05 convs); ASVA_STOCK_VAE=1 keeps the module's
-        own decode."""
-        if latents.is_cuda and os.environ.get("ASVA_STOCK_VAE", "0") != "1":
-            from asva_b200 import vae as _vae
-            self.vae = _vae.wrap_vae(self.vae)
+        """(b f) c h w latents -> images in [0, 1] on the CPU (:205-213)."""
+        self._maybe_fast_vae(latents.is_cuda)
         latents = latents.to(dtype=next(self.vae.parameters()).dtype) / self.vae.config.scaling_factor
         image = self.vae.decode(latents).sample
         return (image / 2 + 0.5).clamp(0, 1).cpu().float()

@@ -9,7 +9,8 @@ resnet.py `ResnetBlock2D`, upsampling.py `Upsample2D`, attention_processor.py `A
 `_from_deprecated_attn_block`).  diffusers cannot be installed here, so this restates its published algorithm for the
 SD-1.5 VAE config (block_out_channels (128, 256, 512, 512), layers_per_block 2, latent_channels 4, norm_num_groups 32,
 act_fn silu, one single-head 512-wide attention in the mid block, eps 1e-6): PARITY UNPINNED against the library itself;
-what is pinned is the CUDA decoder against this restatement."""
+what is pinned is the CUDA decoder / encoder against this restatement.  `encode_moments` restates the ENCODER half
+(`encode_latents`, pipeline :199-203,309-310)."""
 import math
 from typing import Dict, List, Tuple
 
@@ -55,6 +56,43 @@ def state_dict_shapes(cfg: dict = None) -> List[Tuple[str, Tuple[int, ...]]]:
         prev = co
     out.extend([("decoder.conv_norm_out.weight", (ch[-1],)), ("decoder.conv_norm_out.bias", (ch[-1],)),
                 ("decoder.conv_out.weight", (oc, ch[-1], 3, 3)), ("decoder.conv_out.bias", (oc,))])
+    return out
+
+
+def encoder_state_dict_shapes(cfg: dict = None) -> List[Tuple[str, Tuple[int, ...]]]:
+    """(key, shape) of the encoder half (`encoder.*`, `quant_conv.*`) of a diffusers AutoencoderKL checkpoint."""
+    c = dict(DEFAULT_CONFIG)
+    c.update(cfg or {})
+    ch = list(c["block_out_channels"])  # 128, 256, 512, 512
+    L = c["layers_per_block"]
+    zc = c["latent_channels"]
+    out = [("encoder.conv_in.weight", (ch[0], 3, 3, 3)), ("encoder.conv_in.bias", (ch[0],))]
+
+    def res(p, ci, co):
+        out.extend([(p + ".norm1.weight", (ci,)), (p + ".norm1.bias", (ci,)),
+                    (p + ".conv1.weight", (co, ci, 3, 3)), (p + ".conv1.bias", (co,)),
+                    (p + ".norm2.weight", (co,)), (p + ".norm2.bias", (co,)),
+                    (p + ".conv2.weight", (co, co, 3, 3)), (p + ".conv2.bias", (co,))])
+        if ci != co:
+            out.extend([(p + ".conv_shortcut.weight", (co, ci, 1, 1)), (p + ".conv_shortcut.bias", (co,))])
+
+    prev = ch[0]
+    for i, co in enumerate(ch):
+        for j in range(L):
+            res(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
+        if i < len(ch) - 1:
+            out.extend([(f"encoder.down_blocks.{i}.downsamplers.0.conv.weight", (co, co, 3, 3)),
+                        (f"encoder.down_blocks.{i}.downsamplers.0.conv.bias", (co,))])
+        prev = co
+    res("encoder.mid_block.resnets.0", ch[-1], ch[-1])
+    a = "encoder.mid_block.attentions.0"
+    out.extend([(a + ".group_norm.weight", (ch[-1],)), (a + ".group_norm.bias", (ch[-1],))])
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        out.extend([(f"{a}.{n}.weight", (ch[-1], ch[-1])), (f"{a}.{n}.bias", (ch[-1],))])
+    res("encoder.mid_block.resnets.1", ch[-1], ch[-1])
+    out.extend([("encoder.conv_norm_out.weight", (ch[-1],)), ("encoder.conv_norm_out.bias", (ch[-1],)),
+                ("encoder.conv_out.weight", (2 * zc, ch[-1], 3, 3)), ("encoder.conv_out.bias", (2 * zc,)),
+                ("quant_conv.weight", (2 * zc, 2 * zc, 1, 1)), ("quant_conv.bias", (2 * zc,))])
     return out
 
 
@@ -116,3 +154,31 @@ def decode(sd: SD, z: torch.Tensor, cfg: dict = None, dtype: torch.dtype = torch
                          sd[f"decoder.up_blocks.{i}.upsamplers.0.conv.bias"], padding=1)
     x = F.silu(F.group_norm(x, g, sd["decoder.conv_norm_out.weight"], sd["decoder.conv_norm_out.bias"], 1e-6))
     return _conv(x, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
+
+
+def encode_moments(sd: SD, x: torch.Tensor, cfg: dict = None, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """AutoencoderKL.encode(x).latent_dist.parameters: x (n, 3, H, W) in [-1, 1] -> moments (n, 2*latent, H/8, W/8) =
+    [mean | logvar] (vae.py `Encoder.forward` + `quant_conv`).  Downsample2D of the VAE pads (0, 1, 0, 1) and convolves
+    with stride 2 and NO padding (downsampling.py, `padding=0` for DownEncoderBlock2D).  The latent the pipeline uses is
+    mean + exp(0.5 * clamp(logvar, -30, 20)) * randn  (DiagonalGaussianDistribution.sample)."""
+    if dtype != torch.float32:
+        sd = {k: v.to(dtype) for k, v in sd.items()}
+        x = x.to(dtype)
+    c = dict(DEFAULT_CONFIG)
+    c.update(cfg or {})
+    g = c["norm_num_groups"]
+    n_down = len(c["block_out_channels"])
+    x = _conv(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1)
+    for i in range(n_down):
+        for j in range(c["layers_per_block"]):
+            x = resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", x, g)
+        if i < n_down - 1:
+            x = F.pad(x, (0, 1, 0, 1))
+            x = _conv(x, sd[f"encoder.down_blocks.{i}.downsamplers.0.conv.weight"],
+                      sd[f"encoder.down_blocks.{i}.downsamplers.0.conv.bias"], stride=2)
+    x = resnet(sd, "encoder.mid_block.resnets.0", x, g)
+    x = mid_attention(sd, "encoder.mid_block.attentions.0", x, g)
+    x = resnet(sd, "encoder.mid_block.resnets.1", x, g)
+    x = F.silu(F.group_norm(x, g, sd["encoder.conv_norm_out.weight"], sd["encoder.conv_norm_out.bias"], 1e-6))
+    x = _conv(x, sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1)
+    return _conv(x, sd["quant_conv.weight"], sd["quant_conv.bias"])

@@ -155,8 +155,8 @@ def data_utils_stub(n_samples=32000):
 
 class StubAutoencoderKL(torch.nn.Module):
     """Shaped like diffusers.AutoencoderKL for the calls the pipeline makes: a parameter tree whose state_dict() has the
-    library's decoder keys (`post_quant_conv.*`, `decoder.*`), `.config`, `.dtype`, `encode(x).latent_dist.sample()`
-    (StubVAE's pooling) and `decode(z).sample` computed by the restated decoder (oracle/vae_ref.py) on whatever device
+    library's keys (`encoder.*`, `quant_conv.*`, `post_quant_conv.*`, `decoder.*`), `.config`, `.dtype`,
+    `encode(x).latent_dist.sample()` and `decode(z).sample` computed by the restated VAE (oracle/vae_ref.py) on whatever device
     the parameters live on - it plays the stock module that asva_b200.vae.FastDecodeVAE wraps."""
 
     def __init__(self, block_out_channels=(128, 256, 512, 512), seed=7):
@@ -165,7 +165,8 @@ class StubAutoencoderKL(torch.nn.Module):
         self.cfg = dict(block_out_channels=tuple(block_out_channels))
         self.config = _Cfg(block_out_channels=tuple(block_out_channels), scaling_factor=0.18215, latent_channels=4,
                            layers_per_block=2, out_channels=3, norm_num_groups=32)
-        sd = synth.synth_state_dict(vae_ref.state_dict_shapes(self.cfg), seed=seed)
+        sd = synth.synth_state_dict(vae_ref.state_dict_shapes(self.cfg) + vae_ref.encoder_state_dict_shapes(self.cfg),
+                                    seed=seed)
         for key, val in sd.items():
             mod = self
             parts = key.split(".")
@@ -180,7 +181,9 @@ class StubAutoencoderKL(torch.nn.Module):
         return next(self.parameters()).dtype
 
     def encode(self, x):
-        return StubVAE.encode(self, x)
+        from asva_b200.vae import DiagonalGaussian
+        from oracle import vae_ref
+        return types.SimpleNamespace(latent_dist=DiagonalGaussian(vae_ref.encode_moments(dict(self.state_dict()), x, self.cfg)))
 
     def decode(self, z, return_dict=True):
         from oracle import vae_ref

@@ -418,3 +418,23 @@ def test_vae_decoder_engine_logic_vs_oracle_cpu():
     assert got.shape == want.shape == (2, 3, 64, 64)
     assert _rel(got, want) < 2e-5, _rel(got, want)
     assert vae.is_autoencoder_kl_state_dict(sd) and not vae.is_autoencoder_kl_state_dict({"x": 1})
+
+
+def test_vae_encoder_engine_logic_vs_oracle_cpu():
+    """VAEEncoderEngine (stride-2 convs padded right / bottom only, attention-as-GEMMs, quant_conv) in fp32 on the CPU
+    == the restated AutoencoderKL encoder; DiagonalGaussian reproduces mean + std * noise."""
+    from asva_b200 import vae
+    from oracle import vae_ref
+    cfg = dict(block_out_channels=(64, 64, 128, 128))
+    sd = synth.synth_state_dict(vae_ref.encoder_state_dict_shapes(cfg), seed=4)
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(12)) * 2 - 1
+    with torch.no_grad():
+        want = vae_ref.encode_moments(sd, x, cfg)
+    eng = vae.VAEEncoderEngine(sd, cfg, device="cpu", backend=SimBackend(), act_dtype=torch.float32)
+    got = eng.encode_moments(x)
+    assert got.shape == want.shape == (2, 8, 8, 8)
+    assert _rel(got, want) < 2e-5, _rel(got, want)
+    d = vae.DiagonalGaussian(got)
+    z = d.sample(torch.Generator().manual_seed(1))
+    n = torch.randn(d.mean.shape, generator=torch.Generator().manual_seed(1))
+    assert torch.allclose(z, got[:, :4] + torch.exp(0.5 * got[:, 4:].clamp(-30, 20)) * n) and torch.equal(d.mode(), got[:, :4])

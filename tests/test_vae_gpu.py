@@ -49,6 +49,25 @@ def test_vae_decode_vs_oracle(cuda_backend, n, h, w):
         assert rel <= 1.5 * anchor and cos >= 0.9995, (rel, anchor, cos)
 
 
+@pytest.mark.parametrize("n,H,W", [(1, 256, 256), (2, 128, 192)])
+def test_vae_encode_vs_oracle(cuda_backend, n, H, W):
+    from oracle import vae_ref
+    sd = synth.synth_state_dict(vae_ref.encoder_state_dict_shapes(), seed=4)
+    x = torch.rand(n, 3, H, W, generator=torch.Generator().manual_seed(200 + n)) * 2 - 1
+    with torch.no_grad():
+        want = vae_ref.encode_moments(sd, x)
+        low = vae_ref.encode_moments(sd, x, dtype=torch.bfloat16).float()
+    anchor = float((low - want).norm() / want.norm())
+    eng = vae.VAEEncoderEngine(sd, device=DEV)
+    for rep in range(2):
+        got = eng.encode_moments(x.to(DEV)).cpu()
+        assert got.shape == (n, 8, H // 8, W // 8) and torch.isfinite(got).all()
+        rel = float((got - want).norm() / want.norm())
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0))
+        print(f"[parity] vae encode n{n} {H}x{W} call {rep}: rel-L2 {rel:.3e} (bf16-eager anchor {anchor:.3e}) cos {cos:.6f}")
+        assert rel <= 1.5 * anchor and cos >= 0.9995, (rel, anchor, cos)
+
+
 def test_pipeline_decodes_with_the_engine(cuda_backend, monkeypatch):
     """decode_latents wraps an AutoencoderKL-shaped module (diffusers state-dict keys) in FastDecodeVAE; the videos
     match the module's own decode, and ASVA_STOCK_VAE=1 leaves the module alone."""
@@ -66,6 +85,12 @@ def test_pipeline_decodes_with_the_engine(cuda_backend, monkeypatch):
     rel = float((fast - stock).norm() / stock.norm())
     print(f"[parity] pipeline.decode_latents engine vs stock module: rel-L2 {rel:.3e}")
     assert rel < 2e-2
-    # encode / config / dtype still come from the wrapped module
+    # config / dtype still come from the wrapped module; encode runs on the engine too (diffusers encoder keys present)
     assert pipe.vae.config.scaling_factor == 0.18215 and pipe.vae.dtype == torch.float32
-    assert pipe.vae.encode(torch.zeros(1, 3, 64, 64, device=DEV)).latent_dist.sample().shape == (1, 4, 8, 8)
+    img = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(3)).to(DEV) * 2 - 1
+    dist = pipe.vae.encode(img).latent_dist
+    ref = v.encode(img).latent_dist
+    assert dist.sample().shape == (1, 4, 8, 8)
+    rel_e = float((dist.mean - ref.mean).norm() / ref.mean.norm())
+    print(f"[parity] FastDecodeVAE.encode mean vs stock module: rel-L2 {rel_e:.3e}")
+    assert rel_e < 3e-2 and isinstance(pipe.vae._enc, vae.VAEEncoderEngine)
