@@ -54,6 +54,14 @@ class GemmDesc(C.Structure):
         ("ws", C.c_void_p),
         ("ws_bytes", C.c_int64),
         ("epilogue", C.c_int32),
+        ("ln_cols", C.c_int32),
+        ("stats_out", C.c_void_p),
+        ("ln_stats", C.c_void_p),
+        ("ln_wsum", C.c_void_p),
+        ("ln_stat_rows", C.c_int64),
+        ("ln_grp_rows", C.c_int32),
+        ("ln_grp_stride", C.c_int32),
+        ("ln_eps", C.c_float),
         ("reserved", C.c_int32),
     ]
 

@@ -76,6 +76,14 @@ struct GemmKParams {
   int64_t ldo;
   const __nv_bfloat16* res_ptr[2];
   int64_t res_ld[2];
+  // row statistics / LayerNorm fold (asva_gemm_desc.stats_out, .ln_*)
+  float* stats_out;       // [N/32][stats_rows][2]: (sum, sum of squares) of every stored row per 32-column slot
+  int64_t stats_rows;
+  const float* ln_stats;  // [ln_slots][ln_stat_rows][2]
+  const float* ln_wsum;   // [N]
+  int64_t ln_stat_rows;
+  int32_t ln_slots, ln_grp_rows, ln_grp_stride;
+  float ln_inv_c, ln_eps;
 };
 
 struct TileCoord {
@@ -116,6 +124,80 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Global output row of tile row (r1, r2, r3) (-1: the row lies outside the tile or the tensor).
+__device__ __forceinline__ int64_t tile_out_row(const GemmKParams& p, const TileCoord& tc, int r, int r1, int r2, int r3) {
+  const int a1 = tc.o1 + r1, a2 = tc.o2 + r2, a3 = tc.o3 + r3;
+  const bool valid = (r < p.rows_per_tile) && (a1 < p.out_dims[0]) && (a2 < p.out_dims[1]) && (a3 < p.out_dims[2]);
+  return valid ? (static_cast<int64_t>(a3) * p.out_dims[1] + a2) * p.out_dims[0] + a1 : -1;
+}
+
+// LayerNorm fold: out = rs * acc + (bias + rm * wsum[col]) with rs = rstd, rm = -mean * rstd of the row the
+// accumulator row was computed from; the sums were left per 32-column slot by the producing GEMM (or are 1 / 0).
+__device__ __forceinline__ void row_fold(const GemmKParams& p, int64_t row, float& rs, float& rm) {
+  rs = 1.f;
+  rm = 0.f;
+  if (p.ln_stats == nullptr || row < 0) return;
+  int64_t sr = row;
+  if (p.ln_grp_rows > 0) sr = (row / p.ln_grp_rows) * p.ln_grp_stride + row % p.ln_grp_rows;
+  const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + sr;
+  float sum = 0.f, sq = 0.f;
+  for (int i = 0; i < p.ln_slots; ++i) {
+    const float2 v = __ldg(st + i * p.ln_stat_rows);
+    sum += v.x;
+    sq += v.y;
+  }
+  const float mean = sum * p.ln_inv_c;
+  const float var = fmaxf(sq * p.ln_inv_c - mean * mean, 0.f);
+  rs = rsqrtf(var + p.ln_eps);
+  rm = -mean * rs;
+}
+
+// b += rm * wsum[col0 .. col0+31] (the folded LayerNorm's mean term joins the bias registers)
+__device__ __forceinline__ void fold_bias(const GemmKParams& p, float4 (&b)[8], int col0, float rm) {
+  if (p.ln_wsum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (col0 + j * 4 < p.N) {
+      const float4 w = ldg4(p.ln_wsum + col0 + j * 4);
+      b[j].x = fmaf(rm, w.x, b[j].x);
+      b[j].y = fmaf(rm, w.y, b[j].y);
+      b[j].z = fmaf(rm, w.z, b[j].z);
+      b[j].w = fmaf(rm, w.w, b[j].w);
+    }
+  }
+}
+
+// The additive column terms of 4 adjacent outputs of one row: bias + row addend + (LayerNorm fold) rm * wsum.
+__device__ __forceinline__ float4 col_terms(const GemmKParams& p, const float* addp, int col, float rm) {
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < p.N) {
+    if (p.bias != nullptr) b = ldg4(p.bias + col);
+    if (addp != nullptr) {
+      const float4 a = ldg4(addp + col);
+      b.x += a.x; b.y += a.y; b.z += a.z; b.w += a.w;
+    }
+    if (p.ln_wsum != nullptr) {
+      const float4 w = ldg4(p.ln_wsum + col);
+      b.x = fmaf(rm, w.x, b.x); b.y = fmaf(rm, w.y, b.y); b.z = fmaf(rm, w.z, b.z); b.w = fmaf(rm, w.w, b.w);
+    }
+  }
+  return b;
+}
+
+// (sum, sum of squares) of the 32 fp32 values a thread is about to store for its row -> stats[slot][row]
+__device__ __forceinline__ void emit_row_stats(const GemmKParams& p, const uint32_t (&v)[32], int col0, int64_t row) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float x = __uint_as_float(v[j]);
+    s[j & 3] += x;
+    q[j & 3] = fmaf(x, x, q[j & 3]);
+  }
+  if (row >= 0 && col0 < p.N)
+    *reinterpret_cast<float2*>(p.stats_out + (static_cast<int64_t>(col0 >> 5) * p.stats_rows + row) * 2) =
+        make_float2((s[0] + s[1]) + (s[2] + s[3]), (q[0] + q[1]) + (q[2] + q[3]));
+}
 
 
 // Per-warp epilogue (epi == 2; bf16 output, no GEGLU, no split-K). Every epilogue warp owns the 32 x 32 sub-panels of
@@ -309,7 +391,7 @@ __device__ __forceinline__ void residual_issuer_wide(const GemmKParams& p, int r
   }
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool RS>
 __device__ __forceinline__ void epilogue_warp_tma_wide(const GemmKParams& p, int warp, int lane, int rank, int tile0,
                                                        int tile_step, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                                        uint64_t* tmem_empty_bar, uint64_t* res_full,
@@ -339,13 +421,12 @@ __device__ __forceinline__ void epilogue_warp_tma_wide(const GemmKParams& p, int
     const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
     const int chunks = wide_chunks<BN, CG>(p, tc.n0);
     const int n_panels = (chunks + 1) >> 1;
+    int64_t grow = -1;
+    if (RS || p.add_ptr != nullptr) grow = tile_out_row(p, tc, r, r1, r2, r3);
     const float* addp = nullptr;
-    if (p.add_ptr != nullptr) {
-      const int a1 = tc.o1 + r1, a2 = tc.o2 + r2, a3 = tc.o3 + r3;
-      const bool valid = (r < p.rows_per_tile) && (a1 < p.out_dims[0]) && (a2 < p.out_dims[1]) && (a3 < p.out_dims[2]);
-      const int64_t row = valid ? (static_cast<int64_t>(a3) * p.out_dims[1] + a2) * p.out_dims[0] + a1 : 0;
-      addp = p.add_ptr + (row / p.add_div) * p.add_ld;
-    }
+    if (p.add_ptr != nullptr) addp = p.add_ptr + ((grow < 0 ? 0 : grow) / p.add_div) * p.add_ld;
+    float rs = 1.f, rm = 0.f;
+    if constexpr (RS) row_fold(p, grow, rs, rm);
     int q_last = n_panels - 1;
     if (((pc + q_last) & 1u) != g) --q_last;
     mbar_wait(&tmem_full_bar[acc], acc_ph);
@@ -386,6 +467,9 @@ __device__ __forceinline__ void epilogue_warp_tma_wide(const GemmKParams& p, int
             }
           }
         }
+        if constexpr (RS) {
+          if (on) fold_bias(p, b, col0, rm);
+        }
       };
       load_bias(acol, true);
       tmem_ld_wait();
@@ -395,22 +479,22 @@ __device__ __forceinline__ void epilogue_warp_tma_wide(const GemmKParams& p, int
         if (lane == 0) release_acc(&tmem_empty_bar[acc]);
       }
       ASVA_TR(p, warp, 4 + 20 * t + 6 * trp);
-      // accumulator + bias (+ row addend) in fp32, in place
+      // accumulator (* the row's rstd under the LayerNorm fold, else * 1: exact) + bias (+ row addend) in fp32, in place
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v0[4 * j + 0] = __float_as_uint(__uint_as_float(v0[4 * j + 0]) + b[j].x);
-        v0[4 * j + 1] = __float_as_uint(__uint_as_float(v0[4 * j + 1]) + b[j].y);
-        v0[4 * j + 2] = __float_as_uint(__uint_as_float(v0[4 * j + 2]) + b[j].z);
-        v0[4 * j + 3] = __float_as_uint(__uint_as_float(v0[4 * j + 3]) + b[j].w);
+        v0[4 * j + 0] = __float_as_uint(RS ? fmaf(__uint_as_float(v0[4 * j + 0]), rs, b[j].x) : __uint_as_float(v0[4 * j + 0]) + b[j].x);
+        v0[4 * j + 1] = __float_as_uint(RS ? fmaf(__uint_as_float(v0[4 * j + 1]), rs, b[j].y) : __uint_as_float(v0[4 * j + 1]) + b[j].y);
+        v0[4 * j + 2] = __float_as_uint(RS ? fmaf(__uint_as_float(v0[4 * j + 2]), rs, b[j].z) : __uint_as_float(v0[4 * j + 2]) + b[j].z);
+        v0[4 * j + 3] = __float_as_uint(RS ? fmaf(__uint_as_float(v0[4 * j + 3]), rs, b[j].w) : __uint_as_float(v0[4 * j + 3]) + b[j].w);
       }
       if (two) {
         load_bias(acol + 32, true);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          v1[4 * j + 0] = __float_as_uint(__uint_as_float(v1[4 * j + 0]) + b[j].x);
-          v1[4 * j + 1] = __float_as_uint(__uint_as_float(v1[4 * j + 1]) + b[j].y);
-          v1[4 * j + 2] = __float_as_uint(__uint_as_float(v1[4 * j + 2]) + b[j].z);
-          v1[4 * j + 3] = __float_as_uint(__uint_as_float(v1[4 * j + 3]) + b[j].w);
+          v1[4 * j + 0] = __float_as_uint(RS ? fmaf(__uint_as_float(v1[4 * j + 0]), rs, b[j].x) : __uint_as_float(v1[4 * j + 0]) + b[j].x);
+          v1[4 * j + 1] = __float_as_uint(RS ? fmaf(__uint_as_float(v1[4 * j + 1]), rs, b[j].y) : __uint_as_float(v1[4 * j + 1]) + b[j].y);
+          v1[4 * j + 2] = __float_as_uint(RS ? fmaf(__uint_as_float(v1[4 * j + 2]), rs, b[j].z) : __uint_as_float(v1[4 * j + 2]) + b[j].z);
+          v1[4 * j + 3] = __float_as_uint(RS ? fmaf(__uint_as_float(v1[4 * j + 3]), rs, b[j].w) : __uint_as_float(v1[4 * j + 3]) + b[j].w);
         }
       }
       ASVA_TR(p, warp, 5 + 20 * t + 6 * trp);
@@ -442,6 +526,12 @@ __device__ __forceinline__ void epilogue_warp_tma_wide(const GemmKParams& p, int
         if (two) add_half(v1, 4);
         __syncwarp();  // every lane of this warp has read its rows of the slot
         if (lane == 0) mbar_arrive(&res_empty[slot]);
+      }
+      if constexpr (RS) {
+        if (p.stats_out != nullptr) {
+          emit_row_stats(p, v0, acol, grow);
+          if (two) emit_row_stats(p, v1, acol + 32, grow);
+        }
       }
       uint32_t pk[32];  // the row's 64 bf16 outputs, packed
 #pragma unroll
@@ -493,7 +583,7 @@ __device__ __forceinline__ void epilogue_warp_tma_wide(const GemmKParams& p, int
 // ring and mbarriers, its own TMA loads and stores through tensor maps whose row box is the quadrant's 32-row slice of
 // the tile (host: sub-box feasibility). No block-level barrier is left in the epilogue - eight independent chains per
 // CTA keep the TMA / TMEM / L2 latencies of one panel under the work of the others.
-template <int BN, bool GEGLU, int CG>
+template <int BN, bool GEGLU, int CG, bool RS>
 __device__ __forceinline__ void epilogue_warp_tma_narrow(const GemmKParams& p, int warp, int lane, int rank, int tile0,
                                                   int tile_step, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                                   uint64_t* tmem_empty_bar, uint64_t* res_full_bar, uint8_t* res_ring,
@@ -551,13 +641,12 @@ __device__ __forceinline__ void epilogue_warp_tma_narrow(const GemmKParams& p, i
     const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
     const int n_panels = tile_panels<BN, GEGLU>(p, tc.n0);
     const int n0_out = GEGLU ? (tc.n0 >> 1) : tc.n0;
+    int64_t grow = -1;
+    if (RS || p.add_ptr != nullptr) grow = tile_out_row(p, tc, r, r1, r2, r3);
     const float* addp = nullptr;
-    if (p.add_ptr != nullptr) {
-      const int a1 = tc.o1 + r1, a2 = tc.o2 + r2, a3 = tc.o3 + r3;
-      const bool valid = (r < p.rows_per_tile) && (a1 < p.out_dims[0]) && (a2 < p.out_dims[1]) && (a3 < p.out_dims[2]);
-      const int64_t row = valid ? (static_cast<int64_t>(a3) * p.out_dims[1] + a2) * p.out_dims[0] + a1 : 0;
-      addp = p.add_ptr + (row / p.add_div) * p.add_ld;
-    }
+    if (p.add_ptr != nullptr) addp = p.add_ptr + ((grow < 0 ? 0 : grow) / p.add_div) * p.add_ld;
+    float rs = 1.f, rm = 0.f;
+    if constexpr (RS) row_fold(p, grow, rs, rm);
     int q_last = n_panels - 1;
     if (((pc + q_last) & 1u) != g) --q_last;
     mbar_wait(&tmem_full_bar[acc], acc_ph);
@@ -586,27 +675,38 @@ __device__ __forceinline__ void epilogue_warp_tma_narrow(const GemmKParams& p, i
           if (lane == 0) release_acc(&tmem_empty_bar[acc]);
         }
         const int acol = tc.n0 + q * 32;
-        if (p.bias != nullptr) {
+        if constexpr (RS) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (acol + j * 4 < p.N) {
-              const float4 b = ldg4(p.bias + acol + j * 4);
-              v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
-              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
-              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
-              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+          for (int j = 0; j < 8; ++j) {  // acc * rstd (1 without the LayerNorm fold: exact) + column terms
+            const float4 b = col_terms(p, addp, acol + j * 4, rm);
+            v[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 0]), rs, b.x));
+            v[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 1]), rs, b.y));
+            v[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 2]), rs, b.z));
+            v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), rs, b.w));
+          }
+        } else {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (acol + j * 4 < p.N) {
+                const float4 b = ldg4(p.bias + acol + j * 4);
+                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+              }
             }
           }
-        }
-        if (addp != nullptr) {
+          if (addp != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (acol + j * 4 < p.N) {
-              const float4 b = ldg4(addp + acol + j * 4);
-              v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
-              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
-              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
-              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+            for (int j = 0; j < 8; ++j) {
+              if (acol + j * 4 < p.N) {
+                const float4 b = ldg4(addp + acol + j * 4);
+                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+              }
             }
           }
         }
@@ -634,6 +734,9 @@ __device__ __forceinline__ void epilogue_warp_tma_narrow(const GemmKParams& p, i
             rph ^= 1u;
           }
         }
+        if constexpr (RS) {
+          if (p.stats_out != nullptr) emit_row_stats(p, v, acol, grow);
+        }
       } else {
         // tile columns [0,64) = value h, [64,128) = gate g; output = (h + bh) * gelu(g + bg)
         uint32_t gv[32];
@@ -648,15 +751,23 @@ __device__ __forceinline__ void epilogue_warp_tma_narrow(const GemmKParams& p, i
         const int acol = tc.n0 + q * 32;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
-          if (p.bias != nullptr) {
-            bh = ldg4(p.bias + acol + j * 4);
-            bg = ldg4(p.bias + acol + 64 + j * 4);
+          if constexpr (RS) {
+            const float4 bh = col_terms(p, nullptr, acol + j * 4, rm), bg = col_terms(p, nullptr, acol + 64 + j * 4, rm);
+            v[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 0]), rs, bh.x) * gelu_erf_f(fmaf(__uint_as_float(gv[4 * j + 0]), rs, bg.x)));
+            v[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 1]), rs, bh.y) * gelu_erf_f(fmaf(__uint_as_float(gv[4 * j + 1]), rs, bg.y)));
+            v[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 2]), rs, bh.z) * gelu_erf_f(fmaf(__uint_as_float(gv[4 * j + 2]), rs, bg.z)));
+            v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), rs, bh.w) * gelu_erf_f(fmaf(__uint_as_float(gv[4 * j + 3]), rs, bg.w)));
+          } else {
+            float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+            if (p.bias != nullptr) {
+              bh = ldg4(p.bias + acol + j * 4);
+              bg = ldg4(p.bias + acol + 64 + j * 4);
+            }
+            v[4 * j + 0] = __float_as_uint((__uint_as_float(v[4 * j + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gv[4 * j + 0]) + bg.x));
+            v[4 * j + 1] = __float_as_uint((__uint_as_float(v[4 * j + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gv[4 * j + 1]) + bg.y));
+            v[4 * j + 2] = __float_as_uint((__uint_as_float(v[4 * j + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gv[4 * j + 2]) + bg.z));
+            v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gv[4 * j + 3]) + bg.w));
           }
-          v[4 * j + 0] = __float_as_uint((__uint_as_float(v[4 * j + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gv[4 * j + 0]) + bg.x));
-          v[4 * j + 1] = __float_as_uint((__uint_as_float(v[4 * j + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gv[4 * j + 1]) + bg.y));
-          v[4 * j + 2] = __float_as_uint((__uint_as_float(v[4 * j + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gv[4 * j + 2]) + bg.z));
-          v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gv[4 * j + 3]) + bg.w));
         }
       }
       ASVA_TR(p, warp, 6 + 20 * t + 6 * trp);
@@ -703,7 +814,10 @@ __device__ __forceinline__ void epilogue_warp_tma_narrow(const GemmKParams& p, i
   ASVA_TR(p, warp, 63);
 }
 
-template <int BN, bool GEGLU, int CG>
+// RS: the instantiations that carry the row-statistics / LayerNorm-fold code (asva_gemm_desc.stats_out, .ln_*); the
+// others are the plain epilogues, untouched by it (the fold's extra loads in the shared path cost the plain launches
+// 10 - 60 %, measured: tools/lnfold_probe.py).
+template <int BN, bool GEGLU, int CG, bool RS>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
   constexpr int kABytes = 128 * 128;
   constexpr int kBBytes = (BN / CG) * 128;  // a CTA of a pair holds half of the W tile's rows
@@ -961,13 +1075,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   } else if (warp >= 4 && p.epi == 3) {
     if constexpr (!GEGLU) {
       if (!p.out_fp32)
-        epilogue_warp_tma_wide<BN, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar, tmem_empty_bar,
+        epilogue_warp_tma_wide<BN, CG, RS>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar, tmem_empty_bar,
                                        res_full_bar, res_full_bar + 8, res_ring, out_ring);
       else
-        epilogue_warp_tma_narrow<BN, GEGLU, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar,
+        epilogue_warp_tma_narrow<BN, GEGLU, CG, RS>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar,
                                                 tmem_empty_bar, res_full_bar, res_ring, out_ring);
     } else {
-      epilogue_warp_tma_narrow<BN, GEGLU, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar,
+      epilogue_warp_tma_narrow<BN, GEGLU, CG, RS>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar,
                                               tmem_empty_bar, res_full_bar, res_ring, out_ring);
     }
   } else if (warp >= 4) {
@@ -1026,14 +1140,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
       const int n_panels = tile_panels<BN, GEGLU>(p, tc.n0);
       const int n0_out = GEGLU ? (tc.n0 >> 1) : tc.n0;
+      int64_t grow = -1;
+      if (RS || p.add_ptr != nullptr) grow = tile_out_row(p, tc, r, r1, r2, r3);
       const float* addp = nullptr;
-      if (p.add_ptr != nullptr) {
-        int a1 = tc.o1 + r1, a2 = tc.o2 + r2, a3 = tc.o3 + r3;
-        const bool valid = (r < p.rows_per_tile) && (a1 < p.out_dims[0]) && (a2 < p.out_dims[1]) &&
-                           (a3 < p.out_dims[2]);
-        const int64_t row = valid ? (static_cast<int64_t>(a3) * p.out_dims[1] + a2) * p.out_dims[0] + a1 : 0;
-        addp = p.add_ptr + (row / p.add_div) * p.add_ld;
-      }
+      if (p.add_ptr != nullptr) addp = p.add_ptr + ((grow < 0 ? 0 : grow) / p.add_div) * p.add_ld;
+      float rs = 1.f, rm = 0.f;
+      if constexpr (RS) row_fold(p, grow, rs, rm);
       int q_last = n_panels - 1;
       if (((pc + q_last) & 1u) != g) --q_last;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
@@ -1057,27 +1169,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             if (lane == 0) release_acc(&tmem_empty_bar[acc]);
           }
           const int acol = tc.n0 + q * 32;
-          if (p.bias != nullptr) {
+          if constexpr (RS) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (acol + j * 4 < p.N) {
-                const float4 b = ldg4(p.bias + acol + j * 4);
-                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
-                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
-                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
-                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+            for (int j = 0; j < 8; ++j) {  // acc * rstd (1 without the LayerNorm fold: exact) + column terms
+              const float4 b = col_terms(p, addp, acol + j * 4, rm);
+              v[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 0]), rs, b.x));
+              v[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 1]), rs, b.y));
+              v[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 2]), rs, b.z));
+              v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), rs, b.w));
+            }
+          } else {
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (acol + j * 4 < p.N) {
+                  const float4 b = ldg4(p.bias + acol + j * 4);
+                  v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+                  v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                  v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                  v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+                }
               }
             }
-          }
-          if (addp != nullptr) {
+            if (addp != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (acol + j * 4 < p.N) {
-                const float4 b = ldg4(addp + acol + j * 4);
-                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
-                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
-                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
-                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+              for (int j = 0; j < 8; ++j) {
+                if (acol + j * 4 < p.N) {
+                  const float4 b = ldg4(addp + acol + j * 4);
+                  v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+                  v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                  v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                  v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+                }
               }
             }
           }
@@ -1104,6 +1227,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               rph ^= 1u;
             }
           }
+          if constexpr (RS) {
+            if (p.stats_out != nullptr) emit_row_stats(p, v, acol, grow);
+          }
         } else {
           // tile columns [0,64) = value h, [64,128) = gate g; output = (h + bh) * gelu(g + bg)
           uint32_t gv[32];
@@ -1118,15 +1244,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           const int acol = tc.n0 + q * 32;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
-            if (p.bias != nullptr) {
-              bh = ldg4(p.bias + acol + j * 4);
-              bg = ldg4(p.bias + acol + 64 + j * 4);
+            if constexpr (RS) {
+              const float4 bh = col_terms(p, nullptr, acol + j * 4, rm), bg = col_terms(p, nullptr, acol + 64 + j * 4, rm);
+              v[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 0]), rs, bh.x) * gelu_erf_f(fmaf(__uint_as_float(gv[4 * j + 0]), rs, bg.x)));
+              v[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 1]), rs, bh.y) * gelu_erf_f(fmaf(__uint_as_float(gv[4 * j + 1]), rs, bg.y)));
+              v[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 2]), rs, bh.z) * gelu_erf_f(fmaf(__uint_as_float(gv[4 * j + 2]), rs, bg.z)));
+              v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), rs, bh.w) * gelu_erf_f(fmaf(__uint_as_float(gv[4 * j + 3]), rs, bg.w)));
+            } else {
+              float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+              if (p.bias != nullptr) {
+                bh = ldg4(p.bias + acol + j * 4);
+                bg = ldg4(p.bias + acol + 64 + j * 4);
+              }
+              v[4 * j + 0] = __float_as_uint((__uint_as_float(v[4 * j + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gv[4 * j + 0]) + bg.x));
+              v[4 * j + 1] = __float_as_uint((__uint_as_float(v[4 * j + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gv[4 * j + 1]) + bg.y));
+              v[4 * j + 2] = __float_as_uint((__uint_as_float(v[4 * j + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gv[4 * j + 2]) + bg.z));
+              v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gv[4 * j + 3]) + bg.w));
             }
-            v[4 * j + 0] = __float_as_uint((__uint_as_float(v[4 * j + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gv[4 * j + 0]) + bg.x));
-            v[4 * j + 1] = __float_as_uint((__uint_as_float(v[4 * j + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gv[4 * j + 1]) + bg.y));
-            v[4 * j + 2] = __float_as_uint((__uint_as_float(v[4 * j + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gv[4 * j + 2]) + bg.z));
-            v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gv[4 * j + 3]) + bg.w));
           }
         }
         // ---- stage the panel (swizzled exactly as the output tensor map expects) and store it with TMA
@@ -1180,19 +1314,22 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
                                                               const float* __restrict__ add_ptr, int64_t add_ld,
                                                               int add_div, const __nv_bfloat16* res0, int64_t ld0,
                                                               const __nv_bfloat16* res1, int64_t ld1, void* out,
-                                                              int64_t ldo, int out_fp32) {
+                                                              int64_t ldo, int out_fp32, float* stats_out) {
   pdl_trigger();
   pdl_wait();
   const int nchunk = N >> 3;
   const int64_t total = M * nchunk;
   const int64_t plane = M * static_cast<int64_t>(N);
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t row = i / nchunk;
-    const int col = static_cast<int>(i % nchunk) * 8;
+    const bool on = i < total;
+    if (__ballot_sync(0xffffffffu, on) == 0u) break;  // the whole warp leaves together (row statistics shuffle)
+    const int64_t row = on ? i / nchunk : 0;
+    const int col = on ? static_cast<int>(i % nchunk) * 8 : 0;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (on) {
     const float* src = ws + row * N + col;
     for (int s = 0; s < S; ++s) {
       const float4 a = *reinterpret_cast<const float4*>(src + s * plane);
@@ -1227,6 +1364,22 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
       w.z = pack_bf16x2(v[4], v[5]);
       w.w = pack_bf16x2(v[6], v[7]);
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + row * ldo + col) = w;
+    }
+    }
+    if (stats_out != nullptr) {
+      // N % 32 == 0: the four lanes of an aligned quad hold one row's 32-column slot (asva_gemm_desc.stats_out)
+      float sm = 0.f, sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sm += v[j];
+        sq = fmaf(v[j], v[j], sq);
+      }
+      sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      if (on && (threadIdx.x & 3) == 0)
+        *reinterpret_cast<float2*>(stats_out + (static_cast<int64_t>(col >> 5) * M + row) * 2) = make_float2(sm, sq);
     }
   }
 }
@@ -1336,13 +1489,15 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
   int sub[3];
   const bool sub_ok = sub_box(d, sub);
   int want_epi = d->epilogue ? d->epilogue : (env_epi ? env_epi : (n_res > 0 ? 2 : kDefaultEpi));
+  const bool row_stats = d->stats_out != nullptr || d->ln_cols > 0;  // forms 1 and 3 carry the statistics / fold code
+  if (want_epi == 2 && row_stats) want_epi = sub_ok ? 3 : 1;
   if (want_epi == 2 && (d->geglu || d->out_fp32)) want_epi = 1;
   if (want_epi == 3 && (!sub_ok || (n_res > 0 && d->out_fp32))) want_epi = 1;
   if (want_epi != 2 && want_epi != 3) want_epi = 1;
   const int bns[4] = {64, 128, 160, 256};
   const int splits[10] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
   const int want_bn = d->geglu ? 128 : (d->block_n ? d->block_n : env_bn);
-  const int want_split = d->geglu ? 1 : (d->split_k ? d->split_k : env_split);
+  const int want_split = (d->geglu || d->ln_cols > 0) ? 1 : (d->split_k ? d->split_k : env_split);
   const int want_cg = d->cta_group ? d->cta_group : env_cg;
   const int64_t max_split = (d->ws != nullptr) ? d->ws_bytes / (M * static_cast<int64_t>(d->N) * 4) : 1;
   double best_cost = 1e300;
@@ -1382,7 +1537,7 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
   return best;
 }
 
-template <int BN, bool GEGLU, int CG>
+template <int BN, bool GEGLU, int CG, bool RS>
 static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t stream) {
   static bool configured_d[kMaxDevices] = {false};  // function attributes and occupancy are per device
   static int max_ctas_d[kMaxDevices] = {0};
@@ -1391,7 +1546,7 @@ static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t strea
   bool& configured = configured_d[dev];
   int& max_ctas = max_ctas_d[dev];
   if (!configured) {
-    ASVA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ASVA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU, CG, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kSmemLimit));
     max_ctas = g_num_sms;
     if (CG == 2) {  // how many CTA pairs the GPU can hold at once (GPCs with an odd SM count lose one)
@@ -1408,7 +1563,7 @@ static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t strea
       q.attrs = &at;
       q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, GEGLU, CG>, &q) == cudaSuccess && n > 0)
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, GEGLU, CG, RS>, &q) == cudaSuccess && n > 0)
         max_ctas = 2 * n;
       else
         max_ctas = g_num_sms / 2 * 2;
@@ -1418,19 +1573,19 @@ static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t strea
   }
   const int want = kp.total_tiles * CG;
   const int grid = want < max_ctas ? want : max_ctas;
-  ASVA_CUDA_OK(launch_k(gemm_tc_kernel<BN, GEGLU, CG>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, CG, kp));
+  ASVA_CUDA_OK(launch_k(gemm_tc_kernel<BN, GEGLU, CG, RS>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, CG, kp));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-template <int CG>
+template <int CG, bool RS>
 static int dispatch_gemm(const GemmKParams& kp, int bn, bool geglu, int smem, cudaStream_t stream) {
-  if (geglu) return launch_gemm<128, true, CG>(kp, smem, stream);
+  if (geglu) return launch_gemm<128, true, CG, RS>(kp, smem, stream);
   switch (bn) {
-    case 64: return launch_gemm<64, false, CG>(kp, smem, stream);
-    case 128: return launch_gemm<128, false, CG>(kp, smem, stream);
-    case 160: return launch_gemm<160, false, CG>(kp, smem, stream);
-    default: return launch_gemm<256, false, CG>(kp, smem, stream);
+    case 64: return launch_gemm<64, false, CG, RS>(kp, smem, stream);
+    case 128: return launch_gemm<128, false, CG, RS>(kp, smem, stream);
+    case 160: return launch_gemm<160, false, CG, RS>(kp, smem, stream);
+    default: return launch_gemm<256, false, CG, RS>(kp, smem, stream);
   }
 }
 
@@ -1492,6 +1647,7 @@ extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, in
         c.cta_group = cg;
         c.epilogue = epi;
         if (d->geglu && (bi != 1 || si != 0)) continue;
+        if (d->ln_cols > 0 && si != 0) continue;  // folded launches do not split K
         GemmPlan pl;
         if (compute_plan(&c, &pl) != 0) continue;
         if (pl.bn != c.block_n || pl.split != c.split_k || pl.cg != c.cta_group || pl.epi != epi) continue;  // not feasible
@@ -1609,6 +1765,12 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   ASVA_REQUIRE(d->add.ptr == nullptr || (d->add.ld % 4 == 0 && d->add.div >= 1),
                "asva_gemm: rowadd ld must be a multiple of 4 and div >= 1");
 
+  ASVA_REQUIRE(d->stats_out == nullptr || (!d->geglu && !d->out_fp32 && d->N % 32 == 0),
+               "asva_gemm: stats_out needs a bf16, non-GEGLU output with N %% 32 == 0 (N=%d)", d->N);
+  ASVA_REQUIRE(d->ln_cols == 0 || (d->ln_cols > 0 && d->ln_cols % 32 == 0 && d->ln_stats != nullptr &&
+                                   d->ln_wsum != nullptr && d->ln_stat_rows > 0 && d->ln_grp_rows >= 0),
+               "asva_gemm: LayerNorm fold needs ln_stats, ln_wsum, ln_stat_rows and ln_cols %% 32 == 0");
+
   const GemmPlan plan = plan_gemm(d, m_tiles, M, kb_total, n_res, g_num_sms);
   const int bn = plan.bn;
   const bool split = plan.split > 1;
@@ -1645,7 +1807,21 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
     kp.add_ptr = d->add.ptr;
     kp.add_ld = d->add.ld;
     kp.add_div = d->add.div > 0 ? d->add.div : 1;
+    kp.stats_out = d->stats_out;  // (a split launch leaves them to its reduce kernel)
+    kp.stats_rows = M;
   }
+  if (d->ln_cols > 0) {
+    ASVA_REQUIRE(!split && plan.epi != 2, "asva_gemm: LayerNorm fold with split-K / epilogue 2");
+    kp.ln_stats = d->ln_stats;
+    kp.ln_wsum = d->ln_wsum;
+    kp.ln_stat_rows = d->ln_stat_rows;
+    kp.ln_slots = d->ln_cols / 32;
+    kp.ln_grp_rows = d->ln_grp_rows;
+    kp.ln_grp_stride = d->ln_grp_stride;
+    kp.ln_inv_c = 1.0f / static_cast<float>(d->ln_cols);
+    kp.ln_eps = d->ln_eps;
+  }
+  ASVA_REQUIRE(d->stats_out == nullptr || plan.epi != 2, "asva_gemm: stats_out with epilogue 2");
 
   for (int src = 0; src < 2; ++src) {
     if (d->a[src] == nullptr) continue;
@@ -1732,8 +1908,11 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   kp.mn_tiles = (int)(((m_tiles + plan.cg - 1) / plan.cg) * kp.n_tiles_n);  // pairs of m tiles when cg == 2
   kp.total_tiles = kp.mn_tiles * plan.split;
   const int smem = smem_for(bn, plan.cg, plan.stages, kp.n_res_slots, kp.out_fp32);
-  const int rc = plan.cg == 2 ? dispatch_gemm<2>(kp, bn, d->geglu != 0, smem, stream)
-                              : dispatch_gemm<1>(kp, bn, d->geglu != 0, smem, stream);
+  const bool rowstat = kp.stats_out != nullptr || kp.ln_stats != nullptr;
+  const int rc = plan.cg == 2 ? (rowstat ? dispatch_gemm<2, true>(kp, bn, d->geglu != 0, smem, stream)
+                                         : dispatch_gemm<2, false>(kp, bn, d->geglu != 0, smem, stream))
+                              : (rowstat ? dispatch_gemm<1, true>(kp, bn, d->geglu != 0, smem, stream)
+                                         : dispatch_gemm<1, false>(kp, bn, d->geglu != 0, smem, stream));
 #ifdef ASVA_DEBUG_SWITCHES
   if (trace_on && rc == 0) {
     static long long h[12 * 64];
@@ -1759,7 +1938,8 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   ASVA_CUDA_OK(launch_k(splitk_finalize_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1,
                         reinterpret_cast<const float*>(d->ws), plan.split, M, d->N, d->bias, d->add.ptr, d->add.ld,
                         d->add.div > 0 ? d->add.div : 1, reinterpret_cast<const __nv_bfloat16*>(res[0]), res_ld[0],
-                        reinterpret_cast<const __nv_bfloat16*>(res[1]), res_ld[1], d->out, d->ldo, d->out_fp32));
+                        reinterpret_cast<const __nv_bfloat16*>(res[1]), res_ld[1], d->out, d->ldo, d->out_fp32,
+                        d->stats_out));
   ASVA_CUDA_OK(cudaGetLastError());
   return 0;
 }

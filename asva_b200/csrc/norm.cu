@@ -84,6 +84,98 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
 }
 
+// LayerNorm, sub-warp form: a row is held by 8, 16 or 32 lanes with NCH 16-byte chunks each (C = 8 * lanes * NCH - the
+// SD-1.5 widths 320 / 640 / 1280 are 5 chunks on 8 / 16 / 32 lanes), so a warp normalises 4 / 2 / 1 rows at a time
+// with every lane busy (the one-warp-per-row form above leaves 3/4 of the lanes idle on the second chunk of a
+// 320-wide row and gives each warp one row: ~12 us for the 24576 x 320 rows of a level-0 block, 2.6 TB/s).  gamma /
+// beta sit in shared memory (loaded before the dependent-launch wait), the warps loop over row groups with the next
+// group's loads issued before the current group's arithmetic, and the grid is sized for equal trip counts.
+template <int NCH>
+__global__ void __launch_bounds__(256, 2) layernorm_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta,
+                                                                const float* __restrict__ pos,
+                                                                __nv_bfloat16* __restrict__ out, int64_t M, int C,
+                                                                float eps, int N, int F, int lanes_log2) {
+  extern __shared__ float gb[];  // gamma[C] | beta[C]
+  pdl_trigger();
+  for (int i = threadIdx.x; i < (C >> 2); i += 256) {
+    reinterpret_cast<float4*>(gb)[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+    reinterpret_cast<float4*>(gb + C)[i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+  }
+  __syncthreads();
+  pdl_wait();
+  const int lanes = 1 << lanes_log2, rows_per_warp = 32 >> lanes_log2;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> lanes_log2, li = lane & (lanes - 1);
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * 8;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  int64_t grp = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  uint4 nxt[NCH];
+  auto fetch = [&](int64_t g) {
+    const int64_t row = g * rows_per_warp + sub;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      nxt[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row < M) nxt[i] = *reinterpret_cast<const uint4*>(x + row * C + (li + lanes * i) * 8);
+    }
+  };
+  if (grp * rows_per_warp < M) fetch(grp);
+  for (; grp * rows_per_warp < M; grp += n_warps) {  // warp-uniform trip count
+    const int64_t row = grp * rows_per_warp + sub;
+    float v[NCH][8];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const float2 a = unpack_bf16x2(nxt[i].x), b = unpack_bf16x2(nxt[i].y), c = unpack_bf16x2(nxt[i].z),
+                   d = unpack_bf16x2(nxt[i].w);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
+      v[i][4] = c.x; v[i][5] = c.y; v[i][6] = d.x; v[i][7] = d.y;
+    }
+    if ((grp + n_warps) * rows_per_warp < M) fetch(grp + n_warps);
+    if (pos != nullptr && row < M) {
+      const float* pr = pos + static_cast<int64_t>((row / N) % F) * C;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(pr + (li + lanes * i) * 8));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(pr + (li + lanes * i) * 8) + 1);
+        v[i][0] += p0.x; v[i][1] += p0.y; v[i][2] += p0.z; v[i][3] += p0.w;
+        v[i][4] += p1.x; v[i][5] += p1.y; v[i][6] += p1.z; v[i][7] += p1.w;
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    for (int o = lanes >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dlt = v[i][j] - mean;
+        sq = fmaf(dlt, dlt, sq);
+      }
+    for (int o = lanes >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+    if (row < M) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c0 = (li + lanes * i) * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(gb + c0), g1 = *reinterpret_cast<const float4*>(gb + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(gb + C + c0), b1 = *reinterpret_cast<const float4*>(gb + C + c0 + 4);
+        uint4 u;
+        u.x = pack_bf16x2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
+        u.y = pack_bf16x2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
+        u.z = pack_bf16x2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
+        u.w = pack_bf16x2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+        *reinterpret_cast<uint4*>(out + row * C + c0) = u;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics, two deterministic stages.
 //   stage 1: grid (splits, n_inst, cblocks); a CTA reduces a row range x a block of 8-channel chunks into
@@ -724,10 +816,30 @@ extern "C" int asva_layernorm(const void* x, const float* gamma, const float* be
   ASVA_REQUIRE(C % 8 == 0 && C >= 8 && C <= 8 * 32 * kLnMaxChunks, "asva_layernorm: C=%d unsupported", C);
   ASVA_REQUIRE(M >= 1, "asva_layernorm: M must be positive");
   ASVA_REQUIRE(pos == nullptr || (N >= 1 && F >= 1), "asva_layernorm: pos needs N, F");
-  const unsigned blocks = static_cast<unsigned>((M + 7) / 8);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
   const int n = N > 0 ? N : 1, f = F > 0 ? F : 1;
+  // sub-warp form: the fewest lanes per row (8, 16, 32) that hold the row in at most 5 chunks each
+  for (int ll = 3; ll <= 5; ++ll) {
+    const int lanes = 1 << ll;
+    if (C % (8 * lanes) != 0 || C / (8 * lanes) > 5) continue;
+    const int nch = C / (8 * lanes);
+    const int64_t groups = (M + (32 / lanes) - 1) / (32 / lanes);
+    const int64_t cap = static_cast<int64_t>(device_sms()) * 2 * 8;  // resident warps at 2 CTAs per SM
+    const int64_t iters = (groups + cap - 1) / cap;
+    const unsigned blocks = static_cast<unsigned>((groups + 8 * iters - 1) / (8 * iters));
+    const size_t smem = static_cast<size_t>(C) * 8;
+#define ASVA_LNR_CASE(K) \
+  case K: ASVA_CUDA_OK(launch_k(layernorm_rows_kernel<K>, dim3(blocks), dim3(256), smem, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f, ll)); break;
+    switch (nch) {
+      ASVA_LNR_CASE(1) ASVA_LNR_CASE(2) ASVA_LNR_CASE(3) ASVA_LNR_CASE(4)
+      default: ASVA_CUDA_OK(launch_k(layernorm_rows_kernel<5>, dim3(blocks), dim3(256), smem, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f, ll)); break;
+    }
+#undef ASVA_LNR_CASE
+    ASVA_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  const unsigned blocks = static_cast<unsigned>((M + 7) / 8);
 #define ASVA_LN_CASE(K) \
   case K: ASVA_CUDA_OK(launch_k(layernorm_kernel<K>, dim3(blocks), dim3(256), 0, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f)); break;
   switch ((C / 8 + 31) / 32) {

@@ -14,6 +14,7 @@ Cross-attention keys/values depend only on the clip's text/audio context, so `se
 clip; `pos_embedding_temp` depends only on F and is built in `prepare`.  All buffers are allocated in `prepare`, so
 `forward` performs no allocation and no host<->device traffic and can be captured in a CUDA graph."""
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -92,6 +93,9 @@ class UNetEngine:
         # Buffer generation: bumped whenever prepare() / set_context() (re)allocates device buffers.  Anything that
         # captured device addresses (CUDA graphs of the launch sequence) keys itself on it and re-captures on change.
         self.gen = 0
+        # LayerNorm fold (ops.LnFold): off by default - measured slower than the LayerNorm passes it removes (DESIGN.md
+        # section 5); ASVA_LN_FOLD=1 turns it on for A/B runs
+        self.fold_ln = os.environ.get("ASVA_LN_FOLD", "0") == "1"
         self._bufs: Dict[tuple, torch.Tensor] = {}
         self._ctx_bufs: Dict[tuple, torch.Tensor] = {}
         self._pack(sd)
@@ -102,6 +106,17 @@ class UNetEngine:
 
     def _bf(self, t):
         return t.float().to(self.dev, self.dt).contiguous()
+
+    def _fold_ln(self, w: torch.Tensor, bias: Optional[torch.Tensor], norm) -> tuple:
+        """LayerNorm(x; gamma, beta) W^T + bias = rstd * (x (W gamma)^T - mean * wsum) + (W beta + bias):
+        -> (W gamma in the activation dtype, wsum of exactly those rounded values, folded bias), see ops.LnFold."""
+        gamma, beta = norm
+        w = w.float().to(self.dev)
+        wg = (w * gamma.view(1, -1)).to(self.dt).contiguous()
+        fb = w @ beta
+        if bias is not None:
+            fb = fb + bias.float().to(self.dev)
+        return wg, wg.float().sum(1).contiguous(), fb.contiguous()
 
     def _pack_res(self, sd: SD, p: str) -> dict:
         r = dict(name=p, conv1=_Conv(sd, p + ".conv1", self.dev, self.dt), conv2=_Conv(sd, p + ".conv2", self.dev, self.dt),
@@ -131,12 +146,19 @@ class UNetEngine:
             a[n + ".o_w"] = self._bf(sd[f"{b}.{n}.to_out.0.weight"])
             a[n + ".o_b"] = self._f32(sd[f"{b}.{n}.to_out.0.bias"])
         a["attn_temp.qkv"] = torch.cat([a["attn_temp.q"], a["attn_temp.kv"]], 0).contiguous()
+        # LayerNorm folded into the projection behind it (ops.LnFold): W * gamma, its row sums, W beta (+ bias)
+        kv1 = torch.cat([sd[f"{b}.attn1.to_k.weight"].float(), sd[f"{b}.attn1.to_v.weight"].float()], 0)
+        a["attn1.qf"] = self._fold_ln(sd[f"{b}.attn1.to_q.weight"], None, a["norm1"])
+        a["attn1.kvf"] = self._fold_ln(kv1, None, a["norm1"])
+        a["attn_audio.qf"] = self._fold_ln(sd[f"{b}.attn_audio.to_q.weight"], None, a["norm_audio"])
+        a["attn2.qf"] = self._fold_ln(sd[f"{b}.attn2.to_q.weight"], None, a["norm2"])
         # GEGLU: every 128-column tile of the first FF GEMM holds [64 value | 64 gate] columns
         w1, b1 = sd[f"{b}.ff.net.0.proj.weight"].float(), sd[f"{b}.ff.net.0.proj.bias"].float()
         inner = w1.shape[0] // 2
         wv, wg = w1[:inner].view(inner // 64, 64, C), w1[inner:].view(inner // 64, 64, C)
         a["ff1_w"] = self._bf(torch.stack([wv, wg], dim=1).reshape(2 * inner, C))
         a["ff1_b"] = self._f32(torch.stack([b1[:inner].view(-1, 64), b1[inner:].view(-1, 64)], dim=1).reshape(-1))
+        a["ff1f"] = self._fold_ln(torch.stack([wv, wg], dim=1).reshape(2 * inner, C), a["ff1_b"], a["norm3"])
         a["ff2_w"], a["ff2_b"] = self._bf(sd[f"{b}.ff.net.2.weight"]), self._f32(sd[f"{b}.ff.net.2.bias"])
         a["pos1_w"], a["pos1_b"] = self._bf(sd[f"{b}.pos_embedding_temp.linear_1.weight"]), self._f32(sd[f"{b}.pos_embedding_temp.linear_1.bias"])
         a["pos2_w"], a["pos2_b"] = self._bf(sd[f"{b}.pos_embedding_temp.linear_2.weight"]), self._f32(sd[f"{b}.pos_embedding_temp.linear_2.bias"])
@@ -347,16 +369,32 @@ class UNetEngine:
         self._ffconv_tail(r["conv2"], y2, out, B, F, N, res1=res)
         return out
 
-    def _attention(self, a: dict, name: str, t, n, B, F, N, kv, G, R, nk, mask=None, mask_rows=1):
-        """t <- t + Wo softmax(Q K^T / sqrt(d)) V + bo   with Q = Wq n (head-split epilogue)."""
+    def _ln_fold(self, a: dict, key: str, st, **kw) -> "ops.LnFold":
+        _, wsum, _ = a[key]
+        return ops.LnFold(stats=st, wsum=wsum, cols=a["C"], eps=1e-5, **kw)
+
+    def _attention(self, a: dict, name: str, t, n, B, F, N, kv, G, R, nk, mask=None, mask_rows=1, st=None,
+                   emit=False):
+        """t <- t + Wo softmax(Q K^T / sqrt(d)) V + bo   with Q = Wq n (head-split epilogue).
+        st: the row statistics of t - then n is unused and Q = Wq LayerNorm(t) by the fold (ops.LnFold); emit: the
+        output projection leaves the statistics of the new t in st for the next sub-block."""
         be, C, d, dpad, H = self.be, a["C"], a["d"], a["dpad"], self.heads
         q = self.buf("attn_q", (B * F * N, C))
-        be.gemm(ops.spec_linear(n, a[name + ".q"], q))
+        if st is not None:
+            wq, _, bq = a[name + ".qf"]
+            sp = ops.spec_linear(t, wq, q, bias=bq)
+            sp.ln = self._ln_fold(a, name + ".qf", st)
+            be.gemm(sp)
+        else:
+            be.gemm(ops.spec_linear(n, a[name + ".q"], q))
         o = self.buf("attn_o", (B * F * N, C))
         be.attention(ops.AttnSpec(q=q, kv=kv, out=o, G=G, heads=H, R=R, Nk=nk, d=d, dpad=dpad, ldq=C, ldkv=2 * C, ldo=C,
                                   kv_rows_per_group=nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d), mask=mask,
                                   mask_ld=(mask.shape[1] if mask is not None else 0), mask_rows=mask_rows))
-        be.gemm(ops.spec_linear(o, a[name + ".o_w"], t, bias=a[name + ".o_b"], res0=t))
+        sp = ops.spec_linear(o, a[name + ".o_w"], t, bias=a[name + ".o_b"], res0=t)
+        if emit:
+            sp.stats_out = st
+        be.gemm(sp)
 
     def _transformer(self, a: dict, x, B, F, h, w, idx: int, out_tag: str):
         be, N, C = self.be, h * w, a["C"]
@@ -364,34 +402,58 @@ class UNetEngine:
         g = self.buf("gn_out", (M, C))
         be.groupnorm(x, C, None, 0, B * F, N, self.groups, 1e-6, a["gn_g"], a["gn_b"], False, g)
         t = self.buf("tok", (M, C))
-        be.gemm(ops.spec_linear(g, a["pi_w"], t, bias=a["pi_b"]))
         n = self.buf("ln_out", (M, C))
+        # LayerNorm fold (ops.LnFold): four of the block's five LayerNorms never run as a pass - the GEMM that writes
+        # the token rows t also leaves their row sums in st, and the projection behind the LayerNorm reads t itself.
+        # (norm_temp keeps its kernel: its input is t + pos, whose row sums the producer does not know.)
+        fold = self.fold_ln and C % 32 == 0
+        st = self.buf("ln_stats", (C // 32, M, 2), torch.float32) if fold else None
+        sp = ops.spec_linear(g, a["pi_w"], t, bias=a["pi_b"])
+        sp.stats_out = st
+        be.gemm(sp)
         # 1. first-frame spatial attention: K/V from the frame-0 rows only (utils.py:137-143)
-        be.layernorm(t, a["norm1"][0], a["norm1"][1], None, n, M, C, 1e-5, N, F)
         kv0 = self.buf("kv0", (B * N, 2 * C))
-        av = ops.AView(n, (C, N, B, 1), (C, F * N * C, B * F * N * C))
-        be.gemm(ops.spec_rows3(av, (N, B, 1), a["attn1.kv"], kv0))
-        self._attention(a, "attn1", t, n, B, F, N, kv0, B, F * N, N)
+        if fold:
+            av = ops.AView(t, (C, N, B, 1), (C, F * N * C, B * F * N * C))
+            wkv, _, bkv = a["attn1.kvf"]
+            sp = ops.spec_rows3(av, (N, B, 1), wkv, kv0, bias=bkv)
+            sp.ln = self._ln_fold(a, "attn1.kvf", st, grp_rows=N, grp_stride=F * N)
+            be.gemm(sp)
+        else:
+            be.layernorm(t, a["norm1"][0], a["norm1"][1], None, n, M, C, 1e-5, N, F)
+            av = ops.AView(n, (C, N, B, 1), (C, F * N * C, B * F * N * C))
+            be.gemm(ops.spec_rows3(av, (N, B, 1), a["attn1.kv"], kv0))
+        self._attention(a, "attn1", t, n, B, F, N, kv0, B, F * N, N, st=st, emit=fold)
         # 2./3. audio (masked) and text cross-attention onto the per-clip projected contexts
         for name, norm in (("attn_audio", "norm_audio"), ("attn2", "norm2")):
             cx = self.ctx[name]
-            be.layernorm(t, a[norm][0], a[norm][1], None, n, M, C, 1e-5, N, F)
+            if not fold:
+                be.layernorm(t, a[norm][0], a[norm][1], None, n, M, C, 1e-5, N, F)
             mask = self.ctx["mask"] if name == "attn_audio" else None
+            emit = fold and name == "attn_audio"  # attn2's output feeds norm_temp, which keeps its kernel
             if cx["inv"]:
-                self._attention(a, name, t, n, B, F, N, cx["kv"][idx], B, F * N, cx["nk"], mask, N)
+                self._attention(a, name, t, n, B, F, N, cx["kv"][idx], B, F * N, cx["nk"], mask, N, st=st, emit=emit)
             else:
-                self._attention(a, name, t, n, B, F, N, cx["kv"][idx], B * F, N, cx["nk"], mask, N)
+                self._attention(a, name, t, n, B, F, N, cx["kv"][idx], B * F, N, cx["nk"], mask, N, st=st, emit=emit)
         # 4. temporal attention per pixel; pos goes into the LayerNorm input only (:352-358)
         be.layernorm(t, a["norm_temp"][0], a["norm_temp"][1], a["pos"], n, M, C, 1e-5, N, F)
         qkv = self.buf("qkv_t", (M, 3 * C))
         be.gemm(ops.spec_linear(n, a["attn_temp.qkv"], qkv))
         o = self.buf("attn_o", (M, C))
         be.temporal_attention(qkv, o, B, F, N, self.heads, a["d"], 1.0 / math.sqrt(a["d"]))
-        be.gemm(ops.spec_linear(o, a["attn_temp.o_w"], t, bias=a["attn_temp.o_b"], res0=t))
+        sp = ops.spec_linear(o, a["attn_temp.o_w"], t, bias=a["attn_temp.o_b"], res0=t)
+        sp.stats_out = st
+        be.gemm(sp)
         # 5. GEGLU feed-forward
-        be.layernorm(t, a["norm3"][0], a["norm3"][1], None, n, M, C, 1e-5, N, F)
         ffh = self.buf("ff_h", (M, 4 * C))
-        be.gemm(ops.spec_linear(n, a["ff1_w"], ffh, bias=a["ff1_b"], geglu=True))
+        if fold:
+            w1, _, b1 = a["ff1f"]
+            sp = ops.spec_linear(t, w1, ffh, bias=b1, geglu=True)
+            sp.ln = self._ln_fold(a, "ff1f", st)
+            be.gemm(sp)
+        else:
+            be.layernorm(t, a["norm3"][0], a["norm3"][1], None, n, M, C, 1e-5, N, F)
+            be.gemm(ops.spec_linear(n, a["ff1_w"], ffh, bias=a["ff1_b"], geglu=True))
         be.gemm(ops.spec_linear(ffh, a["ff2_w"], t, bias=a["ff2_b"], res0=t))
         out = self.buf(out_tag, (M, C))
         be.gemm(ops.spec_linear(t, a["po_w"], out, bias=a["po_b"], res0=x))

@@ -45,6 +45,19 @@ class AView:
 
 
 @dataclass
+class LnFold:
+    """LayerNorm folded into the projection that follows it (asva_gemm_desc.ln_*): the GEMM runs on the un-normalised
+    rows with W * gamma and its epilogue applies rstd * (acc - mean * wsum) + (W beta + bias); mean / rstd come from
+    the per-slot row sums `stats` that the GEMM which produced the rows left (GemmSpec.stats_out)."""
+    stats: torch.Tensor   # fp32 [cols/32, rows, 2]: (sum, sum of squares) per 32-column slot
+    wsum: torch.Tensor    # fp32 [N]: sum_k (W gamma)[n, k] of the bf16 weight the GEMM reads
+    cols: int             # C, the normalised width (= K)
+    eps: float
+    grp_rows: int = 0     # output row r reads statistics row (r // grp_rows) * grp_stride + r % grp_rows (0: row r)
+    grp_stride: int = 0
+
+
+@dataclass
 class GemmSpec:
     a: List[Optional[AView]]
     box: Tuple[int, int, int]
@@ -67,7 +80,9 @@ class GemmSpec:
     block_n: int = 0    # 0 = let the library choose (cost model); the engine's tuner sets measured choices
     split_k: int = 0
     cta_group: int = 0
-    epilogue: int = 0   # 0 = auto, 1 = panel (TMA) epilogue, 2 = per-warp (direct) epilogue
+    epilogue: int = 0   # 0 = auto, 1 = panel (TMA) epilogue, 2 = per-warp (direct) epilogue, 3 = warp-private TMA
+    ln: Optional[LnFold] = None
+    stats_out: Optional[torch.Tensor] = None  # fp32 [N/32, M, 2]: row sums of what this GEMM stores (for a later LnFold)
 
     def __post_init__(self):
         k = 0
@@ -306,7 +321,8 @@ class CudaBackend:
     def gemm_signature(s: GemmSpec) -> tuple:
         return (s.box, s.trav, s.out_dims, tuple((g.src, g.num_kb, g.off, g.wk_first >= 0, g.fix2) for g in s.segs),
                 s.N, s.K, s.bias is not None, s.add is not None, sum(r is not None for r in s.res), s.geglu,
-                s.out_fp32, tuple(None if a is None else a.dims for a in s.a))
+                s.out_fp32, tuple(None if a is None else a.dims for a in s.a), s.ln is not None,
+                s.stats_out is not None)
 
     def gemm(self, s: GemmSpec) -> None:
         if s.block_n == 0 and s.split_k == 0 and s.cta_group == 0 and s.epilogue == 0:
@@ -378,6 +394,19 @@ class CudaBackend:
         d.block_n, d.split_k, d.cta_group, d.epilogue = s.block_n, s.split_k, s.cta_group, s.epilogue
         ws = self.splitk_ws()
         d.ws, d.ws_bytes = ws.data_ptr(), ws.numel() * 4
+        if s.stats_out is not None:
+            self._chk_dev(s.stats_out)
+            assert s.stats_out.dtype == torch.float32 and s.stats_out.is_contiguous()
+            assert s.N % 32 == 0 and s.stats_out.numel() >= (s.N // 32) * s.M * 2
+            d.stats_out = s.stats_out.data_ptr()
+        if s.ln is not None:
+            f = s.ln
+            self._chk_dev(f.stats, f.wsum)
+            assert f.stats.dtype == torch.float32 and f.wsum.dtype == torch.float32 and f.wsum.numel() >= s.N
+            assert f.cols % 32 == 0 and f.stats.dim() == 3 and f.stats.shape[0] == f.cols // 32 and f.stats.shape[2] == 2
+            assert f.stats.is_contiguous()
+            d.ln_cols, d.ln_stats, d.ln_wsum = f.cols, f.stats.data_ptr(), f.wsum.data_ptr()
+            d.ln_stat_rows, d.ln_grp_rows, d.ln_grp_stride, d.ln_eps = f.stats.shape[1], f.grp_rows, f.grp_stride, f.eps
         return d
 
     def attention(self, s: AttnSpec) -> None:

@@ -77,7 +77,8 @@ typedef struct asva_gemm_desc {
   int32_t wcols; /* columns of W that exist (>= every seg.wk + 64*num_kb) */
   int32_t cta_group; /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pairs (tcgen05 cta_group::2: 256-row tiles,
                         each CTA of the pair loads half of the W tile) */
-  /* epilogue: out = acc + bias[col] + add + res[0] + res[1]   (GEGLU: (h + bias_h) * gelu_erf(g + bias_g)) */
+  /* epilogue: out = acc + bias[col] + add + res[0] + res[1]   (GEGLU: (h + bias_h) * gelu_erf(g + bias_g));
+   * with the LayerNorm fold (ln_cols below) acc is replaced by rstd_row * (acc - mean_row * ln_wsum[col]) */
   const float* bias; /* [N] fp32 or NULL */
   asva_rowadd add;
   const void* res[2]; /* bf16 residuals res[i][row * res_ld[i] + col]; NULL = disabled; may alias out */
@@ -97,6 +98,25 @@ typedef struct asva_gemm_desc {
                        3 = warp-private TMA epilogue (each of the eight epilogue warps moves the 32 rows of its TMEM
                        quadrant with its own TMA loads / stores, no block-level barrier; any output type; needs a
                        row box whose 32-row quadrants are themselves boxes - otherwise 1 is used) */
+  /* Row statistics and the LayerNorm fold (ff_spatio_audio_temp_transformer_3d.py:288-362: every sub-block of a
+   * BasicTransformerBlock is LayerNorm -> projection).  With W' = W * gamma (column scaling, folded into the packed
+   * weight), wsum[n] = sum_k W'[n][k] and bias' = W beta + bias,
+   *     LayerNorm(x) W^T + bias  =  rstd_r * (x W'^T - mean_r * wsum) + bias'
+   * so the projection runs on the un-normalised rows and the epilogue applies the two per-row scalars - no separate
+   * LayerNorm pass.  The per-row sums come from the GEMM that produced x: with stats_out set, a GEMM also writes, for
+   * every output row and every 32-column slot, (sum, sum of squares) of the fp32 values it stores:
+   *     stats[slot][row][2] fp32, slot = col / 32, row as in out_dims (N % 32 == 0; not with GEGLU / fp32 outputs).
+   * A consumer names such a table in ln_stats; its output row r reads statistics row
+   *     (r / ln_grp_rows) * ln_grp_stride + r % ln_grp_rows      (ln_grp_rows = 0: row r)
+   * and sums the ln_cols / 32 slots in order (deterministic).  ln_cols = 0 turns the fold off.  Folded launches do
+   * not split K and use epilogue form 1 or 3. */
+  int32_t ln_cols;        /* width C of the rows the statistics describe (the K of this GEMM); 0 = off */
+  float* stats_out;       /* [N/32][M][2] fp32 or NULL */
+  const float* ln_stats;  /* [ln_cols/32][ln_stat_rows][2] fp32 */
+  const float* ln_wsum;   /* [N] fp32 */
+  int64_t ln_stat_rows;
+  int32_t ln_grp_rows, ln_grp_stride;
+  float ln_eps;
   int32_t reserved;
 } asva_gemm_desc;
 

@@ -63,6 +63,17 @@ class SimBackend:
         M = acc.shape[0]
         dev = acc.device
         rows = torch.arange(M, device=dev)
+        if s.ln is not None:  # LayerNorm fold: rstd * (acc - mean * wsum); the column terms follow as usual
+            f = s.ln
+            sr = rows if f.grp_rows == 0 else (rows // f.grp_rows) * f.grp_stride + rows % f.grp_rows
+            st = f.stats.float()[:, sr, :]
+            sm, sq = st[..., 0], st[..., 1]
+            tot, tot2 = torch.zeros_like(sm[0]), torch.zeros_like(sq[0])
+            for i in range(st.shape[0]):  # slot order, like the kernel
+                tot, tot2 = tot + sm[i], tot2 + sq[i]
+            mean = tot / f.cols
+            rstd = torch.rsqrt((tot2 / f.cols - mean * mean).clamp_min(0.0) + f.eps)
+            acc = rstd.view(-1, 1) * (acc - mean.view(-1, 1) * f.wsum[: s.N].float().view(1, -1))
         if s.geglu:
             assert s.N % 128 == 0
             if s.bias is not None:
@@ -85,6 +96,11 @@ class SimBackend:
                 idx = (rows * ld).view(-1, 1) + colsN.view(1, -1)
                 val = val + _flat(r)[idx].float()
             n_out = s.N
+            if s.stats_out is not None:  # (sum, sum of squares) of the fp32 values per row and 32-column slot
+                assert s.N % 32 == 0
+                v32 = val.float().view(M, s.N // 32, 32)
+                st = torch.stack([v32.sum(-1), (v32 * v32).sum(-1)], dim=-1).permute(1, 0, 2)
+                s.stats_out.view(-1)[: st.numel()].copy_(st.reshape(-1))
         cols = torch.arange(n_out, device=dev)
         off = (rows * s.ldo).view(-1, 1) + cols.view(1, -1)
         outf = _flat(s.out)

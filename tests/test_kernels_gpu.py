@@ -96,6 +96,129 @@ def test_gemm_two_sources(cuda_backend):
     _report("linear 2-source", got, ref, 4e-3)
 
 
+# ---- row statistics + LayerNorm fold (asva_gemm_desc.stats_out / ln_*, ops.LnFold)
+def _stats_of(x32, C):
+    v = x32.view(x32.shape[0], C // 32, 32)
+    return torch.stack([v.sum(-1), (v * v).sum(-1)], dim=-1).permute(1, 0, 2).contiguous()
+
+
+@pytest.mark.parametrize("M,K,N,bn,cg,split,epi", [
+    (256, 320, 320, 0, 1, 1, 1), (256, 320, 320, 0, 1, 1, 3), (1000, 640, 640, 128, 2, 1, 3), (1000, 640, 640, 128, 2, 1, 1),
+    (300, 320, 320, 160, 1, 1, 3), (24576, 320, 320, 160, 1, 1, 3), (384, 5120, 1280, 64, 1, 2, 3),
+    (384, 5120, 1280, 128, 1, 4, 1), (1536, 1280, 1280, 256, 2, 1, 3), (16, 1280, 1280, 64, 1, 1, 3),
+    (1536, 1280, 1280, 128, 1, 1, 2),
+])
+def test_gemm_row_stats_out(cuda_backend, M, K, N, bn, cg, split, epi):
+    """The producer side: (sum, sum of squares) per row and 32-column slot of the fp32 values the GEMM stores, in
+    every epilogue form that carries it (a request for form 2 is served by 3), the split-K reduce kernel included."""
+    x = _rand((M, K), 301)
+    w = _rand((N, K), 302, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 303, dtype=torch.float32)
+    res = _rand((M, N), 304)
+    spec = ops.spec_linear(x, w, torch.empty(M, N, dtype=torch.bfloat16, device=DEV), bias=bias, res0=res)
+    spec.block_n, spec.cta_group, spec.split_k, spec.epilogue = bn, cg, split, epi
+    st_ref = torch.zeros(N // 32, M, 2, dtype=torch.float32, device=DEV)
+    st_cu = torch.full((N // 32, M, 2), 123.0, dtype=torch.float32, device=DEV)
+    o_ref = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    o_cu = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    SimBackend().gemm(dataclasses.replace(spec, out=o_ref, stats_out=st_ref))
+    sp = dataclasses.replace(spec, out=o_cu, stats_out=st_cu)
+    pl = cuda_backend.gemm_plan(sp)
+    assert pl[4] != 2 and pl[1] == split, pl
+    cuda_backend.gemm(sp)
+    torch.cuda.synchronize()
+    _report(f"stats-out gemm {M}x{K}x{N}", o_cu, o_ref, 4e-3)
+    _report(f"row sums {M}x{K}x{N} plan {pl}", st_cu[..., 0], st_ref[..., 0], 1e-4)
+    _report(f"row sums of squares {M}x{K}x{N} plan {pl}", st_cu[..., 1], st_ref[..., 1], 1e-5)
+
+
+@pytest.mark.parametrize("M,C,N,bn,cg,epi,bias", [
+    (256, 320, 320, 0, 1, 1, False), (256, 320, 320, 0, 1, 3, False), (24576, 320, 320, 160, 1, 3, False),
+    (24576, 320, 320, 160, 1, 1, True), (1000, 640, 640, 128, 2, 3, True), (1000, 640, 1280, 256, 2, 1, False),
+    (1536, 1280, 1280, 128, 1, 3, False), (300, 320, 960, 64, 1, 3, True), (16, 1280, 1280, 64, 1, 0, False),
+])
+def test_gemm_ln_fold(cuda_backend, M, C, N, bn, cg, epi, bias):
+    """The consumer side against LayerNorm -> projection computed directly: rows with a large common offset (mean /
+    std ~ 3) so the mean term matters."""
+    g = torch.Generator(device="cpu").manual_seed(311)
+    x32 = (torch.randn(M, C, generator=g) * (0.5 + torch.rand(M, 1, generator=g)) + 3.0 * torch.randn(M, 1, generator=g))
+    x = x32.to(torch.bfloat16).to(DEV)
+    gamma = (1.0 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    w32 = (torch.randn(N, C, generator=g) / math.sqrt(C)).to(DEV)
+    b32 = torch.randn(N, generator=g).to(DEV) if bias else None
+    wg = (w32 * gamma.view(1, -1)).to(torch.bfloat16).contiguous()
+    wsum = wg.float().sum(1).contiguous()
+    fb = w32 @ beta + (b32 if bias else 0.0)
+    st = _stats_of(x.float(), C)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    spec = ops.spec_linear(x, wg, out, bias=fb.contiguous())
+    spec.ln = ops.LnFold(stats=st, wsum=wsum, cols=C, eps=1e-5)
+    spec.block_n, spec.cta_group, spec.epilogue = bn, cg, epi
+    pl = cuda_backend.gemm_plan(spec)
+    assert pl[1] == 1 and pl[4] in (1, 3) and (epi == 0 or pl[4] == epi), pl
+    cuda_backend.gemm(spec)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w32.t() + (b32 if bias else 0.0)
+    sim = torch.zeros_like(out)
+    SimBackend().gemm(dataclasses.replace(spec, out=sim))
+    _report(f"ln-fold vs sim {M}x{C}x{N} plan {pl}", out, sim, 4e-3)
+    # against the unfolded computation: bf16 rounding of W*gamma and of the output
+    _report(f"ln-fold vs LayerNorm->linear {M}x{C}x{N}", out, ref, 6e-3)
+
+
+@pytest.mark.parametrize("epi", [1, 3])
+def test_gemm_ln_fold_geglu(cuda_backend, epi):
+    M, C = 384, 640
+    g = torch.Generator(device="cpu").manual_seed(312)
+    x = (torch.randn(M, C, generator=g) + 2.0 * torch.randn(M, 1, generator=g)).to(torch.bfloat16).to(DEV)
+    gamma, beta = (1.0 + 0.2 * torch.randn(C, generator=g)).to(DEV), (0.1 * torch.randn(C, generator=g)).to(DEV)
+    w32 = (torch.randn(8 * C, C, generator=g) / math.sqrt(C)).to(DEV)
+    b32 = torch.randn(8 * C, generator=g).to(DEV)
+    wg = (w32 * gamma.view(1, -1)).to(torch.bfloat16).contiguous()
+    out = torch.zeros(M, 4 * C, dtype=torch.bfloat16, device=DEV)
+    spec = ops.spec_linear(x, wg, out, bias=(w32 @ beta + b32).contiguous(), geglu=True)
+    spec.ln = ops.LnFold(stats=_stats_of(x.float(), C), wsum=wg.float().sum(1).contiguous(), cols=C, eps=1e-5)
+    spec.epilogue = epi
+    assert cuda_backend.gemm_plan(spec)[4] == epi
+    cuda_backend.gemm(spec)
+    torch.cuda.synchronize()
+    y = (torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w32.t() + b32).view(M, -1, 2, 64)
+    ref = (y[:, :, 0] * torch.nn.functional.gelu(y[:, :, 1])).reshape(M, 4 * C)
+    sim = torch.zeros_like(out)
+    SimBackend().gemm(dataclasses.replace(spec, out=sim))
+    _report(f"ln-fold geglu vs sim epi{epi}", out, sim, 4e-3)
+    _report(f"ln-fold geglu vs LayerNorm->GEGLU epi{epi}", out, ref, 8e-3)
+
+
+def test_gemm_ln_fold_grouped_rows_chain(cuda_backend):
+    """Producer -> consumer on the device, with the consumer reading the statistics of a strided row subset (the
+    frame-0 rows feeding attn1's K/V projection): t = x W0^T + b (+ statistics), kv = LayerNorm(t)[frame 0] Wkv^T."""
+    B, F, N, C = 2, 3, 64, 320
+    M = B * F * N
+    g = torch.Generator(device="cpu").manual_seed(313)
+    x = _rand((M, C), 314)
+    w0 = _rand((C, C), 315, 1.0 / math.sqrt(C))
+    b0 = (2.0 * torch.randn(C, generator=g)).to(DEV)
+    gamma, beta = (1.0 + 0.2 * torch.randn(C, generator=g)).to(DEV), (0.1 * torch.randn(C, generator=g)).to(DEV)
+    wkv32 = (torch.randn(2 * C, C, generator=g) / math.sqrt(C)).to(DEV)
+    t = torch.zeros(M, C, dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(C // 32, M, 2, dtype=torch.float32, device=DEV)
+    sp = ops.spec_linear(x, w0, t, bias=b0)
+    sp.stats_out = st
+    cuda_backend.gemm(sp)
+    wg = (wkv32 * gamma.view(1, -1)).to(torch.bfloat16).contiguous()
+    kv = torch.zeros(B * N, 2 * C, dtype=torch.bfloat16, device=DEV)
+    av = ops.AView(t, (C, N, B, 1), (C, F * N * C, B * F * N * C))
+    sk = ops.spec_rows3(av, (N, B, 1), wg, kv, bias=(wkv32 @ beta).contiguous())
+    sk.ln = ops.LnFold(stats=st, wsum=wg.float().sum(1).contiguous(), cols=C, eps=1e-5, grp_rows=N, grp_stride=F * N)
+    cuda_backend.gemm(sk)
+    torch.cuda.synchronize()
+    t0 = t.view(B, F, N, C)[:, 0].reshape(B * N, C).float()
+    ref = torch.nn.functional.layer_norm(t0, (C,), gamma, beta, 1e-5) @ wkv32.t()
+    _report("chained ln-fold on frame-0 rows", kv, ref, 6e-3)
+
+
 @pytest.mark.parametrize("M,C", [(256, 320), (384, 640), (200, 1280)])
 @pytest.mark.parametrize("epi", [1, 3])
 def test_gemm_geglu(cuda_backend, M, C, epi):
@@ -297,8 +420,13 @@ def test_temporal_attention(cuda_backend, B, F, N, heads, d):
 
 
 # ------------------------------------------------------------------------------------------------ norms
-@pytest.mark.parametrize("M,C,with_pos", [(1000, 320, False), (513, 640, True), (96, 1280, True)])
+@pytest.mark.parametrize("M,C,with_pos", [(1000, 320, False), (513, 640, True), (96, 1280, True), (24576, 320, True),
+                                          (6144, 640, False), (1537, 1280, False), (7, 320, False), (301, 64, True),
+                                          (130, 128, False), (77, 256, True), (50, 768, False), (33, 1024, True),
+                                          (21, 2048, False), (40, 72, False)])
 def test_layernorm(cuda_backend, M, C, with_pos):
+    # sub-warp kernel: 8 / 16 / 32 lanes per row x 1..5 chunks (C = 64 .. 1280, ragged row counts); C = 2048 and 72
+    # take the one-warp-per-row kernel
     N, F = 3, 4
     x = _rand((M, C), 60, 3.0)
     g, b = _rand((C,), 61, dtype=torch.float32), _rand((C,), 62, dtype=torch.float32)
