@@ -748,6 +748,31 @@ extern "C" int asva_temporal_attention(const void* qkv, void* out, int32_t B, in
   ASVA_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "asva_temporal_attention: head dim %d unsupported", d);
   ASVA_REQUIRE(B >= 1 && N >= 1 && heads >= 1 && F >= 1 && F <= 64, "asva_temporal_attention: bad shape (F=%d)", F);
   ASVA_REQUIRE(scale > 0.f, "asva_temporal_attention: scale must be positive");
+  // memory-bound form (misc.cu) for every shape it serves; the tcgen05 form below for the rest (F > 32, huge C * F)
+  const int rc = temporal_attention_rows(qkv, out, B, F, N, heads, d, scale, stream, false);
+  if (rc != 1) return rc;
+  return asva_temporal_attention_tc(qkv, out, B, F, N, heads, d, scale, stream_);
+}
+
+extern "C" int asva_temporal_attention_rows(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                            int32_t d, float scale, asva_stream_t stream_) {
+  using namespace asva;
+  ASVA_REQUIRE(qkv && out, "asva_temporal_attention_rows: null operand");
+  ASVA_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192 && B >= 1 && N >= 1 && heads >= 1 && F >= 1 && scale > 0.f,
+               "asva_temporal_attention_rows: bad shape");
+  const int rc = temporal_attention_rows(qkv, out, B, F, N, heads, d, scale, reinterpret_cast<cudaStream_t>(stream_), true);
+  ASVA_REQUIRE(rc != 1, "asva_temporal_attention_rows: shape not served (F=%d, C=%d)", F, heads * d);
+  return rc;
+}
+
+extern "C" int asva_temporal_attention_tc(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                          int32_t d, float scale, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ASVA_REQUIRE(qkv && out, "asva_temporal_attention: null operand");
+  ASVA_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "asva_temporal_attention: head dim %d unsupported", d);
+  ASVA_REQUIRE(B >= 1 && N >= 1 && heads >= 1 && F >= 1 && F <= 64, "asva_temporal_attention: bad shape (F=%d)", F);
+  ASVA_REQUIRE(scale > 0.f, "asva_temporal_attention: scale must be positive");
   const int C = heads * d;
   const int dka = (d + 63) / 64;
   const int kv = (dka == 1) ? 128 : 64;

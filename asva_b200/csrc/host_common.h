@@ -77,4 +77,9 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     if (!(cond)) return ::asva::fail(ASVA_ERR_INVALID, __VA_ARGS__);   \
   } while (0)
 
+// misc.cu: the memory-bound temporal attention; 0 = launched, 1 = shape not served by it (force: not served at all;
+// else: also the shapes where the tcgen05 form measured faster), other = error code
+int temporal_attention_rows(const void* qkv, void* out, int B, int F, int N, int H, int d, float scale,
+                            cudaStream_t stream, bool force);
+
 }  // namespace asva

@@ -281,6 +281,166 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Temporal self-attention over the frame axis, memory-bound form (ff_spatio_audio_temp_transformer_3d.py:343-360: every
+// pixel attends over its own F frames; F^2 * d MACs per pixel and head against 4 * C * F bytes of q / k / v / out).
+// The tcgen05 form (attn_tc.cu) spends a 128-row MMA tile on 10 pixels x 12 frames and runs at ~1.1 TB/s; here a CTA
+// owns P consecutive pixels of one clip: the F row slabs [P][3C] (contiguous in qkv) arrive by bulk-async copies on one
+// mbarrier, one thread per (pixel, head, query frame) computes its F scores and its d outputs in fp32 straight from
+// shared memory (lanes of the same pixel and head read identical K / V addresses: broadcasts), overwrites its own q
+// slot with the bf16 output, and the F * P output rows leave by bulk-async stores.  Several CTAs per SM keep loads,
+// arithmetic and stores of different pixel groups overlapped.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+template <int FT>  // frames rounded up (loops over frames unroll, scores stay in registers)
+__global__ void __launch_bounds__(512) temporal_rows_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            __nv_bfloat16* __restrict__ out, int F, int N, int H, int d,
+                                                            int P, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t tsm[];
+  const int C = H * d;
+  const uint32_t row_bytes = static_cast<uint32_t>(3 * C) * 2u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tsm + static_cast<size_t>(F) * P * row_bytes);
+  const int gpb = (N + P - 1) / P;
+  const int b = blockIdx.x / gpb;
+  const int n0 = (blockIdx.x - b * gpb) * P;
+  const int pe = min(P, N - n0);
+  const uint32_t base = smem_u32(tsm);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(F * pe) * row_bytes);
+    for (int f = 0; f < F; ++f)
+      bulk_load_1d(base + static_cast<uint32_t>(f * P) * row_bytes,
+                   qkv + (static_cast<int64_t>(b * F + f) * N + n0) * 3 * C, static_cast<uint32_t>(pe) * row_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  const int item = threadIdx.x;
+  if (item < pe * H * F) {
+    const int fq = item % F, ph = item / F;
+    const int h = ph % H, p = ph / H;
+    const uint32_t qa = base + static_cast<uint32_t>(fq * P + p) * row_bytes + static_cast<uint32_t>(h * d) * 2u;
+    const uint32_t ka = base + static_cast<uint32_t>(p) * row_bytes + static_cast<uint32_t>(C + h * d) * 2u;
+    const uint32_t va = ka + static_cast<uint32_t>(C) * 2u;
+    const uint32_t fstride = static_cast<uint32_t>(P) * row_bytes;
+    float s[FT];
+#pragma unroll
+    for (int j = 0; j < FT; ++j) s[j] = 0.f;
+    for (int c = 0; c < d; c += 8) {
+      float q[8];
+      bf16x8_to_f32(lds128(qa + c * 2), q);
+#pragma unroll
+      for (int j = 0; j < FT; ++j) {
+        if (j < F) {
+          float k[8];
+          bf16x8_to_f32(lds128(ka + j * fstride + c * 2), k);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s[j] = fmaf(q[e], k[e], s[j]);
+        }
+      }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < FT; ++j)
+      if (j < F) m = fmaxf(m, s[j]);
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < FT; ++j) {
+      s[j] = (j < F) ? exp2f((s[j] - m) * scale_log2) : 0.f;
+      l += s[j];
+    }
+    const float inv = 1.0f / l;
+    for (int c = 0; c < d; c += 8) {
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < FT; ++j) {
+        if (j < F) {
+          float v[8];
+          bf16x8_to_f32(lds128(va + j * fstride + c * 2), v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = fmaf(s[j], v[e], o[e]);
+        }
+      }
+      // the output takes the place of this thread's own q chunk (nobody else reads it)
+      st_shared_v4(qa + c * 2, pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
+                   pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
+    }
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * pe; i += blockDim.x) {
+    const int f = i / pe, p = i - f * pe;
+    bulk_store_1d(out + (static_cast<int64_t>(b * F + f) * N + n0 + p) * C,
+                  base + static_cast<uint32_t>(f * P + p) * row_bytes, static_cast<uint32_t>(C) * 2u);
+  }
+  bulk_commit();
+  bulk_wait_read<0>();
+}
+
+template <int FT>
+static int launch_temporal_rows(const void* qkv, void* out, int B, int F, int N, int H, int d, int P, float scale,
+                                int threads, size_t smem, cudaStream_t stream) {
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    ASVA_CUDA_OK(cudaFuncSetAttribute(temporal_rows_kernel<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[dev] = true;
+  }
+  const unsigned grid = static_cast<unsigned>(B) * static_cast<unsigned>((N + P - 1) / P);
+  ASVA_CUDA_OK(launch_k(temporal_rows_kernel<FT>, dim3(grid), dim3(threads), smem, stream, 1,
+                        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), F, N, H, d, P,
+                        scale * 1.4426950408889634f));
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// -> 0 launched, < 0 error, 1 = shape not served by this form (the caller uses the tcgen05 kernel)
+int temporal_attention_rows(const void* qkv, void* out, int B, int F, int N, int H, int d, float scale,
+                            cudaStream_t stream, bool force) {
+  const int C = H * d;
+  const int64_t slab = static_cast<int64_t>(F) * 3 * C * 2;  // one pixel: F rows of q | k | v
+  if (F > 32 || H * F > 512 || slab + 16 > 200 * 1024 || static_cast<int64_t>(B) * N > (1ll << 30)) return 1;
+  // Measured (tools/temporal_probe.py, profiles/r2_temporal_probe.md): one thread per (pixel, head, query) wins for
+  // short heads and clips (d = 40: 32.9 vs 55.9 us at 12 frames x 1024 px); with d >= 80 a thread's serial dot
+  // products, with F > 16 its F^2 growth, make the tcgen05 form the faster one.
+  if (!force && (d > 40 || F > 16)) return 1;
+  int P = static_cast<int>((56 * 1024) / slab);  // ~4 CTAs per SM
+  if (P < 1) P = 1;
+  if (P > 4) P = 4;
+  while (P > 1 && P * H * F > 512) --P;
+  if (P > N) P = N;
+  const int threads = ((P * H * F + 31) / 32) * 32;
+  const size_t smem = static_cast<size_t>(P) * slab + 16;
+  if (F <= 8) return launch_temporal_rows<8>(qkv, out, B, F, N, H, d, P, scale, threads, smem, stream);
+  if (F <= 12) return launch_temporal_rows<12>(qkv, out, B, F, N, H, d, P, scale, threads, smem, stream);
+  if (F <= 16) return launch_temporal_rows<16>(qkv, out, B, F, N, H, d, P, scale, threads, smem, stream);
+  if (F <= 24) return launch_temporal_rows<24>(qkv, out, B, F, N, H, d, P, scale, threads, smem, stream);
+  return launch_temporal_rows<32>(qkv, out, B, F, N, H, d, P, scale, threads, smem, stream);
+}
+
 }  // namespace asva
 
 extern "C" int asva_softmax_rows(const float* scores, int64_t lds, void* probs, int64_t ldp, int64_t rows,

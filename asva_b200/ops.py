@@ -421,11 +421,14 @@ class CudaBackend:
             _lib.check(self.lib.asva_attention(d, self._stream()), "asva_attention")
         self.launches += 1
 
-    def temporal_attention(self, qkv, out, B, F, N, heads, d, scale) -> None:
+    def temporal_attention(self, qkv, out, B, F, N, heads, d, scale, tc: Optional[bool] = None) -> None:
+        """tc=True / False: the tcgen05 / the memory-bound form by name (None: the entry point that picks per shape)."""
         self._chk_dev(qkv, out)
+        fn = (self.lib.asva_temporal_attention if tc is None else
+              self.lib.asva_temporal_attention_tc if tc else self.lib.asva_temporal_attention_rows)
         with self._timed('temporal_attention'):
-            _lib.check(self.lib.asva_temporal_attention(qkv.data_ptr(), out.data_ptr(), B, F, N, heads, d, scale,
-                                                    self._stream()), "asva_temporal_attention")
+            _lib.check(fn(qkv.data_ptr(), out.data_ptr(), B, F, N, heads, d, scale, self._stream()),
+                       "asva_temporal_attention")
         self.launches += 1
 
     def layernorm(self, x, gamma, beta, pos, out, M, C, eps, N, F) -> None:

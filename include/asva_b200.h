@@ -161,12 +161,22 @@ typedef struct asva_attn_desc {
 
 int asva_attention(const asva_attn_desc* d, asva_stream_t stream);
 
-/* Temporal self-attention core over the frame axis (F x F per pixel and head) on tcgen05: blocks of floor(KV/F)
- * pixels x F frames are queries and keys of one block-diagonal tile, gathered by 5-D TMA boxes (attn_tc.cu).
+/* Temporal self-attention core over the frame axis (F x F per pixel and head).
  * Replaces the SDPA inside attn_temp (ff_spatio_audio_temp_transformer_3d.py:352-358).
- *   qkv : bf16 [B][F][N][3C] (q | k | v), out: bf16 [B][F][N][C] */
+ *   qkv : bf16 [B][F][N][3C] (q | k | v), out: bf16 [B][F][N][C]
+ * The op moves 8 C F bytes per pixel for 4 F^2 C flops - memory-bound - so the default form (misc.cu) streams each
+ * pixel group's q | k | v rows into shared memory with bulk-async copies and computes in fp32 on the CUDA cores, one
+ * thread per (pixel, head, query frame); wider heads and longer clips (d > 40 or F > 16, where a thread's serial
+ * dot products dominate) and shapes it does not serve take the tcgen05 form.  asva_temporal_attention_tc is that tcgen05 form by name: blocks of floor(KV/F) pixels x F frames are
+ * queries and keys of one block-diagonal tile, gathered by 5-D TMA boxes (attn_tc.cu). */
 int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
                             int32_t d, float scale, asva_stream_t stream);
+int asva_temporal_attention_tc(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                               int32_t d, float scale, asva_stream_t stream);
+/* the memory-bound form by name (F <= 32, F * 6C bytes within shared memory; ASVA_ERR_INVALID otherwise).  The default
+ * entry point uses it where it measured faster than the tcgen05 form: d <= 40 and F <= 16. */
+int asva_temporal_attention_rows(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                 int32_t d, float scale, asva_stream_t stream);
 
 /* LayerNorm over C (eps, affine) of x[M][C] (+ optional positional rows pos[F][C] added BEFORE the norm, frame
  * index = (row / N) % F) -> bf16.  Replaces nn.LayerNorm norm1/norm_audio/norm2/norm_temp/norm3

@@ -407,14 +407,22 @@ def test_attention_large_scores(cuda_backend):
     _report("attention rescale", out_cu, out_ref, 1e-2)
 
 
-@pytest.mark.parametrize("B,F,N,heads,d", [(2, 12, 64, 8, 40), (1, 8, 16, 8, 160), (2, 24, 33, 8, 80), (1, 1, 8, 8, 40)])
-def test_temporal_attention(cuda_backend, B, F, N, heads, d):
+@pytest.mark.parametrize("B,F,N,heads,d", [(2, 12, 64, 8, 40), (1, 8, 16, 8, 160), (2, 24, 33, 8, 80), (1, 1, 8, 8, 40),
+                                           (2, 12, 1024, 8, 40), (2, 12, 256, 8, 80), (2, 12, 16, 8, 160),
+                                           (1, 16, 35, 8, 40), (1, 24, 5, 8, 160), (1, 32, 9, 4, 40), (1, 40, 6, 8, 40),
+                                           (3, 7, 1, 2, 8)])
+@pytest.mark.parametrize("tc", [None, False, True])
+def test_temporal_attention(cuda_backend, B, F, N, heads, d, tc):
+    """asva_temporal_attention (picks per shape) and both forms by name: the memory-bound one (pixel groups of 1-4,
+    ragged last group, F up to 32) and the tcgen05 one."""
+    if tc is False and F > 32:
+        pytest.skip("the memory-bound form serves F <= 32")
     C = heads * d
     qkv = _rand((B, F, N, 3 * C), 50)
     o_ref = torch.zeros(B, F, N, C, dtype=torch.bfloat16, device=DEV)
-    o_cu = torch.zeros_like(o_ref)
+    o_cu = torch.full_like(o_ref, 7.0)
     SimBackend().temporal_attention(qkv, o_ref, B, F, N, heads, d, 1.0 / math.sqrt(d))
-    cuda_backend.temporal_attention(qkv, o_cu, B, F, N, heads, d, 1.0 / math.sqrt(d))
+    cuda_backend.temporal_attention(qkv, o_cu, B, F, N, heads, d, 1.0 / math.sqrt(d), tc=tc)
     torch.cuda.synchronize()
     _report("temporal attention", o_cu.view(-1, C), o_ref.view(-1, C), 4e-3)
 
