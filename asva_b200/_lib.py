@@ -88,10 +88,8 @@ ABI = {
     "asva_attention": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p]),
     "asva_temporal_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_float, C.c_void_p]),
-    "asva_temporal_attention_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                          C.c_int32, C.c_float, C.c_void_p]),
-    "asva_temporal_attention_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                          C.c_int32, C.c_float, C.c_void_p]),
+    "asva_temporal_attention_form": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "asva_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                  C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "asva_groupnorm_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
@@ -101,6 +99,7 @@ ABI = {
     "asva_groupnorm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                 C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "asva_groupnorm_sync_bytes": (C.c_int64, []),
+    "asva_groupnorm_form": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32]),
     "asva_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p]),

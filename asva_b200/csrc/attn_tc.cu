@@ -740,32 +740,44 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
   return rc;
 }
 
-extern "C" int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
-                                       int32_t d, float scale, asva_stream_t stream_) {
+static int asva_temporal_attention_tc(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                      int32_t d, float scale, asva_stream_t stream_);
+
+static int temporal_checks(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads, int32_t d,
+                           float scale) {
   using namespace asva;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ASVA_REQUIRE(qkv && out, "asva_temporal_attention: null operand");
   ASVA_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "asva_temporal_attention: head dim %d unsupported", d);
   ASVA_REQUIRE(B >= 1 && N >= 1 && heads >= 1 && F >= 1 && F <= 64, "asva_temporal_attention: bad shape (F=%d)", F);
   ASVA_REQUIRE(scale > 0.f, "asva_temporal_attention: scale must be positive");
-  // memory-bound form (misc.cu) for every shape it serves; the tcgen05 form below for the rest (F > 32, huge C * F)
-  const int rc = temporal_attention_rows(qkv, out, B, F, N, heads, d, scale, stream, false);
-  if (rc != 1) return rc;
+  return 0;
+}
+
+extern "C" int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                       int32_t d, float scale, asva_stream_t stream_) {
+  return asva_temporal_attention_form(qkv, out, B, F, N, heads, d, scale, 0, stream_);
+}
+
+extern "C" int asva_temporal_attention_form(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                            int32_t d, float scale, int32_t form, asva_stream_t stream_) {
+  using namespace asva;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = temporal_checks(qkv, out, B, F, N, heads, d, scale)) return rc;
+  ASVA_REQUIRE(form >= 0 && form <= 3, "asva_temporal_attention_form: form %d", form);
+  if (form == 0 || form == 3) {  // warp-MMA form (misc.cu) for every shape it serves
+    const int rc = temporal_attention_mma(qkv, out, B, F, N, heads, d, scale, stream);
+    if (rc != 1) return rc;
+    ASVA_REQUIRE(form == 0, "asva_temporal_attention_form: warp-MMA form does not serve F=%d, C=%d", F, heads * d);
+  }
+  if (form == 2) {
+    const int rc = temporal_attention_rows(qkv, out, B, F, N, heads, d, scale, stream, true);
+    ASVA_REQUIRE(rc != 1, "asva_temporal_attention_form: thread-per-query form does not serve F=%d, C=%d", F, heads * d);
+    return rc;
+  }
   return asva_temporal_attention_tc(qkv, out, B, F, N, heads, d, scale, stream_);
 }
 
-extern "C" int asva_temporal_attention_rows(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
-                                            int32_t d, float scale, asva_stream_t stream_) {
-  using namespace asva;
-  ASVA_REQUIRE(qkv && out, "asva_temporal_attention_rows: null operand");
-  ASVA_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192 && B >= 1 && N >= 1 && heads >= 1 && F >= 1 && scale > 0.f,
-               "asva_temporal_attention_rows: bad shape");
-  const int rc = temporal_attention_rows(qkv, out, B, F, N, heads, d, scale, reinterpret_cast<cudaStream_t>(stream_), true);
-  ASVA_REQUIRE(rc != 1, "asva_temporal_attention_rows: shape not served (F=%d, C=%d)", F, heads * d);
-  return rc;
-}
-
-extern "C" int asva_temporal_attention_tc(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+static int asva_temporal_attention_tc(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
                                           int32_t d, float scale, asva_stream_t stream_) {
   using namespace asva;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -81,5 +81,8 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 // else: also the shapes where the tcgen05 form measured faster), other = error code
 int temporal_attention_rows(const void* qkv, void* out, int B, int F, int N, int H, int d, float scale,
                             cudaStream_t stream, bool force);
+// misc.cu: the warp-MMA temporal attention; 0 = launched, 1 = shape not served, other = error code
+int temporal_attention_mma(const void* qkv, void* out, int B, int F, int N, int H, int d, float scale,
+                           cudaStream_t stream);
 
 }  // namespace asva

@@ -441,6 +441,220 @@ int temporal_attention_rows(const void* qkv, void* out, int B, int F, int N, int
   return launch_temporal_rows<32>(qkv, out, B, F, N, H, d, P, scale, threads, smem, stream);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Temporal attention, warp-MMA form.  Same data path as temporal_rows_kernel (bulk-async slabs in, bulk-async rows
+// out, outputs written over the q slots) but the F x F problem of a (pixel, head) is ONE warp's job on mma.sync
+// m16n8k16 (bf16 in, fp32 accumulate): S = Q K^T from ldmatrix fragments, softmax on the accumulator fragments (a row
+// lives in the four lanes of a quad), P re-used in registers as the A operand of P V (V through ldmatrix.trans).
+// ~120 warp instructions per problem instead of ~850: the kernel is then bound by its 8 C F bytes per pixel.  tcgen05
+// does not fit this shape - its smallest tile is 64 x 8 x 16 with the accumulator in TMEM, here a problem is 12 x 12 x 40.
+// Shared memory rows are padded by 16 bytes so the 8 rows of an ldmatrix tile fall into distinct bank groups.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int MT>  // 16-frame tiles: F <= 16 * MT
+__global__ void __launch_bounds__(128) temporal_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                           __nv_bfloat16* __restrict__ out, int F, int N, int H, int d,
+                                                           int P, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t tsm[];
+  constexpr int NT = 2 * MT;  // 8-key tiles
+  const int C = H * d;
+  const uint32_t row_bytes = static_cast<uint32_t>(3 * C) * 2u;
+  const uint32_t pitch = row_bytes + 16u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tsm + static_cast<size_t>(F) * P * pitch);
+  const int gpb = (N + P - 1) / P;
+  const int b = blockIdx.x / gpb;
+  const int n0 = (blockIdx.x - b * gpb) * P;
+  const int pe = min(P, N - n0);
+  const uint32_t base = smem_u32(tsm);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(F * pe) * row_bytes);
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * pe; i += blockDim.x) {  // row (p, f) of the slab <- qkv row (b, f, n0 + p)
+    const int p = i / F, f = i - p * F;
+    bulk_load_1d(base + static_cast<uint32_t>(i) * pitch, qkv + (static_cast<int64_t>(b * F + f) * N + n0 + p) * 3 * C,
+                 row_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int lr = lane >> 2, lc = (lane & 3) * 2;  // accumulator fragment: rows lr, lr + 8; columns lc, lc + 1
+  const int ksteps = (d + 15) >> 4;
+  for (int ph = warp; ph < pe * H; ph += nwarps) {
+    const int p = ph / H, h = ph - p * H;
+    const uint32_t q0 = base + static_cast<uint32_t>(p * F) * pitch + static_cast<uint32_t>(h * d) * 2u;  // row f: + f * pitch
+    const uint32_t k0 = q0 + static_cast<uint32_t>(C) * 2u, v0 = k0 + static_cast<uint32_t>(C) * 2u;
+    float s[MT][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const bool half = (ks * 16 + 8 >= d);  // the step's upper 8 channels lie past the head: zero them in A
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = min(mt * 16 + (lane & 15), F - 1);
+        ldsm_x4(q0 + static_cast<uint32_t>(row) * pitch + static_cast<uint32_t>(ks * 16 + (lane >> 4) * 8) * 2u, a[mt]);
+        if (half) a[mt][2] = a[mt][3] = 0u;
+      }
+#pragma unroll
+      for (int np = 0; np < MT; ++np) {  // 16 keys per ldmatrix.x4: two 8-key tiles
+        const int key = min(np * 16 + (lane & 7) + ((lane >> 4) << 3), F - 1);
+        uint32_t bk[4];
+        ldsm_x4(k0 + static_cast<uint32_t>(key) * pitch + static_cast<uint32_t>(ks * 16 + ((lane >> 3) & 1) * 8) * 2u, bk);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(s[mt][2 * np], a[mt], bk[0], bk[1]);
+          mma_bf16_16816(s[mt][2 * np + 1], a[mt], bk[2], bk[3]);
+        }
+      }
+    }
+    // softmax over the keys of each row (keys >= F masked); probabilities packed as the A operand of P V
+    uint32_t pa[MT][MT][4];  // [m tile][16-key step]
+    float inv[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = nt * 8 + lc + (e & 1);
+          if (key >= F) s[mt][nt][e] = -INFINITY;
+          mx[e >> 1] = fmaxf(mx[e >> 1], s[mt][nt][e]);
+        }
+      float sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = exp2f((s[mt][nt][e] - mx[e >> 1]) * scale_log2);
+          s[mt][nt][e] = pv;
+          sum[e >> 1] += pv;
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+        inv[mt][r] = 1.0f / sum[r];
+      }
+#pragma unroll
+      for (int kt = 0; kt < MT; ++kt) {
+        pa[mt][kt][0] = pack_bf16x2(s[mt][2 * kt][0], s[mt][2 * kt][1]);
+        pa[mt][kt][1] = pack_bf16x2(s[mt][2 * kt][2], s[mt][2 * kt][3]);
+        pa[mt][kt][2] = pack_bf16x2(s[mt][2 * kt + 1][0], s[mt][2 * kt + 1][1]);
+        pa[mt][kt][3] = pack_bf16x2(s[mt][2 * kt + 1][2], s[mt][2 * kt + 1][3]);
+      }
+    }
+    __syncwarp();  // every lane is done with q before the outputs take its place
+    // O = P V, 16 channels (two 8-channel tiles) per step; the last step of a head with d % 16 == 8 keeps its first tile
+    for (int c0 = 0; c0 < d; c0 += 16) {
+      float o[MT][2][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[mt][t][e] = 0.f;
+      const bool two = c0 + 8 < d;
+#pragma unroll
+      for (int kt = 0; kt < MT; ++kt) {
+        const int key = min(kt * 16 + (lane & 15), F - 1);
+        const int ch = c0 + ((lane >> 4) << 3);
+        uint32_t bv[4];
+        ldsm_x4_t(v0 + static_cast<uint32_t>(key) * pitch + static_cast<uint32_t>(two ? ch : c0) * 2u, bv);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(o[mt][0], pa[mt][kt], bv[0], bv[1]);
+          if (two) mma_bf16_16816(o[mt][1], pa[mt][kt], bv[2], bv[3]);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t == 1 && !two) continue;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int row = mt * 16 + lr + r * 8;
+            if (row < F)
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(q0 + static_cast<uint32_t>(row) * pitch +
+                                                          static_cast<uint32_t>(c0 + t * 8 + lc) * 2u),
+                           "r"(pack_bf16x2(o[mt][t][2 * r] * inv[mt][r], o[mt][t][2 * r + 1] * inv[mt][r]))
+                           : "memory");
+          }
+        }
+    }
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * pe; i += blockDim.x) {
+    const int p = i / F, f = i - p * F;
+    bulk_store_1d(out + (static_cast<int64_t>(b * F + f) * N + n0 + p) * C, base + static_cast<uint32_t>(i) * pitch,
+                  static_cast<uint32_t>(C) * 2u);
+  }
+  bulk_commit();
+  bulk_wait_read<0>();
+}
+
+template <int MT>
+static int launch_temporal_mma(const void* qkv, void* out, int B, int F, int N, int H, int d, int P, float scale,
+                               size_t smem, cudaStream_t stream) {
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    ASVA_CUDA_OK(cudaFuncSetAttribute(temporal_mma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[dev] = true;
+  }
+  const unsigned grid = static_cast<unsigned>(B) * static_cast<unsigned>((N + P - 1) / P);
+  ASVA_CUDA_OK(launch_k(temporal_mma_kernel<MT>, dim3(grid), dim3(128), smem, stream, 1,
+                        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), F, N, H, d, P,
+                        scale * 1.4426950408889634f));
+  ASVA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// -> 0 launched, 1 = shape not served (F > 32 or a pixel's slab beyond shared memory), other = error code
+int temporal_attention_mma(const void* qkv, void* out, int B, int F, int N, int H, int d, float scale,
+                           cudaStream_t stream) {
+  const int C = H * d;
+  const int64_t slab = static_cast<int64_t>(F) * (3 * C * 2 + 16);  // one pixel: F padded rows of q | k | v
+  if (F > 32 || slab + 16 > 220 * 1024 || static_cast<int64_t>(B) * N > (1ll << 30)) return 1;
+  int P = static_cast<int>((48 * 1024) / slab);  // ~4 CTAs per SM
+  if (P < 1) P = 1;
+  if (P > 4) P = 4;
+  if (P > N) P = N;
+  const size_t smem = static_cast<size_t>(P) * slab + 16;
+  if (F <= 16) return launch_temporal_mma<1>(qkv, out, B, F, N, H, d, P, scale, smem, stream);
+  return launch_temporal_mma<2>(qkv, out, B, F, N, H, d, P, scale, smem, stream);
+}
+
 }  // namespace asva
 
 extern "C" int asva_softmax_rows(const float* scores, int64_t lds, void* probs, int64_t ldp, int64_t rows,

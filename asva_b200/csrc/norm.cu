@@ -411,6 +411,145 @@ __device__ __forceinline__ uint4 gn_affine8(const uint4& u, const float4 (&t)[4]
   return o;
 }
 
+// ------------------------------------------------------------------------------------------------
+// GroupNorm in two launches for the few-instances x many-rows norms (a whole clip per instance at the top resolution:
+// 2 x 12288 rows x 320..960 channels).  The one-launch forms pay for their grid-wide meeting: the barrier kernel below
+// runs those shapes at 1.1-1.8 TB/s (29 us for 31 MB of traffic).  Here the kernel boundary is the barrier:
+//   A  gn2_stats_kernel: CTA (split, inst) reduces full rows of its row range (whole 128-byte lines, no strips) to
+//      per-GROUP partials ws[inst][split][group][2] - a few KB per instance instead of per-channel tables;
+//   B  gn2_apply_kernel: every CTA folds its instance's splits x groups partials (fp64, fixed order) into per-channel
+//      (scale, shift) in shared memory, then streams its rows: one read (L2-warm from A), one write.
+// With programmatic dependent launch B's prologue overlaps A's tail.  Deterministic: no atomics.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn2_stats_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+                                                        const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
+                                                        int splits, int cw, int rows_per_pass, int groups,
+                                                        float* __restrict__ ws) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float red[];  // [rows_per_pass][cw*8][2], then [cw*8][2] per-channel sums
+  const int Ctot = C0 + C1;
+  const int split = blockIdx.x, inst = blockIdx.y;
+  const int rl = threadIdx.x / cw;
+  const int cl = threadIdx.x % cw;
+  const bool active = rl < rows_per_pass;
+  const int64_t rbeg = rows * split / splits, rend = rows * (split + 1) / splits;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (active) {
+    const int c = cl * 8;
+    const __nv_bfloat16* src;
+    int ld, cc;
+    if (c < C0) { src = x0; ld = C0; cc = c; } else { src = x1; ld = C1; cc = c - C0; }
+    src += (static_cast<int64_t>(inst) * rows) * ld + cc;
+    int64_t r = rbeg + rl;
+    for (; r + rows_per_pass < rend; r += 2 * rows_per_pass) {  // two rows in flight per thread
+      const uint4 u0 = *reinterpret_cast<const uint4*>(src + r * ld);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(src + (r + rows_per_pass) * ld);
+      gn_accum8(u0, s, q);
+      gn_accum8(u1, s, q);
+    }
+    if (r < rend) gn_accum8(*reinterpret_cast<const uint4*>(src + r * ld), s, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[((rl * cw + cl) * 8 + j) * 2 + 0] = s[j];
+      red[((rl * cw + cl) * 8 + j) * 2 + 1] = q[j];
+    }
+  }
+  __syncthreads();
+  float* chan = red + rows_per_pass * cw * 16;
+  for (int t = threadIdx.x; t < Ctot; t += blockDim.x) {
+    float ss = 0.f, qq = 0.f;
+    for (int r = 0; r < rows_per_pass; ++r) {
+      ss += red[((r * cw) * 8 + t) * 2 + 0];
+      qq += red[((r * cw) * 8 + t) * 2 + 1];
+    }
+    chan[2 * t] = ss;
+    chan[2 * t + 1] = qq;
+  }
+  __syncthreads();
+  const int cpg = Ctot / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float ss = 0.f, qq = 0.f;
+    for (int c = 0; c < cpg; ++c) {
+      ss += chan[2 * (g * cpg + c)];
+      qq += chan[2 * (g * cpg + c) + 1];
+    }
+    *reinterpret_cast<float2*>(ws + ((static_cast<int64_t>(inst) * splits + split) * groups + g) * 2) = make_float2(ss, qq);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn2_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+                                                        const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
+                                                        int splits, int groups, float eps,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int silu,
+                                                        const float* __restrict__ ws, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float4 tab[];  // [Ctot / 2]: (scale, shift) of two adjacent channels; then float mr[groups][2]
+  pdl_trigger();
+  const int Ctot = C0 + C1;
+  const int nchunk = Ctot >> 3;
+  const int cpg = Ctot / groups;
+  const int inst = blockIdx.y;
+  float* mr = reinterpret_cast<float*>(tab + Ctot / 2);
+  pdl_wait();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double cnt = static_cast<double>(rows) * cpg;
+    for (int g = warp; g < groups; g += 8) {
+      double sm = 0.0, sq = 0.0;
+      for (int sp = lane; sp < splits; sp += 32) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(ws + ((static_cast<int64_t>(inst) * splits + sp) * groups + g) * 2));
+        sm += static_cast<double>(v.x);
+        sq += static_cast<double>(v.y);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      if (lane == 0) {
+        const double mean = sm / cnt;
+        double var = sq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr[2 * g] = static_cast<float>(mean);
+        mr[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      }
+    }
+  }
+  __syncthreads();
+  for (int c2 = threadIdx.x; c2 < Ctot / 2; c2 += blockDim.x) {
+    const int c = 2 * c2;
+    const int ga = c / cpg, gb = (c + 1) / cpg;
+    const float sa = mr[2 * ga + 1] * __ldg(gamma + c), sb = mr[2 * gb + 1] * __ldg(gamma + c + 1);
+    tab[c2] = make_float4(sa, __ldg(beta + c) - mr[2 * ga] * sa, sb, __ldg(beta + c + 1) - mr[2 * gb] * sb);
+  }
+  __syncthreads();
+  // CTA x of the instance owns a row range; thread (rl, cl) walks it rpp rows at a time on ONE 8-channel chunk, whose
+  // four (scale, shift) pairs stay in registers - no index arithmetic and no table reads inside the loop
+  const int cw = nchunk, rpp = blockDim.x / cw;
+  const int rl = threadIdx.x / cw, cl = threadIdx.x - rl * cw;
+  if (rl >= rpp) return;
+  const float4 t[4] = {tab[cl * 4], tab[cl * 4 + 1], tab[cl * 4 + 2], tab[cl * 4 + 3]};
+  const int64_t rbeg = rows * blockIdx.x / gridDim.x, rend = rows * (blockIdx.x + 1) / gridDim.x;
+  const int c = cl * 8;
+  const __nv_bfloat16* src;
+  int ld;
+  if (c < C0) { src = x0 + c; ld = C0; } else { src = x1 + (c - C0); ld = C1; }
+  src += static_cast<int64_t>(inst) * rows * ld;
+  __nv_bfloat16* dst = out + static_cast<int64_t>(inst) * rows * Ctot + c;
+  int64_t r = rbeg + rl;
+  for (; r + rpp < rend; r += 2 * rpp) {  // two rows in flight per thread
+    const uint4 u0 = *reinterpret_cast<const uint4*>(src + r * ld);
+    const uint4 u1 = *reinterpret_cast<const uint4*>(src + (r + rpp) * ld);
+    *reinterpret_cast<uint4*>(dst + r * Ctot) = gn_affine8(u0, t, silu);
+    *reinterpret_cast<uint4*>(dst + (r + rpp) * Ctot) = gn_affine8(u1, t, silu);
+  }
+  if (r < rend) *reinterpret_cast<uint4*>(dst + r * Ctot) = gn_affine8(*reinterpret_cast<const uint4*>(src + r * ld), t, silu);
+}
+
+
 __global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
                                                        const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
                                                        int splits, int cblocks, int cw, int rows_per_pass, int groups,
@@ -902,7 +1041,41 @@ extern "C" int asva_groupnorm_apply(const void* x0, int32_t C0, const void* x1, 
   return 0;
 }
 
-extern "C" int64_t asva_groupnorm_sync_bytes(void) { return 8 + 2 * 8 * 4096; }
+// sync_ws layout: [0, 65544) counters + fp64 accumulators of the grid-barrier kernel (kept zeroed by it);
+// [kGn2WsOffset, + kGn2WsBytes) per-group partials of the two-launch form (no initial state)
+constexpr int64_t kGn2WsOffset = 66048, kGn2WsBytes = 256 * 1024;
+extern "C" int64_t asva_groupnorm_sync_bytes(void) { return kGn2WsOffset + kGn2WsBytes; }
+
+namespace asva {
+// Which kernel(s) asva_groupnorm runs: 0 = cluster kernel, 1 = grid-barrier kernel, 2 = two launches (stats, apply).
+static int gn_pick_form(int n_inst, int64_t rows, int Ctot, int groups, GnClusterPlan* cpo) {
+  const GnClusterPlan cp = gn_cluster_plan(n_inst, rows, Ctot, groups);
+  if (cpo != nullptr) *cpo = cp;
+  // few units x many rows (a whole clip per instance at the top resolution): 8 CTAs per unit cannot fill the GPU
+  // and narrow column strips waste DRAM bursts - those shapes read full rows instead
+  const int64_t bytes = static_cast<int64_t>(n_inst) * rows * Ctot * 2;
+  const bool narrow = cp.ok && (int64_t)n_inst * (groups / cp.gb) <= 16 && bytes > (12ll << 20);
+  int form = (cp.ok && !narrow) ? 0 : 1;
+  const bool two_ok = Ctot / 8 <= 128 && rows >= 64;
+  if (form == 1 && two_ok && bytes > (4ll << 20)) form = 2;
+#ifdef ASVA_DEBUG_SWITCHES
+  if (const char* e = getenv("ASVA_GN_NO_CLUSTER"))
+    if (e[0] == '1' && form == 0) form = 1;
+  if (const char* e = getenv("ASVA_GN_FORM")) {  // 0 / 1 / 2 where feasible (tools/norm_probe.py)
+    const int f = atoi(e);
+    if (f == 0 && cp.ok) form = 0;
+    if (f == 1) form = 1;
+    if (f == 2 && two_ok) form = 2;
+  }
+#endif
+  return form;
+}
+}  // namespace asva
+
+extern "C" int asva_groupnorm_form(int32_t n_inst, int64_t rows, int32_t C, int32_t groups) {
+  if (n_inst < 1 || rows < 1 || C < 8 || groups < 1 || C % groups != 0) return -1;
+  return asva::gn_pick_form(n_inst, rows, C, groups, nullptr);
+}
 
 extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t n_inst, int64_t rows,
                               int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
@@ -917,38 +1090,53 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
   ASVA_REQUIRE(n_inst >= 1 && rows >= 1, "asva_groupnorm: empty problem");
   ASVA_REQUIRE((int64_t)n_inst * groups <= 4096, "asva_groupnorm: n_inst * groups = %lld exceeds the workspace",
                (long long)n_inst * groups);
-  {
-#ifdef ASVA_DEBUG_SWITCHES
-    static int no_cluster = -1;
-    if (no_cluster < 0) {
-      const char* e = getenv("ASVA_GN_NO_CLUSTER");
-      no_cluster = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-#else
-    constexpr int no_cluster = 0;
-#endif
-    const GnClusterPlan cp = gn_cluster_plan(n_inst, rows, Ctot, groups);
-    // few units x many rows (a whole clip per instance at the top resolution): 8 CTAs per unit cannot fill the GPU
-    // and narrow column strips waste DRAM bursts - the grid-barrier kernel below reads full rows instead
-    const int64_t bytes = static_cast<int64_t>(n_inst) * rows * Ctot * 2;
-    const bool narrow = cp.ok && (int64_t)n_inst * (groups / cp.gb) <= 16 && bytes > (12ll << 20);
-    if (cp.ok && !no_cluster && !narrow) {
-      const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(x0);
-      const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1);
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  GnClusterPlan cp;
+  const int form = gn_pick_form(n_inst, rows, Ctot, groups, &cp);
+  if (form == 0) {
+    const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(x0);
+    const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #define ASVA_GN_LAUNCH(K)                                                                                          \
   ASVA_CUDA_OK(launch_k(gn_cluster_kernel<K>, dim3(cp.grid), dim3(cp.threads), 0, stream, cp.cs, a0, C0, a1, C1, rows, \
                         groups, cp.gb, cp.cs, eps, gamma, beta, silu, o))
-      switch (cp.kmax) {
-        case 4: ASVA_GN_LAUNCH(4); break;
-        case 8: ASVA_GN_LAUNCH(8); break;
-        case 16: ASVA_GN_LAUNCH(16); break;
-        default: ASVA_GN_LAUNCH(0); break;
-      }
-#undef ASVA_GN_LAUNCH
-      ASVA_CUDA_OK(cudaGetLastError());
-      return 0;
+    switch (cp.kmax) {
+      case 4: ASVA_GN_LAUNCH(4); break;
+      case 8: ASVA_GN_LAUNCH(8); break;
+      case 16: ASVA_GN_LAUNCH(16); break;
+      default: ASVA_GN_LAUNCH(0); break;
     }
+#undef ASVA_GN_LAUNCH
+    ASVA_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  if (form == 2) {
+    const int sms = device_sms();
+    const int cw = Ctot / 8;
+    const int rpp = 256 / cw;
+    int64_t splits = (2 * sms + n_inst - 1) / n_inst;
+    const int64_t max_splits = rows / (4 * static_cast<int64_t>(rpp));
+    if (splits > max_splits) splits = max_splits;
+    const int64_t ws_cap = kGn2WsBytes / (static_cast<int64_t>(n_inst) * groups * 8);
+    if (splits > ws_cap) splits = ws_cap;
+    if (splits < 1) splits = 1;
+    ASVA_REQUIRE(static_cast<int64_t>(n_inst) * splits * groups * 8 <= kGn2WsBytes, "asva_groupnorm: workspace too small");
+    float* ws2 = reinterpret_cast<float*>(reinterpret_cast<char*>(sync_ws) + kGn2WsOffset);
+    const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(x0);
+    const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1);
+    const size_t smem_a = (static_cast<size_t>(rpp) * cw * 16 + static_cast<size_t>(Ctot) * 2) * sizeof(float);
+    ASVA_CUDA_OK(launch_k(gn2_stats_kernel, dim3(static_cast<unsigned>(splits), n_inst), dim3(256), smem_a, stream, 1, a0,
+                          C0, a1, C1, rows, static_cast<int>(splits), cw, rpp, groups, ws2));
+    ASVA_CUDA_OK(cudaGetLastError());
+    int64_t bpi = (static_cast<int64_t>(sms) * 4 + n_inst - 1) / n_inst;
+    const int64_t need = rows / (4 * static_cast<int64_t>(rpp));  // at least four passes of rows per CTA
+    if (bpi > need) bpi = need;
+    if (bpi < 1) bpi = 1;
+    const size_t smem_b = static_cast<size_t>(Ctot) * 8 + static_cast<size_t>(groups) * 8;
+    ASVA_CUDA_OK(launch_k(gn2_apply_kernel, dim3(static_cast<unsigned>(bpi), n_inst), dim3(256), smem_b, stream, 1, a0, C0,
+                          a1, C1, rows, static_cast<int>(splits), groups, eps, gamma, beta, silu,
+                          static_cast<const float*>(ws2), reinterpret_cast<__nv_bfloat16*>(out)));
+    ASVA_CUDA_OK(cudaGetLastError());
+    return 0;
   }
   // generic form (channel groups that do not bundle into 16-byte strips): grid-barrier kernel
   int& g_gn_cap = g_gn_cap_d[current_device()];

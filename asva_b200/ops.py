@@ -421,14 +421,12 @@ class CudaBackend:
             _lib.check(self.lib.asva_attention(d, self._stream()), "asva_attention")
         self.launches += 1
 
-    def temporal_attention(self, qkv, out, B, F, N, heads, d, scale, tc: Optional[bool] = None) -> None:
-        """tc=True / False: the tcgen05 / the memory-bound form by name (None: the entry point that picks per shape)."""
+    def temporal_attention(self, qkv, out, B, F, N, heads, d, scale, form: int = 0) -> None:
+        """form: 0 = auto, 1 = tcgen05, 2 = thread per query, 3 = warp-MMA (asva_temporal_attention_form)."""
         self._chk_dev(qkv, out)
-        fn = (self.lib.asva_temporal_attention if tc is None else
-              self.lib.asva_temporal_attention_tc if tc else self.lib.asva_temporal_attention_rows)
         with self._timed('temporal_attention'):
-            _lib.check(fn(qkv.data_ptr(), out.data_ptr(), B, F, N, heads, d, scale, self._stream()),
-                       "asva_temporal_attention")
+            _lib.check(self.lib.asva_temporal_attention_form(qkv.data_ptr(), out.data_ptr(), B, F, N, heads, d, scale,
+                                                         form, self._stream()), "asva_temporal_attention")
         self.launches += 1
 
     def layernorm(self, x, gamma, beta, pos, out, M, C, eps, N, F) -> None:
@@ -463,7 +461,8 @@ class CudaBackend:
             _lib.check(self.lib.asva_groupnorm(x0.data_ptr(), C0, _ptr(x1), C1, n_inst, rows, groups, eps,
                                                gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
                                                sync.data_ptr(), self._stream()), "asva_groupnorm")
-        self.launches += 1
+        Ct = C0 + (C1 if x1 is not None else 0)
+        self.launches += 2 if self.lib.asva_groupnorm_form(n_inst, rows, Ct, groups) == 2 else 1
 
     def groupnorm_apply(self, x0, C0, x1, C1, stats, n_inst, n_img, h, w, silu, upsample, out) -> None:
         self._chk_dev(x0, x1, stats, out)

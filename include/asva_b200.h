@@ -164,19 +164,18 @@ int asva_attention(const asva_attn_desc* d, asva_stream_t stream);
 /* Temporal self-attention core over the frame axis (F x F per pixel and head).
  * Replaces the SDPA inside attn_temp (ff_spatio_audio_temp_transformer_3d.py:352-358).
  *   qkv : bf16 [B][F][N][3C] (q | k | v), out: bf16 [B][F][N][C]
- * The op moves 8 C F bytes per pixel for 4 F^2 C flops - memory-bound - so the default form (misc.cu) streams each
- * pixel group's q | k | v rows into shared memory with bulk-async copies and computes in fp32 on the CUDA cores, one
- * thread per (pixel, head, query frame); wider heads and longer clips (d > 40 or F > 16, where a thread's serial
- * dot products dominate) and shapes it does not serve take the tcgen05 form.  asva_temporal_attention_tc is that tcgen05 form by name: blocks of floor(KV/F) pixels x F frames are
- * queries and keys of one block-diagonal tile, gathered by 5-D TMA boxes (attn_tc.cu). */
+ * The op moves 8 C F bytes per pixel for 4 F^2 C flops - memory-bound.  Forms (asva_temporal_attention_form):
+ *   3  warp-MMA (misc.cu): a CTA streams the q | k | v rows of a few pixels into shared memory with bulk-async copies,
+ *      one warp per (pixel, head) runs S = Q K^T, the softmax and P V on mma.sync m16n8k16 fragments, outputs leave
+ *      by bulk-async stores.  F <= 32.  The default wherever it serves.
+ *   1  tcgen05 (attn_tc.cu): blocks of floor(KV/F) pixels x F frames are queries and keys of one block-diagonal
+ *      128-row tile gathered by 5-D TMA boxes.  F <= 64; the fallback for F > 32.
+ *   2  one CUDA-core thread per (pixel, head, query frame), same data path as 3 (kept as the measured baseline).
+ *   0  auto. */
 int asva_temporal_attention(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
                             int32_t d, float scale, asva_stream_t stream);
-int asva_temporal_attention_tc(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
-                               int32_t d, float scale, asva_stream_t stream);
-/* the memory-bound form by name (F <= 32, F * 6C bytes within shared memory; ASVA_ERR_INVALID otherwise).  The default
- * entry point uses it where it measured faster than the tcgen05 form: d <= 40 and F <= 16. */
-int asva_temporal_attention_rows(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
-                                 int32_t d, float scale, asva_stream_t stream);
+int asva_temporal_attention_form(const void* qkv, void* out, int32_t B, int32_t F, int32_t N, int32_t heads,
+                                 int32_t d, float scale, int32_t form, asva_stream_t stream);
 
 /* LayerNorm over C (eps, affine) of x[M][C] (+ optional positional rows pos[F][C] added BEFORE the norm, frame
  * index = (row / N) % F) -> bf16.  Replaces nn.LayerNorm norm1/norm_audio/norm2/norm_temp/norm3
@@ -215,6 +214,10 @@ int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, int32
                    int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu, void* out,
                    void* sync_ws, asva_stream_t stream);
 int64_t asva_groupnorm_sync_bytes(void);
+/* Which kernels asva_groupnorm runs for a shape: 0 = cluster kernel (DSMEM exchange, one launch), 1 = grid-barrier
+ * kernel (one launch), 2 = two launches (full-row statistics to per-group partials, then reduce + apply): the
+ * few-instances x many-rows norms of the top resolution.  -1: invalid shape. */
+int asva_groupnorm_form(int32_t n_inst, int64_t rows, int32_t C, int32_t groups);
 
 /* conv_in front end: fp32 latents [Bs][Cl][F][h][w] (Cl<=7) -> bf16 im2col rows [B*F*h*w][64] for the 3x3, pad 1
  * conv (column = tap*Cl + c, zero padded to 64); batch b reads latent b % Bs (CFG duplication,

@@ -126,7 +126,7 @@ class SimBackend:
         outv = torch.as_strided(_flat(s.out), (G * R, H * d), (s.ldo, 1))
         outv.copy_(o.to(s.out.dtype))
 
-    def temporal_attention(self, qkv, out, B, F, N, heads, d, scale, tc=None) -> None:
+    def temporal_attention(self, qkv, out, B, F, N, heads, d, scale, form=0) -> None:
         self.launches += 1
         C = heads * d
         t = qkv.view(B, F, N, 3, heads, d).float()

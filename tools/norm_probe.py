@@ -57,6 +57,33 @@ def main():
             print(f"{(n_inst, rows, C0, C1)}: " + "  ".join(f"cs{c}/T{t}/k{k}={u:.1f}" for u, c, t, k in res[:6]),
                   flush=True)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "--forms":  # debug library: every GroupNorm form on every workload shape
+        print("| n_inst | rows | C0 | C1 | default form | cluster us | barrier us | two-launch us |")
+        print("|---|---|---|---|---|---|---|---|")
+        shapes = [(2, 12288, 320, 0), (24, 1024, 320, 0), (2, 12288, 640, 320), (2, 12288, 320, 320), (2, 3072, 640, 0),
+                  (24, 256, 640, 0), (2, 3072, 1280, 640), (2, 3072, 640, 640), (2, 3072, 640, 320), (2, 768, 1280, 0),
+                  (24, 64, 1280, 0), (2, 768, 1280, 1280), (2, 768, 1280, 640), (2, 192, 1280, 0), (24, 16, 1280, 0),
+                  (2, 192, 1280, 1280)]
+        for n_inst, rows, C0, C1 in shapes:
+            C = C0 + C1
+            xs0 = [torch.randn(n_inst * rows, C0, device=DEV).bfloat16() for _ in range(4)]
+            xs1 = [torch.randn(n_inst * rows, C1, device=DEV).bfloat16() if C1 else None for _ in range(4)]
+            outs = [torch.empty(n_inst * rows, C, device=DEV, dtype=torch.bfloat16) for _ in range(4)]
+            g, b = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+            os.environ.pop("ASVA_GN_FORM", None)
+            dflt = be.lib.asva_groupnorm_form(n_inst, rows, C, 32)
+            cells = []
+            for f in (0, 1, 2):
+                os.environ["ASVA_GN_FORM"] = str(f)
+                if be.lib.asva_groupnorm_form(n_inst, rows, C, 32) != f:
+                    cells.append("-")
+                    continue
+                us = timeit(lambda i: be.groupnorm(xs0[i % 4], C0, xs1[i % 4], C1, n_inst, rows, 32, 1e-5, g, b, True,
+                                                   outs[i % 4]))
+                cells.append(f"{us:.1f}")
+            os.environ.pop("ASVA_GN_FORM", None)
+            print(f"| {n_inst} | {rows} | {C0} | {C1} | {dflt} | " + " | ".join(cells) + " |", flush=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--single":  # eager launches of a few GroupNorm shapes (for ncu)
         for n_inst, rows, C0, C1 in [(2, 12288, 320, 0), (24, 1024, 320, 0), (2, 3072, 640, 0), (2, 12288, 640, 320)]:
             x0 = torch.randn(n_inst * rows, C0, device=DEV).bfloat16()

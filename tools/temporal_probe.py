@@ -17,8 +17,8 @@ DEV = "cuda"
 
 def main():
     be = ops.backend()
-    print("| B | F | N | C | d | rows kernel us | GB/s | tcgen05 us | GB/s |")
-    print("|---|---|---|---|---|---|---|---|---|")
+    print("| B | F | N | C | d | warp-MMA us | GB/s | thread/query us | GB/s | tcgen05 us | GB/s |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|")
     H = 8
     for F in (8, 12, 16, 24):
         for N, C in ((1024, 320), (256, 640), (64, 1280), (16, 1280)):
@@ -28,10 +28,10 @@ def main():
             out = [torch.empty(B, F, N, C, device=DEV, dtype=torch.bfloat16) for _ in range(NB)]
             by = B * F * N * 4 * C * 2
             t = []
-            for tc in (False, True):  # by name: memory-bound, tcgen05
+            for form in (3, 2, 1):
                 t.append(timeit(lambda i: be.temporal_attention(qkv[i % NB], out[i % NB], B, F, N, H, d,
-                                                                1 / math.sqrt(d), tc=tc)))
-            print(f"| {B} | {F} | {N} | {C} | {d} | {t[0]:.1f} | {by / t[0] / 1e3:.0f} | {t[1]:.1f} | {by / t[1] / 1e3:.0f} |",
+                                                                1 / math.sqrt(d), form=form)))
+            print(f"| {B} | {F} | {N} | {C} | {d} | " + " | ".join(f"{x:.1f} | {by / x / 1e3:.0f}" for x in t) + " |",
                   flush=True)
 
 
