@@ -421,7 +421,7 @@ __device__ __forceinline__ uint4 gn_affine8(const uint4& u, const float4 (&t)[4]
 //      (scale, shift) in shared memory, then streams its rows: one read (L2-warm from A), one write.
 // With programmatic dependent launch B's prologue overlaps A's tail.  Deterministic: no atomics.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn2_stats_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+__global__ void __launch_bounds__(512) gn2_stats_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
                                                         const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
                                                         int splits, int cw, int rows_per_pass, int groups,
                                                         float* __restrict__ ws) {
@@ -444,13 +444,19 @@ __global__ void __launch_bounds__(256) gn2_stats_kernel(const __nv_bfloat16* __r
     if (c < C0) { src = x0; ld = C0; cc = c; } else { src = x1; ld = C1; cc = c - C0; }
     src += (static_cast<int64_t>(inst) * rows) * ld + cc;
     int64_t r = rbeg + rl;
-    for (; r + rows_per_pass < rend; r += 2 * rows_per_pass) {  // two rows in flight per thread
-      const uint4 u0 = *reinterpret_cast<const uint4*>(src + r * ld);
-      const uint4 u1 = *reinterpret_cast<const uint4*>(src + (r + rows_per_pass) * ld);
+    const int64_t st = static_cast<int64_t>(rows_per_pass) * ld;
+    for (; r + 3 * rows_per_pass < rend; r += 4 * rows_per_pass) {  // four rows in flight per thread
+      const __nv_bfloat16* a = src + r * ld;
+      const uint4 u0 = *reinterpret_cast<const uint4*>(a);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(a + st);
+      const uint4 u2 = *reinterpret_cast<const uint4*>(a + 2 * st);
+      const uint4 u3 = *reinterpret_cast<const uint4*>(a + 3 * st);
       gn_accum8(u0, s, q);
       gn_accum8(u1, s, q);
+      gn_accum8(u2, s, q);
+      gn_accum8(u3, s, q);
     }
-    if (r < rend) gn_accum8(*reinterpret_cast<const uint4*>(src + r * ld), s, q);
+    for (; r < rend; r += rows_per_pass) gn_accum8(*reinterpret_cast<const uint4*>(src + r * ld), s, q);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       red[((rl * cw + cl) * 8 + j) * 2 + 0] = s[j];
@@ -469,18 +475,40 @@ __global__ void __launch_bounds__(256) gn2_stats_kernel(const __nv_bfloat16* __r
     chan[2 * t + 1] = qq;
   }
   __syncthreads();
+  // per-group sums of this CTA, then of its cluster of 8 (distributed shared memory): the apply kernel then folds
+  // splits / 8 partials per group instead of splits (its prologue is paid by every one of its CTAs)
   const int cpg = Ctot / groups;
+  float* gsum = chan + 2 * Ctot;  // [groups][2]
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float ss = 0.f, qq = 0.f;
     for (int c = 0; c < cpg; ++c) {
       ss += chan[2 * (g * cpg + c)];
       qq += chan[2 * (g * cpg + c) + 1];
     }
-    *reinterpret_cast<float2*>(ws + ((static_cast<int64_t>(inst) * splits + split) * groups + g) * 2) = make_float2(ss, qq);
+    gsum[2 * g] = ss;
+    gsum[2 * g + 1] = qq;
   }
+  cluster_sync_all();
+  if (cluster_ctarank() == 0) {
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      float ss = 0.f, qq = 0.f;
+      const uint32_t la = smem_u32(gsum + 2 * g);
+      for (uint32_t rk = 0; rk < 8; ++rk) {
+        uint32_t ra;
+        float a, b;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rk));
+        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(ra) : "memory");
+        ss += a;
+        qq += b;
+      }
+      *reinterpret_cast<float2*>(ws + ((static_cast<int64_t>(inst) * (splits >> 3) + (split >> 3)) * groups + g) * 2) =
+          make_float2(ss, qq);
+    }
+  }
+  cluster_sync_all();  // the peers' shared memory stays alive until rank 0 has read it
 }
 
-__global__ void __launch_bounds__(256) gn2_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+__global__ void __launch_bounds__(256, 4) gn2_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
                                                         const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
                                                         int splits, int groups, float eps,
                                                         const float* __restrict__ gamma,
@@ -495,26 +523,30 @@ __global__ void __launch_bounds__(256) gn2_apply_kernel(const __nv_bfloat16* __r
   float* mr = reinterpret_cast<float*>(tab + Ctot / 2);
   pdl_wait();
   {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // eight lanes per group fold its partials (independent loads: one round trip for all groups), fp64, fixed order
+    const int part = threadIdx.x & 7;
     const double cnt = static_cast<double>(rows) * cpg;
-    for (int g = warp; g < groups; g += 8) {
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+      const int g = g0 + (threadIdx.x >> 3);
       double sm = 0.0, sq = 0.0;
-      for (int sp = lane; sp < splits; sp += 32) {
-        const float2 v = __ldcg(reinterpret_cast<const float2*>(ws + ((static_cast<int64_t>(inst) * splits + sp) * groups + g) * 2));
-        sm += static_cast<double>(v.x);
-        sq += static_cast<double>(v.y);
+      if (g < groups) {
+        for (int sp = part; sp < splits; sp += 8) {
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(ws + ((static_cast<int64_t>(inst) * splits + sp) * groups + g) * 2));
+          sm += static_cast<double>(v.x);
+          sq += static_cast<double>(v.y);
+        }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 4; o > 0; o >>= 1) {
         sm += __shfl_xor_sync(0xffffffffu, sm, o);
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
       }
-      if (lane == 0) {
+      if (part == 0 && g < groups) {
         const double mean = sm / cnt;
         double var = sq / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
         mr[2 * g] = static_cast<float>(mean);
-        mr[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        mr[2 * g + 1] = rsqrtf(static_cast<float>(var) + eps);
       }
     }
   }
@@ -540,13 +572,21 @@ __global__ void __launch_bounds__(256) gn2_apply_kernel(const __nv_bfloat16* __r
   src += static_cast<int64_t>(inst) * rows * ld;
   __nv_bfloat16* dst = out + static_cast<int64_t>(inst) * rows * Ctot + c;
   int64_t r = rbeg + rl;
-  for (; r + rpp < rend; r += 2 * rpp) {  // two rows in flight per thread
-    const uint4 u0 = *reinterpret_cast<const uint4*>(src + r * ld);
-    const uint4 u1 = *reinterpret_cast<const uint4*>(src + (r + rpp) * ld);
-    *reinterpret_cast<uint4*>(dst + r * Ctot) = gn_affine8(u0, t, silu);
-    *reinterpret_cast<uint4*>(dst + (r + rpp) * Ctot) = gn_affine8(u1, t, silu);
+  const int64_t si = static_cast<int64_t>(rpp) * ld, so = static_cast<int64_t>(rpp) * Ctot;
+  for (; r + 3 * rpp < rend; r += 4 * rpp) {  // four rows in flight per thread
+    const __nv_bfloat16* a = src + r * ld;
+    __nv_bfloat16* o = dst + r * Ctot;
+    const uint4 u0 = *reinterpret_cast<const uint4*>(a);
+    const uint4 u1 = *reinterpret_cast<const uint4*>(a + si);
+    const uint4 u2 = *reinterpret_cast<const uint4*>(a + 2 * si);
+    const uint4 u3 = *reinterpret_cast<const uint4*>(a + 3 * si);
+    *reinterpret_cast<uint4*>(o) = gn_affine8(u0, t, silu);
+    *reinterpret_cast<uint4*>(o + so) = gn_affine8(u1, t, silu);
+    *reinterpret_cast<uint4*>(o + 2 * so) = gn_affine8(u2, t, silu);
+    *reinterpret_cast<uint4*>(o + 3 * so) = gn_affine8(u3, t, silu);
   }
-  if (r < rend) *reinterpret_cast<uint4*>(dst + r * Ctot) = gn_affine8(*reinterpret_cast<const uint4*>(src + r * ld), t, silu);
+  for (; r < rend; r += rpp)
+    *reinterpret_cast<uint4*>(dst + r * Ctot) = gn_affine8(*reinterpret_cast<const uint4*>(src + r * ld), t, silu);
 }
 
 
@@ -1056,7 +1096,7 @@ static int gn_pick_form(int n_inst, int64_t rows, int Ctot, int groups, GnCluste
   const int64_t bytes = static_cast<int64_t>(n_inst) * rows * Ctot * 2;
   const bool narrow = cp.ok && (int64_t)n_inst * (groups / cp.gb) <= 16 && bytes > (12ll << 20);
   int form = (cp.ok && !narrow) ? 0 : 1;
-  const bool two_ok = Ctot / 8 <= 128 && rows >= 64;
+  const bool two_ok = Ctot / 8 <= 128 && rows >= 8 * 4 * (512 / (Ctot / 8));  // 8 statistics CTAs of >= 4 passes
   if (form == 1 && two_ok && bytes > (4ll << 20)) form = 2;
 #ifdef ASVA_DEBUG_SWITCHES
   if (const char* e = getenv("ASVA_GN_NO_CLUSTER"))
@@ -1112,20 +1152,22 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
   if (form == 2) {
     const int sms = device_sms();
     const int cw = Ctot / 8;
-    const int rpp = 256 / cw;
-    int64_t splits = (2 * sms + n_inst - 1) / n_inst;
-    const int64_t max_splits = rows / (4 * static_cast<int64_t>(rpp));
+    const int rpp = 256 / cw, rpp_a = 512 / cw;  // rows per pass of the apply (256 threads) / the statistics CTA (512)
+    int64_t splits = (2 * sms) / n_inst;  // statistics CTAs per instance: two per SM, in clusters of 8
+    const int64_t max_splits = rows / (4 * static_cast<int64_t>(rpp_a));
     if (splits > max_splits) splits = max_splits;
-    const int64_t ws_cap = kGn2WsBytes / (static_cast<int64_t>(n_inst) * groups * 8);
+    const int64_t ws_cap = kGn2WsBytes / (static_cast<int64_t>(n_inst) * groups * 8) * 8;
     if (splits > ws_cap) splits = ws_cap;
-    if (splits < 1) splits = 1;
-    ASVA_REQUIRE(static_cast<int64_t>(n_inst) * splits * groups * 8 <= kGn2WsBytes, "asva_groupnorm: workspace too small");
+    splits = splits / 8 * 8;
+    if (splits < 8) splits = 8;
+    ASVA_REQUIRE(static_cast<int64_t>(n_inst) * (splits / 8) * groups * 8 <= kGn2WsBytes, "asva_groupnorm: workspace too small");
     float* ws2 = reinterpret_cast<float*>(reinterpret_cast<char*>(sync_ws) + kGn2WsOffset);
     const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(x0);
     const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1);
-    const size_t smem_a = (static_cast<size_t>(rpp) * cw * 16 + static_cast<size_t>(Ctot) * 2) * sizeof(float);
-    ASVA_CUDA_OK(launch_k(gn2_stats_kernel, dim3(static_cast<unsigned>(splits), n_inst), dim3(256), smem_a, stream, 1, a0,
-                          C0, a1, C1, rows, static_cast<int>(splits), cw, rpp, groups, ws2));
+    const size_t smem_a = (static_cast<size_t>(rpp_a) * cw * 16 + static_cast<size_t>(Ctot) * 2 + static_cast<size_t>(groups) * 2) * sizeof(float);
+    ASVA_REQUIRE(smem_a <= 48 * 1024, "asva_groupnorm: statistics CTA needs %zu bytes of shared memory", smem_a);
+    ASVA_CUDA_OK(launch_k(gn2_stats_kernel, dim3(static_cast<unsigned>(splits), n_inst), dim3(512), smem_a, stream, 8, a0,
+                          C0, a1, C1, rows, static_cast<int>(splits), cw, rpp_a, groups, ws2));
     ASVA_CUDA_OK(cudaGetLastError());
     int64_t bpi = (static_cast<int64_t>(sms) * 4 + n_inst - 1) / n_inst;
     const int64_t need = rows / (4 * static_cast<int64_t>(rpp));  // at least four passes of rows per CTA
@@ -1133,7 +1175,7 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
     if (bpi < 1) bpi = 1;
     const size_t smem_b = static_cast<size_t>(Ctot) * 8 + static_cast<size_t>(groups) * 8;
     ASVA_CUDA_OK(launch_k(gn2_apply_kernel, dim3(static_cast<unsigned>(bpi), n_inst), dim3(256), smem_b, stream, 1, a0, C0,
-                          a1, C1, rows, static_cast<int>(splits), groups, eps, gamma, beta, silu,
+                          a1, C1, rows, static_cast<int>(splits / 8), groups, eps, gamma, beta, silu,
                           static_cast<const float*>(ws2), reinterpret_cast<__nv_bfloat16*>(out)));
     ASVA_CUDA_OK(cudaGetLastError());
     return 0;
