@@ -73,7 +73,7 @@ class AttnDesc(C.Structure):
         ("G", C.c_int32), ("heads", C.c_int32), ("R", C.c_int32), ("Nk", C.c_int32), ("d", C.c_int32),
         ("dpad", C.c_int32),
         ("kv_rows_per_group", C.c_int32), ("k_col0", C.c_int32), ("v_col0", C.c_int32), ("mask_rows", C.c_int32),
-        ("scale", C.c_float), ("reserved", C.c_int32),
+        ("scale", C.c_float), ("form", C.c_int32),
     ]
 
 

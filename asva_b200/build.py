@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libasva_b200.so")
-SOURCES = ["host_common.cu", "gemm_tc.cu", "attn_tc.cu", "norm.cu", "misc.cu"]
+SOURCES = ["host_common.cu", "gemm_tc.cu", "attn_tc.cu", "attn_mma.cu", "norm.cu", "misc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DASVA_NO_FAST_MATH",

@@ -637,6 +637,13 @@ extern "C" int asva_attention(const asva_attn_desc* d, asva_stream_t stream_) {
                (long long)d->ldq);
   ASVA_REQUIRE(d->mask == nullptr || d->mask_rows >= 1, "asva_attention: mask_rows must be >= 1");
   ASVA_REQUIRE(d->kv_rows_per_group >= d->Nk, "asva_attention: kv_rows_per_group < Nk");
+  ASVA_REQUIRE(d->form >= 0 && d->form <= 2, "asva_attention: form %d", d->form);
+  if (d->form == 2) {  // the warp-MMA kernel for small key sets (attn_mma.cu), by request only: measured slower than the
+                       // tcgen05 kernel on every workload shape (profiles/r2_attn_mma.md)
+    const int rc = attention_small_keys(d, stream);
+    ASVA_REQUIRE(rc != 1, "asva_attention: the warp-MMA form does not serve Nk=%d, d=%d", d->Nk, d->d);
+    return rc;
+  }
 
   AttnKParams kp;
   memset(&kp, 0, sizeof(kp));

@@ -81,6 +81,8 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 // else: also the shapes where the tcgen05 form measured faster), other = error code
 int temporal_attention_rows(const void* qkv, void* out, int B, int F, int N, int H, int d, float scale,
                             cudaStream_t stream, bool force);
+// attn_mma.cu: attention against <= 128 keys on warp MMA; 0 = launched, 1 = shape not served, other = error code
+int attention_small_keys(const asva_attn_desc* d, cudaStream_t stream);
 // misc.cu: the warp-MMA temporal attention; 0 = launched, 1 = shape not served, other = error code
 int temporal_attention_mma(const void* qkv, void* out, int B, int F, int N, int H, int d, float scale,
                            cudaStream_t stream);

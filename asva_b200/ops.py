@@ -121,6 +121,7 @@ class AttnSpec:
     mask: Optional[torch.Tensor] = None  # uint8 [G*R/mask_rows, mask_ld]
     mask_ld: int = 0
     mask_rows: int = 1
+    form: int = 0  # 0 = auto, 1 = tcgen05 kernel, 2 = warp-MMA kernel for <= 128 keys (asva_attn_desc.form)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -416,7 +417,7 @@ class CudaBackend:
         d.ldq, d.ldkv, d.ldo, d.mask_ld = s.ldq, s.ldkv, s.ldo, s.mask_ld
         d.G, d.heads, d.R, d.Nk, d.d, d.dpad = s.G, s.heads, s.R, s.Nk, s.d, s.dpad
         d.kv_rows_per_group, d.k_col0, d.v_col0, d.mask_rows = s.kv_rows_per_group, s.k_col0, s.v_col0, s.mask_rows
-        d.scale = s.scale
+        d.scale, d.form = s.scale, s.form
         with self._timed('attention'):
             _lib.check(self.lib.asva_attention(d, self._stream()), "asva_attention")
         self.launches += 1

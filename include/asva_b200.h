@@ -156,7 +156,11 @@ typedef struct asva_attn_desc {
   int32_t G, heads, R, Nk, d, dpad;
   int32_t kv_rows_per_group, k_col0, v_col0, mask_rows;
   float scale;
-  int32_t reserved;
+  int32_t form; /* 0 = auto and 1 = tcgen05 flash kernel (attn_tc.cu); 2 = warp-MMA kernel for small key sets
+                   (attn_mma.cu: Nk <= 128, d <= 160 - K and V of a group staged once in shared memory, 16 query rows
+                   per warp on mma.sync).  Form 2 is an alternative kept for comparison: on B200 it measured slower
+                   than the tcgen05 kernel on every cross-attention / low-resolution shape of the workload - its time
+                   grows with the mma.sync count (22 us at 25 keys, 38 us at 77), profiles/r2_attn_mma.md */
 } asva_attn_desc;
 
 int asva_attention(const asva_attn_desc* d, asva_stream_t stream);

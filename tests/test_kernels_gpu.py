@@ -333,7 +333,7 @@ def test_gemm_strided_out_and_narrow(cuda_backend):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def _attn_case(be, G, heads, R, Nk, d, masked, seed):
+def _attn_case(be, G, heads, R, Nk, d, masked, seed, form=0):
     dpad = ((d + 63) // 64) * 64
     C = heads * d
     q = _rand((G * R, C), seed)
@@ -355,9 +355,9 @@ def _attn_case(be, G, heads, R, Nk, d, masked, seed):
                         kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d), mask=mask,
                         mask_ld=Nk, mask_rows=mask_rows)
     SimBackend().attention(spec)
-    be.attention(dataclasses.replace(spec, out=out_cu))
+    be.attention(dataclasses.replace(spec, out=out_cu, form=form))
     torch.cuda.synchronize()
-    _report(f"attention G{G} R{R} Nk{Nk} d{d} mask{masked}", out_cu, out_ref, 1e-2)
+    _report(f"attention G{G} R{R} Nk{Nk} d{d} mask{masked} form{form}", out_cu, out_ref, 1e-2)
 
 
 @pytest.mark.parametrize("d", [40, 80, 160])
@@ -365,6 +365,36 @@ def _attn_case(be, G, heads, R, Nk, d, masked, seed):
                                           (512, 229, True), (64, 16, False), (16, 16, False), (384, 1, False)])
 def test_attention(cuda_backend, d, R, Nk, masked):
     _attn_case(cuda_backend, 2, 8, R, Nk, d, masked, 30 + d)
+
+
+@pytest.mark.parametrize("form", [1, 2])
+@pytest.mark.parametrize("G,heads,R,Nk,d,masked", [
+    (2, 8, 300, 77, 40, False), (3, 8, 128, 25, 80, True), (2, 8, 768, 64, 160, False), (2, 8, 50, 1, 40, False),
+    (1, 8, 1000, 128, 40, False), (2, 8, 256, 100, 16, True), (24, 8, 64, 25, 160, True), (2, 8, 12288, 77, 40, False),
+    (4, 8, 256, 7, 80, True), (2, 3, 77, 33, 8, False), (2, 10, 260, 81, 64, False), (1, 8, 16, 16, 160, False),
+])
+def test_attention_small_key_sets_both_forms(cuda_backend, G, heads, R, Nk, d, masked, form):
+    """The cross-attention / low-resolution shapes (Nk <= 128) through the tcgen05 kernel (form 1) and the warp-MMA
+    kernel (form 2): ragged row and key counts, head chunks (d = 80 / 160 split the heads over CTAs), per-frame key
+    masks, one key."""
+    _attn_case(cuda_backend, G, heads, R, Nk, d, masked, 140 + Nk + d, form=form)
+
+
+def test_attention_mma_all_keys_masked_rows_give_zero(cuda_backend):
+    G, heads, R, Nk, d = 2, 8, 64, 20, 40
+    C = heads * d
+    q, kv = _rand((G * R, C), 170), _rand((G * Nk, 2 * C), 171)
+    mask = torch.ones(G * 2, Nk, dtype=torch.uint8, device=DEV)
+    mask[1] = 0  # the second half of group 0 may attend nothing
+    out = torch.full((G * R, C), 3.0, dtype=torch.bfloat16, device=DEV)
+    spec = ops.AttnSpec(q=q, kv=kv, out=out, G=G, heads=heads, R=R, Nk=Nk, d=d, dpad=64, ldq=C, ldkv=2 * C, ldo=C,
+                        kv_rows_per_group=Nk, k_col0=0, v_col0=C, scale=1.0 / math.sqrt(d), mask=mask, mask_ld=Nk,
+                        mask_rows=R // 2, form=2)
+    cuda_backend.attention(spec)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert float(out[R // 2:R].float().abs().max()) == 0.0
+    assert float(out[:R // 2].float().abs().max()) > 0.0
 
 
 def test_attention_config4_first_frame_shape(cuda_backend):

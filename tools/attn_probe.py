@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--shapes", default=",".join(k for k in SHAPES if not k.endswith("_hr")))
     ap.add_argument("--single", default="")
     ap.add_argument("--out", default="")
+    ap.add_argument("--form", type=int, default=0, help="asva_attn_desc.form: 0 auto, 1 tcgen05, 2 warp-MMA (Nk <= 128)")
     args = ap.parse_args()
     if args.sweep:
         sweep(args.out, args.once)
@@ -135,6 +136,7 @@ def main():
     for name in args.shapes.split(","):
         s = make(name)
         G, R, Nk, d = SHAPES[name]
+        s.form = args.form if (args.form != 2 or Nk <= 128) else 0
         err = float("nan")
         if G * R * Nk * 8 <= 2 * 12288 * 1024 * 8:
             ref = torch.zeros_like(s.out)
