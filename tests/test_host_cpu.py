@@ -332,6 +332,32 @@ def test_engine_logic_ragged_audio_mask_and_frame_varying_context():
     assert eng.ctx_sig != sig and eng.ctx["mask"] is None  # equal counts per frame: no mask left at all
 
 
+def test_engine_logic_layernorm_fold_cpu():
+    """The LayerNorm fold (ops.LnFold: W * gamma, row statistics from the producing GEMM, rstd * (acc - mean * wsum) +
+    W beta in the consumer's epilogue) sequenced by the engine, in fp32 through the interpreter, against the oracle:
+    the algebra and the bookkeeping (which GEMM emits, which consumes, frame-0 row mapping of attn1's K/V) are exact."""
+    chans = (64, 64, 128, 128)
+    sd = synth.synth_state_dict(_shapes(chans), seed=6)
+    B, F, h, w = 2, 3, 8, 8
+    lat, text, audio, mask = synth.synth_inputs(F=F, h=h, w=w, k=B, seed=31)
+    x = lat.expand(B, -1, -1, -1, -1).contiguous()
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, dict(block_out_channels=chans), x, 321, text, audio, mask)
+    outs = {}
+    for fold in (False, True):
+        be = SimBackend()
+        eng = engine.UNetEngine(sd, dict(block_out_channels=chans), device="cpu", backend=be, act_dtype=torch.float32)
+        eng.fold_ln = fold
+        eng.prepare(B, F, h, w)
+        eng.set_context(text, audio, mask)
+        out = torch.empty(B, 4, F, h, w)
+        eng.forward(x, torch.full((B,), 321.0), out)
+        outs[fold] = (out, be.launches)
+        assert _rel(out, ref) < 5e-5, (fold, _rel(out, ref))
+    # four of the five LayerNorm launches of each of the 16 transformer blocks are gone
+    assert outs[False][1] - outs[True][1] == 4 * 16
+
+
 def test_plan_cache_roundtrip_and_signature(tmp_path):
     """Measured GEMM tile plans are cached per problem shape and can be persisted (ASVA_PLAN_CACHE): the signature
     must depend on the shape and epilogue flags only (not on pointers), and save -> load must reproduce the cache."""
