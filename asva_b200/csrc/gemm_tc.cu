@@ -72,7 +72,12 @@ struct GemmKParams {
   int32_t add_div;
   int32_t epi;  // 1 = panel epilogue (TMA residual ring, TMA stores), 2 = per-warp epilogue (direct loads / stores),
                 // 3 = warp-private TMA epilogue (every warp moves its own 32-row slice of a panel with its own TMA ops)
-  __nv_bfloat16* out_ptr;  // epi == 2 only
+                // 4 = cluster split-K: the csplit CTAs of a cluster hold the K partials of ONE tile in TMEM, exchange
+                //     column slices through distributed shared memory and each finishes one slice (no workspace, no
+                //     reduce launch)
+  int32_t csplit;          // epi == 4: cluster size = K splits of a tile (2 / 4 / 8)
+  int32_t csplit_f32;      // epi == 4: the output is fp32 (out_fp32 stays 0 there: no staging area is laid out)
+  __nv_bfloat16* out_ptr;  // epi == 2 and 4 (direct stores; fp32 outputs through the same pointer)
   int64_t ldo;
   const __nv_bfloat16* res_ptr[2];
   int64_t res_ld[2];
@@ -93,10 +98,11 @@ struct TileCoord {
 // CG = 1: `tile` indexes (split, m tile, n tile). CG = 2 (CTA pair): it indexes (split, PAIR of adjacent m tiles,
 // n tile) and the CTA of rank r takes m tile 2*pair + r (an m tile past the end reads zero fill / stores nothing).
 template <int BN, int CG>
-__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int rank) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int rank, int srank = -1) {
   TileCoord t;
-  t.split = tile / p.mn_tiles;
-  const int rem = tile - t.split * p.mn_tiles;
+  // srank >= 0 (cluster split-K): `tile` indexes (m tile, n tile) and the CTA's rank in its cluster is the K split
+  t.split = srank >= 0 ? srank : tile / p.mn_tiles;
+  const int rem = srank >= 0 ? tile : tile - t.split * p.mn_tiles;
   const int nt = rem % p.n_tiles_n;
   const int mt = (rem / p.n_tiles_n) * CG + rank;
   t.n0 = nt * BN;
@@ -814,6 +820,109 @@ __device__ __forceinline__ void epilogue_warp_tma_narrow(const GemmKParams& p, i
   ASVA_TR(p, warp, 63);
 }
 
+// Cluster split-K (epi == 4).  For problems with few rows and a long K (M = 384 at the deepest level: three m tiles)
+// every tile plan is either operand-feed-bound (narrow tiles re-read A per n tile) or leaves most SMs idle; splitting K
+// fixes both but the workspace form pays a second launch and a round trip of fp32 partials through L2.  Here the S
+// splits of a tile are the S CTAs of one thread-block cluster: each runs the unchanged main loop on its K range into
+// TMEM, then (phase B) every CTA sends each 32-column chunk of its fp32 partial to the CTA that owns that column slice -
+// st.shared::cluster into a receive area that reuses the ring's shared memory - and (phase C) every CTA sums the S
+// partials of its own slice in rank order (deterministic), applies bias / row addend / residuals and stores the rows.
+// Two barrier.cluster round trips replace the reduce kernel.  One tile per CTA (grid = tiles x S).
+template <int BN>
+__device__ __forceinline__ void csplit_scatter(const GemmKParams& p, int warp, int lane, uint32_t srank,
+                                               uint32_t tmem_base, uint32_t recv_base) {
+  const int qd = warp & 3;
+  const uint32_t g = static_cast<uint32_t>(warp - 4) >> 2;
+  const int row = qd * 32 + lane;
+  const int wsl = BN / p.csplit;       // slice width (a multiple of 32)
+  const int nlc = wsl >> 5;            // 32-column chunks per slice
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+  const uint32_t sw = static_cast<uint32_t>(row & 7);
+#pragma unroll 1
+  for (int c = static_cast<int>(g); c < BN / 32; c += 2) {
+    uint32_t v[32];
+    tmem_ld_x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    const uint32_t owner = static_cast<uint32_t>((c * 32) / wsl);
+    const int lc = c - static_cast<int>(owner) * nlc;
+    // receive area of the owner: [source rank][slice chunk][row][32 fp32], 16-byte pieces XOR-swizzled by the row
+    const uint32_t local = recv_base + ((srank * nlc + lc) * 128u + static_cast<uint32_t>(row)) * 128u;
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(owner));
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra + ((static_cast<uint32_t>(j) ^ sw) << 4)),
+                   "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                   : "memory");
+  }
+}
+
+template <int BN, int CG>
+__device__ __forceinline__ void csplit_finish(const GemmKParams& p, int warp, int lane, uint32_t srank, int tile,
+                                              uint32_t recv_base) {
+  const int qd = warp & 3;
+  const uint32_t g = static_cast<uint32_t>(warp - 4) >> 2;
+  const int r = qd * 32 + lane;
+  const int r1 = r % p.box[0], r2 = (r / p.box[0]) % p.box[1], r3 = r / (p.box[0] * p.box[1]);
+  const TileCoord tc = decode_tile<BN, CG>(p, tile, 0, static_cast<int>(srank));
+  const int64_t grow = tile_out_row(p, tc, r, r1, r2, r3);
+  const int wsl = BN / p.csplit, nlc = wsl >> 5;
+  const uint32_t sw = static_cast<uint32_t>(r & 7);
+  const float* addp = (p.add_ptr != nullptr && grow >= 0) ? p.add_ptr + (grow / p.add_div) * p.add_ld : nullptr;
+#pragma unroll 1
+  for (int lc = static_cast<int>(g); lc < nlc; lc += 2) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int src = 0; src < p.csplit; ++src) {  // rank order: the sum does not depend on arrival order
+      const uint32_t a = recv_base + ((static_cast<uint32_t>(src) * nlc + lc) * 128u + static_cast<uint32_t>(r)) * 128u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = ld_shared_f4(a + ((static_cast<uint32_t>(j) ^ sw) << 4));
+        acc[4 * j] += x.x; acc[4 * j + 1] += x.y; acc[4 * j + 2] += x.z; acc[4 * j + 3] += x.w;
+      }
+    }
+    if (grow < 0) continue;
+    const int col0 = tc.n0 + static_cast<int>(srank) * wsl + lc * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // 8 columns at a time
+      const int col = col0 + 8 * j;
+      if (col >= p.N) continue;
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = acc[8 * j + e];
+      if (p.bias != nullptr) {
+        const float4 b0 = ldg4(p.bias + col), b1 = ldg4(p.bias + col + 4);
+        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+      }
+      if (addp != nullptr) {
+        const float4 b0 = ldg4(addp + col), b1 = ldg4(addp + col + 4);
+        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (i < p.n_res) {
+          const uint4 w = *reinterpret_cast<const uint4*>(p.res_ptr[i] + grow * p.res_ld[i] + col);
+          const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z), f3 = unpack_bf16x2(w.w);
+          x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y; x[4] += f2.x; x[5] += f2.y; x[6] += f3.x; x[7] += f3.y;
+        }
+      }
+      if (p.csplit_f32) {
+        float* o = reinterpret_cast<float*>(p.out_ptr) + grow * p.ldo + col;
+        *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      } else {
+        uint4 w;
+        w.x = pack_bf16x2(x[0], x[1]);
+        w.y = pack_bf16x2(x[2], x[3]);
+        w.z = pack_bf16x2(x[4], x[5]);
+        w.w = pack_bf16x2(x[6], x[7]);
+        *reinterpret_cast<uint4*>(p.out_ptr + grow * p.ldo + col) = w;
+      }
+    }
+  }
+}
+
 // RS: the instantiations that carry the row-statistics / LayerNorm-fold code (asva_gemm_desc.stats_out, .ln_*); the
 // others are the plain epilogues, untouched by it (the fold's extra loads in the shared path cost the plain launches
 // 10 - 60 %, measured: tools/lnfold_probe.py).
@@ -843,7 +952,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
   ASVA_TR(p, warp, 0);
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
-  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
+  const bool csplit = (CG == 1) && p.csplit > 1;  // cluster split-K: the cluster rank is the K split of ONE tile
+  const int srank = csplit ? static_cast<int>(cluster_ctarank()) : -1;
+  const int cdiv = csplit ? p.csplit : CG;
+  const int tile0 = blockIdx.x / cdiv, tile_step = gridDim.x / cdiv;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
@@ -912,7 +1024,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       uint32_t s = 0, ph = 1;  // ph = parity to wait for on the empty barrier
       bool ready = true;       // fresh barriers: the "previous phase" of every empty barrier counts as complete
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
-        const TileCoord tc = decode_tile<BN, CG>(p, tile, rank);
+        const TileCoord tc = decode_tile<BN, CG>(p, tile, rank, srank);
         const int i1 = tc.o1 * p.trav[0], i2 = tc.o2 * p.trav[1], i3 = tc.o3 * p.trav[2];
         const int wn0 = tc.n0 + rank * (BN / CG);
         const bool first2 = (tc.o2 == 0);
@@ -1004,7 +1116,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       uint32_t s = 0, ph = 0, t = 0;
       bool ready = false;
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++t) {
-        const TileCoord tc = decode_tile<BN, CG>(p, tile, 0);
+        const TileCoord tc = decode_tile<BN, CG>(p, tile, 0, srank);
         const uint32_t acc = t & 1u, acc_ph = (t >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
         ASVA_TR(p, warp, 4 + 3 * t);
@@ -1064,6 +1176,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       }
     }
     __syncwarp();
+  } else if (warp >= 4 && p.epi == 4) {
+    // cluster split-K: the tile's partial is complete in TMEM buffer 0; the exchange happens below, where every
+    // thread of the cluster meets
+    if (tile0 < p.total_tiles) {
+      mbar_wait(&tmem_full_bar[0], 0);
+      tc_fence_after();
+    }
   } else if (warp >= 4 && !GEGLU && p.epi == 2) {
     epilogue_direct<BN, CG>(p, warp, lane, rank, tile0, tile_step, tmem_base, tmem_full_bar, tmem_empty_bar, out_ring);
   } else if (warp == 2) {
@@ -1300,6 +1419,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     }
     if (leader) bulk_wait_read<0>();  // shared memory may be released; completion of the writes is the grid's completion
   }
+  if constexpr (CG == 1 && !GEGLU) {
+    if (csplit) {
+      // every CTA's main loop is over (its epilogue warps saw the accumulator complete, its producers / issuer left
+      // their loops): the ring's shared memory is free to receive partial slices
+      tc_fence_before();
+      cluster_sync_all();
+      const uint32_t recv = smem_u32(smem);
+      if (warp >= 4 && tile0 < p.total_tiles) {
+        tc_fence_after();
+        csplit_scatter<BN>(p, warp, lane, static_cast<uint32_t>(srank), tmem_base, recv);
+      }
+      cluster_sync_all();  // all slices have landed (release / acquire at cluster scope)
+      if (warp >= 4 && tile0 < p.total_tiles) csplit_finish<BN, CG>(p, warp, lane, static_cast<uint32_t>(srank), tile0, recv);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();  // neither CTA of a pair may leave while the other still uses it
@@ -1493,7 +1627,11 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
   if (want_epi == 2 && row_stats) want_epi = sub_ok ? 3 : 1;
   if (want_epi == 2 && (d->geglu || d->out_fp32)) want_epi = 1;
   if (want_epi == 3 && (!sub_ok || (n_res > 0 && d->out_fp32))) want_epi = 1;
-  if (want_epi != 2 && want_epi != 3) want_epi = 1;
+  // 4 = cluster split-K: the splits of a tile are the CTAs of one cluster (2 / 4 / 8), single-CTA tiles, slices of
+  // whole 32-column chunks; no GEGLU, no row statistics / fold
+  const bool want_cs = want_epi == 4 && !d->geglu && !row_stats;
+  if (want_epi == 4 && !want_cs) want_epi = sub_ok ? 3 : 1;
+  if (want_epi != 2 && want_epi != 3 && want_epi != 4) want_epi = 1;
   const int bns[4] = {64, 128, 160, 256};
   const int splits[10] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
   const int want_bn = d->geglu ? 128 : (d->block_n ? d->block_n : env_bn);
@@ -1507,18 +1645,25 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
   for (int cg = 1; cg <= 2; ++cg) {
     if (want_cg && cg != want_cg && !(cg == 1 && !pair_ok)) continue;
     if (cg == 2 && !pair_ok) continue;
+    if (want_cs && cg != 1) continue;
     for (int bi = 0; bi < 4; ++bi) {
       const int bn = bns[bi];
       if (want_bn && bn != want_bn) continue;
       if (bn > 64 && bn >= 2 * ((d->N + 31) / 32) * 32) continue;  // more than half the tile would be padding
       for (int si = 0; si < 10; ++si) {
         const int sp = splits[si];
-        if (want_split && sp != want_split && !(want_split > max_split && sp == 1)) continue;
-        if (sp > max_split || sp > num_kb) continue;
+        if (want_cs) {
+          if (sp != 2 && sp != 4 && sp != 8) continue;
+          if (want_split && sp != want_split) continue;
+          if ((bn / sp) % 32 != 0 || sp > num_kb) continue;
+        } else {
+          if (want_split && sp != want_split && !(want_split > max_split && sp == 1)) continue;
+          if (sp > max_split || sp > num_kb) continue;
+        }
         const int kbps = (num_kb + sp - 1) / sp;
         if ((num_kb + kbps - 1) / kbps != sp) continue;  // would leave an empty split
-        const int nr = (sp > 1 || want_epi == 2) ? 0 : n_res;
-        if (stages_for(bn, cg, nr, sp > 1 ? 1 : d->out_fp32, (num_kb + sp - 1) / sp) < 2) continue;
+        const int nr = (sp > 1 || want_epi == 2 || want_cs) ? 0 : n_res;
+        if (stages_for(bn, cg, nr, want_cs ? 0 : (sp > 1 ? 1 : d->out_fp32), (num_kb + sp - 1) / sp) < 2) continue;
         const double c = plan_cost(bn, cg, sp, d->N, m_tiles, num_kb, M, sms);
         if (c < best_cost) {
           best_cost = c;
@@ -1529,9 +1674,15 @@ static GemmPlan plan_gemm(const asva_gemm_desc* d, int64_t m_tiles, int64_t M, i
       }
     }
   }
-  best.epi = best.split > 1 ? (want_epi == 3 ? 3 : 1) : want_epi;
+  if (want_cs && best_cost >= 1e300) {  // no cluster split-K plan is feasible: the caller sees a different epilogue back
+    asva_gemm_desc c = *d;
+    c.epilogue = sub_ok ? 3 : 1;
+    return plan_gemm(&c, m_tiles, M, num_kb, n_res, sms);
+  }
+  best.epi = want_cs ? 4 : (best.split > 1 ? (want_epi == 3 ? 3 : 1) : want_epi);
   const int nr = (best.split > 1 || best.epi == 2) ? 0 : n_res;
-  best.stages = stages_for(best.bn, best.cg, nr, best.split > 1 ? 1 : d->out_fp32, (num_kb + best.split - 1) / best.split);
+  best.stages = stages_for(best.bn, best.cg, nr, best.epi == 4 ? 0 : (best.split > 1 ? 1 : d->out_fp32),
+                           (num_kb + best.split - 1) / best.split);
   const int cap = env_int("ASVA_GEMM_STAGES");
   if (cap >= 2 && best.stages > cap) best.stages = cap;
   return best;
@@ -1570,6 +1721,12 @@ static int launch_gemm(const GemmKParams& kp, int smem_bytes, cudaStream_t strea
       (void)cudaGetLastError();
     }
     configured = true;
+  }
+  if (CG == 1 && kp.csplit > 1) {  // cluster split-K: one tile per cluster, not persistent
+    ASVA_CUDA_OK(launch_k(gemm_tc_kernel<BN, GEGLU, CG, RS>, dim3(kp.total_tiles * kp.csplit), dim3(kGemmThreads),
+                          smem_bytes, stream, kp.csplit, kp));
+    ASVA_CUDA_OK(cudaGetLastError());
+    return 0;
   }
   const int want = kp.total_tiles * CG;
   const int grid = want < max_ctas ? want : max_ctas;
@@ -1637,8 +1794,9 @@ extern "C" int asva_gemm_tune(const asva_gemm_desc* d, asva_stream_t stream_, in
   const int splits[6] = {1, 2, 3, 4, 6, 8};
   float best = 1e30f;
   int rc = 0, bb = 0, bs = 0, bc = 0, be = 0;
-  for (int ce = 0; ce < 2 * 3 && rc == 0; ++ce) {
-    const int cg = 1 + ce / 3, epi = 1 + ce % 3;
+  for (int ce = 0; ce < 2 * 4 && rc == 0; ++ce) {
+    const int cg = 1 + ce / 4, epi = 1 + ce % 4;
+    if (epi == 4 && cg != 1) continue;
     for (int bi = 0; bi < 4 && rc == 0; ++bi) {
       for (int si = 0; si < 6 && rc == 0; ++si) {
         asva_gemm_desc c = *d;
@@ -1773,14 +1931,20 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
 
   const GemmPlan plan = plan_gemm(d, m_tiles, M, kb_total, n_res, g_num_sms);
   const int bn = plan.bn;
-  const bool split = plan.split > 1;
+  const bool csplit = plan.epi == 4;             // K split over the CTAs of a cluster: no workspace, no second launch
+  const bool split = plan.split > 1 && !csplit;  // K split through the fp32 workspace + reduce kernel
+  kp.csplit = csplit ? plan.split : 0;
   kp.split_k = plan.split;
   kp.kb_per_split = (kb_total + plan.split - 1) / plan.split;
   kp.n_res = split ? 0 : n_res;
-  kp.out_fp32 = split ? 1 : d->out_fp32;
+  kp.out_fp32 = split ? 1 : (csplit ? 0 : d->out_fp32);
+  kp.csplit_f32 = (csplit && d->out_fp32) ? 1 : 0;
   kp.n_stages = plan.stages;
   kp.epi = plan.epi;
-  const bool direct = plan.epi == 2;
+  const bool direct = plan.epi == 2 || csplit;  // plain pointers for residuals and output
+  ASVA_REQUIRE(!csplit || (plan.cg == 1 && (plan.split == 2 || plan.split == 4 || plan.split == 8) &&
+                           (bn / plan.split) % 32 == 0),
+               "asva_gemm: cluster split-K needs cta_group 1, 2 / 4 / 8 splits and slices of whole 32-column chunks");
   kp.n_res_slots = direct ? 0 : res_slots_for(bn, plan.cg, kp.n_res, kp.out_fp32, kp.kb_per_split);
   if (direct) {
     kp.out_ptr = reinterpret_cast<__nv_bfloat16*>(d->out);
@@ -1866,7 +2030,7 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
     const uint64_t ld = split ? (uint64_t)d->N : (uint64_t)d->ldo;
     void* base = split ? d->ws : d->out;
     uint64_t dims[5] = {(uint64_t)kp.n_out, (uint64_t)d->out_dims[0], (uint64_t)d->out_dims[1],
-                        (uint64_t)d->out_dims[2], (uint64_t)plan.split};
+                        (uint64_t)d->out_dims[2], (uint64_t)(csplit ? 1 : plan.split)};
     uint64_t strides[4] = {ld * es, ld * es * dims[1], ld * es * dims[1] * dims[2],
                            ld * es * dims[1] * dims[2] * dims[3]};
     int rc = make_tmap(&kp.tmO, base, f32 ? TMAP_F32 : TMAP_BF16, (f32 || wide) ? TMAP_SW128 : TMAP_SW64, 5, dims,
@@ -1906,7 +2070,7 @@ extern "C" int asva_gemm(const asva_gemm_desc* d, asva_stream_t stream_) {
   kp.n_tiles_n = (d->N + bn - 1) / bn;
   ASVA_REQUIRE(m_tiles * kp.n_tiles_n * plan.split < (1ll << 31), "asva_gemm: too many tiles");
   kp.mn_tiles = (int)(((m_tiles + plan.cg - 1) / plan.cg) * kp.n_tiles_n);  // pairs of m tiles when cg == 2
-  kp.total_tiles = kp.mn_tiles * plan.split;
+  kp.total_tiles = csplit ? kp.mn_tiles : kp.mn_tiles * plan.split;
   const int smem = smem_for(bn, plan.cg, plan.stages, kp.n_res_slots, kp.out_fp32);
   const bool rowstat = kp.stats_out != nullptr || kp.ln_stats != nullptr;
   const int rc = plan.cg == 2 ? (rowstat ? dispatch_gemm<2, true>(kp, bn, d->geglu != 0, smem, stream)

@@ -80,7 +80,7 @@ class GemmSpec:
     block_n: int = 0    # 0 = let the library choose (cost model); the engine's tuner sets measured choices
     split_k: int = 0
     cta_group: int = 0
-    epilogue: int = 0   # 0 = auto, 1 = panel (TMA) epilogue, 2 = per-warp (direct) epilogue, 3 = warp-private TMA
+    epilogue: int = 0   # 0 = auto, 1 = panel (TMA) epilogue, 2 = per-warp (direct), 3 = warp-private TMA, 4 = cluster split-K
     ln: Optional[LnFold] = None
     stats_out: Optional[torch.Tensor] = None  # fp32 [N/32, M, 2]: row sums of what this GEMM stores (for a later LnFold)
 
@@ -341,7 +341,8 @@ class CudaBackend:
         d = self._gemm_desc(s)
         with self._timed('gemm'):
             _lib.check(self.lib.asva_gemm(d, self._stream()), "asva_gemm")
-        self.launches += 2 if (s.split_k or self.gemm_plan(s, d)[1]) > 1 else 1  # split-K adds the reduce kernel
+        pl = self.gemm_plan(s, d)
+        self.launches += 2 if (pl[1] > 1 and pl[4] != 4) else 1  # workspace split-K adds the reduce kernel
 
     def gemm_plan(self, s: GemmSpec, d=None) -> tuple:
         """(block_n, split_k, cta_group, stages, epilogue) the library will use for this spec."""

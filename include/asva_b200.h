@@ -97,7 +97,11 @@ typedef struct asva_gemm_desc {
                        and 16-byte stores; bf16, non-GEGLU, non-split outputs only - otherwise 1 is used);
                        3 = warp-private TMA epilogue (each of the eight epilogue warps moves the 32 rows of its TMEM
                        quadrant with its own TMA loads / stores, no block-level barrier; any output type; needs a
-                       row box whose 32-row quadrants are themselves boxes - otherwise 1 is used) */
+                       row box whose 32-row quadrants are themselves boxes - otherwise 1 is used);
+                       4 = cluster split-K: with split_k = 2 / 4 / 8 the K splits of a tile are the CTAs of one
+                       thread-block cluster - partials stay in tensor memory, column slices are exchanged through
+                       distributed shared memory and every CTA finishes one slice (no workspace, no reduce kernel);
+                       cta_group 1, block_n / split_k a multiple of 32, no GEGLU - otherwise 3 or 1 is used */
   /* Row statistics and the LayerNorm fold (ff_spatio_audio_temp_transformer_3d.py:288-362: every sub-block of a
    * BasicTransformerBlock is LayerNorm -> projection).  With W' = W * gamma (column scaling, folded into the packed
    * weight), wsum[n] = sum_k W'[n][k] and bias' = W beta + bias,

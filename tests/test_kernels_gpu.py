@@ -96,6 +96,48 @@ def test_gemm_two_sources(cuda_backend):
     _report("linear 2-source", got, ref, 4e-3)
 
 
+# ---- cluster split-K (epilogue form 4)
+@pytest.mark.parametrize("M,K,N,bn,split,nres,f32", [
+    (384, 3840, 1280, 256, 8, 2, False), (384, 3840, 1280, 128, 4, 1, False), (384, 1280, 1280, 64, 2, 0, False),
+    (384, 11520, 1280, 256, 8, 0, False), (130, 640, 320, 64, 2, 2, False), (1536, 1280, 1288, 128, 4, 1, False),
+    (32, 1280, 2560, 256, 4, 0, True), (300, 704, 200, 128, 2, 1, False), (128, 5120, 1280, 160, 5, 0, False),
+])
+def test_gemm_cluster_split_k(cuda_backend, M, K, N, bn, split, nres, f32):
+    """K split over the CTAs of a thread-block cluster (partials in tensor memory, slices exchanged through distributed
+    shared memory): every cluster size, ragged M / N tails, bias + residuals, fp32 outputs; 160 / 5 is not a feasible
+    slice split and must fall back to another epilogue form."""
+    x = _rand((M, K), 321)
+    w = _rand((N, K), 322, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 323, dtype=torch.float32)
+    r0, r1 = (_rand((M, N), 324) if nres > 0 else None), (_rand((M, N), 325) if nres > 1 else None)
+    dt = torch.float32 if f32 else torch.bfloat16
+    spec = ops.spec_linear(x, w, torch.empty(M, N, dtype=dt, device=DEV), bias=bias, res0=r0, res1=r1, out_fp32=f32)
+    spec.block_n, spec.split_k, spec.cta_group, spec.epilogue = bn, split, 1, 4
+    pl = cuda_backend.gemm_plan(spec)
+    if split == 5:
+        assert pl[4] != 4, pl
+        return
+    assert pl[0] == bn and pl[1] == split and pl[2] == 1 and pl[4] == 4, pl
+    n0 = cuda_backend.launches
+    got, ref = _run_gemm_pair(cuda_backend, spec, (M, N), dt, fill=7.0)
+    assert cuda_backend.launches - n0 == 1  # no reduce kernel
+    _report(f"cluster split-K {M}x{K}x{N} bn{bn} S{split}", got, ref, 2e-5 if f32 else 4e-3)
+
+
+def test_gemm_cluster_split_k_conv(cuda_backend):
+    # the level-3 3x3 conv (4 x 4 images, K = 9 * 1280): implicit-GEMM boxes through the same path
+    n_img, h, wd, ci, co = 24, 4, 4, 1280, 1280
+    x = _rand((n_img * h * wd, ci), 331)
+    wt = _rand((co, 9 * ci), 332, 1.0 / math.sqrt(9 * ci))
+    b = _rand((co,), 333, dtype=torch.float32)
+    spec = ops.spec_conv3x3(x, wt, torch.empty(n_img * h * wd, co, dtype=torch.bfloat16, device=DEV), n_img=n_img, h=h,
+                            wd=wd, bias=b)
+    spec.block_n, spec.split_k, spec.cta_group, spec.epilogue = 256, 8, 1, 4
+    assert cuda_backend.gemm_plan(spec)[4] == 4
+    got, ref = _run_gemm_pair(cuda_backend, spec, (n_img * h * wd, co), torch.bfloat16, fill=7.0)
+    _report("cluster split-K conv3x3 L3", got, ref, 4e-3)
+
+
 # ---- row statistics + LayerNorm fold (asva_gemm_desc.stats_out / ln_*, ops.LnFold)
 def _stats_of(x32, C):
     v = x32.view(x32.shape[0], C // 32, 32)

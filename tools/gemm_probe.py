@@ -70,6 +70,8 @@ SHAPES = {
     "tconv1": lambda: tconv(2, 12, 256, 640),
     "tconv2": lambda: tconv(2, 12, 64, 1280),
     "tconv3": lambda: tconv(2, 12, 16, 1280),
+    "tg3": lambda: lin(384, 3840, 1280),          # the gathered conv_temp GEMM of level 3
+    "ff2_3": lambda: lin(384, 5120, 1280),
 }
 
 
@@ -129,7 +131,10 @@ def main():
                 for sp in ((1,) if spec.geglu else [int(x) for x in args.splits.split(",")]):
                     if bn > 64 and bn >= 2 * spec.N:
                         continue
-                    for epi in ((1, 3) if (spec.geglu or spec.out_fp32 or sp > 1) else (1, 2, 3)):
+                    epis = (1, 3) if (spec.geglu or spec.out_fp32 or sp > 1) else (1, 2, 3)
+                    if cg == 1 and sp in (2, 4, 8) and not spec.geglu and (bn // sp) % 32 == 0:
+                        epis = epis + (4,)  # cluster split-K
+                    for epi in epis:
                         out = torch.zeros_like(spec.out)
                         s = dataclasses.replace(spec, out=out, block_n=bn, split_k=sp, cta_group=cg, epilogue=epi)
                         try:
@@ -145,11 +150,13 @@ def main():
         b1 = min((r for r in ok if r[3] == 1), key=lambda r: r[4])
         b2 = min((r for r in ok if r[3] == 2), key=lambda r: r[4], default=None)
         b3 = min((r for r in ok if r[3] == 3), key=lambda r: r[4], default=None)
+        b4 = min((r for r in ok if r[3] == 4), key=lambda r: r[4], default=None)
         lines.append(f"## {name}: M={spec.M} N={spec.N} K={spec.K} segs={len(spec.segs)} box={spec.box}  "
                      f"auto {auto:.1f} us; best cg={best[0]} bn={best[1]} split={best[2]} epi={best[3]} {best[4]:.1f} us "
                      f"({fl / best[4] / 1e6:.0f} TFLOP/s); best panel-epilogue {b1[4]:.1f} us, best per-warp "
                      f"{'-' if b2 is None else format(b2[4], '.1f')} us, best warp-TMA "
-                     f"{'-' if b3 is None else format(b3[4], '.1f')} us")
+                     f"{'-' if b3 is None else format(b3[4], '.1f')} us, best cluster split-K "
+                     f"{'-' if b4 is None else f'{b4[4]:.1f} us (bn {b4[1]} x {b4[2]})'}")
         lines.append("| cg | bn | split | epi | us | TFLOP/s | rel-L2 vs sim |")
         lines.append("|---|---|---|---|---|---|---|")
         for cg, bn, sp, epi, us, err in rows:
