@@ -424,7 +424,7 @@ __device__ __forceinline__ uint4 gn_affine8(const uint4& u, const float4 (&t)[4]
 __global__ void __launch_bounds__(512) gn2_stats_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
                                                         const __nv_bfloat16* __restrict__ x1, int C1, int64_t rows,
                                                         int splits, int cw, int rows_per_pass, int groups,
-                                                        float* __restrict__ ws) {
+                                                        int cs, float* __restrict__ ws) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float red[];  // [rows_per_pass][cw*8][2], then [cw*8][2] per-channel sums
@@ -488,12 +488,19 @@ __global__ void __launch_bounds__(512) gn2_stats_kernel(const __nv_bfloat16* __r
     gsum[2 * g] = ss;
     gsum[2 * g + 1] = qq;
   }
+  if (cs == 1) {  // no cluster: this CTA's sums are a partial of their own
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x)
+      *reinterpret_cast<float2*>(ws + ((static_cast<int64_t>(inst) * splits + split) * groups + g) * 2) =
+          make_float2(gsum[2 * g], gsum[2 * g + 1]);
+    return;
+  }
   cluster_sync_all();
   if (cluster_ctarank() == 0) {
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
       float ss = 0.f, qq = 0.f;
       const uint32_t la = smem_u32(gsum + 2 * g);
-      for (uint32_t rk = 0; rk < 8; ++rk) {
+      for (uint32_t rk = 0; rk < static_cast<uint32_t>(cs); ++rk) {
         uint32_t ra;
         float a, b;
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rk));
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(512) gn2_stats_kernel(const __nv_bfloat16* __r
         ss += a;
         qq += b;
       }
-      *reinterpret_cast<float2*>(ws + ((static_cast<int64_t>(inst) * (splits >> 3) + (split >> 3)) * groups + g) * 2) =
+      *reinterpret_cast<float2*>(ws + ((static_cast<int64_t>(inst) * (splits / cs) + (split / cs)) * groups + g) * 2) =
           make_float2(ss, qq);
     }
   }
@@ -1098,6 +1105,9 @@ static int gn_pick_form(int n_inst, int64_t rows, int Ctot, int groups, GnCluste
   int form = (cp.ok && !narrow) ? 0 : 1;
   const bool two_ok = Ctot / 8 <= 128 && rows >= 8 * 4 * (512 / (Ctot / 8));  // 8 statistics CTAs of >= 4 passes
   if (form == 1 && two_ok && bytes > (4ll << 20)) form = 2;
+  // whole-clip norms (a few instances of >= 10 MB): the two-launch form also beats the cluster kernel's column strips
+  // (2 x 12288 x 640: 32.4 vs 36.3 us; 2 x 12288 x 960: 42.5 vs 54.4)
+  if (form == 0 && two_ok && n_inst <= 4 && bytes > (10ll << 20)) form = 2;
 #ifdef ASVA_DEBUG_SWITCHES
   if (const char* e = getenv("ASVA_GN_NO_CLUSTER"))
     if (e[0] == '1' && form == 0) form = 1;
@@ -1153,21 +1163,29 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
     const int sms = device_sms();
     const int cw = Ctot / 8;
     const int rpp = 256 / cw, rpp_a = 512 / cw;  // rows per pass of the apply (256 threads) / the statistics CTA (512)
-    int64_t splits = (2 * sms) / n_inst;  // statistics CTAs per instance: two per SM, in clusters of 8
+    // statistics CTAs per cluster (their per-group sums meet in distributed shared memory).  Measured on 2 x 12288 x 320
+    // (tools/gn2_cs_probe.sh): 24.2 / 21.8 / 25.4 / 26.4 us for clusters of 1 / 2 / 4 / 8 - pairs halve the partials
+    // the apply kernel folds, larger clusters cost more at launch than they save
+    int gcs = 2;
+#ifdef ASVA_DEBUG_SWITCHES
+    if (const char* e = getenv("ASVA_GN2_CS")) gcs = atoi(e);
+    if (gcs != 1 && gcs != 2 && gcs != 4 && gcs != 8) gcs = 2;
+#endif
+    int64_t splits = (2 * sms) / n_inst;  // statistics CTAs per instance: two per SM, in clusters of gcs
     const int64_t max_splits = rows / (4 * static_cast<int64_t>(rpp_a));
     if (splits > max_splits) splits = max_splits;
-    const int64_t ws_cap = kGn2WsBytes / (static_cast<int64_t>(n_inst) * groups * 8) * 8;
+    const int64_t ws_cap = kGn2WsBytes / (static_cast<int64_t>(n_inst) * groups * 8) * gcs;
     if (splits > ws_cap) splits = ws_cap;
-    splits = splits / 8 * 8;
-    if (splits < 8) splits = 8;
-    ASVA_REQUIRE(static_cast<int64_t>(n_inst) * (splits / 8) * groups * 8 <= kGn2WsBytes, "asva_groupnorm: workspace too small");
+    splits = splits / gcs * gcs;
+    if (splits < gcs) splits = gcs;
+    ASVA_REQUIRE(static_cast<int64_t>(n_inst) * (splits / gcs) * groups * 8 <= kGn2WsBytes, "asva_groupnorm: workspace too small");
     float* ws2 = reinterpret_cast<float*>(reinterpret_cast<char*>(sync_ws) + kGn2WsOffset);
     const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(x0);
     const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1);
     const size_t smem_a = (static_cast<size_t>(rpp_a) * cw * 16 + static_cast<size_t>(Ctot) * 2 + static_cast<size_t>(groups) * 2) * sizeof(float);
     ASVA_REQUIRE(smem_a <= 48 * 1024, "asva_groupnorm: statistics CTA needs %zu bytes of shared memory", smem_a);
-    ASVA_CUDA_OK(launch_k(gn2_stats_kernel, dim3(static_cast<unsigned>(splits), n_inst), dim3(512), smem_a, stream, 8, a0,
-                          C0, a1, C1, rows, static_cast<int>(splits), cw, rpp_a, groups, ws2));
+    ASVA_CUDA_OK(launch_k(gn2_stats_kernel, dim3(static_cast<unsigned>(splits), n_inst), dim3(512), smem_a, stream, gcs, a0,
+                          C0, a1, C1, rows, static_cast<int>(splits), cw, rpp_a, groups, gcs, ws2));
     ASVA_CUDA_OK(cudaGetLastError());
     int64_t bpi = (static_cast<int64_t>(sms) * 4 + n_inst - 1) / n_inst;
     const int64_t need = rows / (4 * static_cast<int64_t>(rpp));  // at least four passes of rows per CTA
@@ -1175,7 +1193,7 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
     if (bpi < 1) bpi = 1;
     const size_t smem_b = static_cast<size_t>(Ctot) * 8 + static_cast<size_t>(groups) * 8;
     ASVA_CUDA_OK(launch_k(gn2_apply_kernel, dim3(static_cast<unsigned>(bpi), n_inst), dim3(256), smem_b, stream, 1, a0, C0,
-                          a1, C1, rows, static_cast<int>(splits / 8), groups, eps, gamma, beta, silu,
+                          a1, C1, rows, static_cast<int>(splits / gcs), groups, eps, gamma, beta, silu,
                           static_cast<const float*>(ws2), reinterpret_cast<__nv_bfloat16*>(out)));
     ASVA_CUDA_OK(cudaGetLastError());
     return 0;
