@@ -937,16 +937,23 @@ static GnClusterPlan gn_cluster_plan(int n_inst, int64_t rows, int Ctot, int gro
   if (units * 8 > (1ll << 30)) return pl;
   // Measured on B200 (tools/norm_probe.py --sweep): the launch should fill the SMs in ONE wave.  Many units -> one
   // small streaming CTA each; few units -> clusters that split the rows, 512 threads, slices held in registers.
-  bool hold = true;
-  if (units >= 296) {
+  // Re-measured at the end of round 2 (after SiLU left the IEEE division): a unit per CTA - no cluster - whenever the
+  // units alone fill the SMs (clusters cost more at launch than they save: 17.4 vs 18.2 us on 24 x 1024 x 320), its
+  // slice held in registers by a 128-thread CTA when it is small (24 x 64 x 1280: 5.7 vs 7.6 us); and clusters of 8 for
+  // the few-unit strips with >= 4096 chunks per CTA even past one CTA per SM (2 x 3072 x 1920: 20.7 vs 28.3 us).
+  bool hold = true, small_unit = false, big8 = false;
+  if (units >= 148) {
     pl.cs = 1;
-    hold = false;
-  } else if (units >= 148) {
-    pl.cs = 2;
-    hold = false;
+    small_unit = rows * bw < 4096;
+    hold = small_unit;
   } else {
     pl.cs = 8;
     while (pl.cs > 1 && units * pl.cs > 160) pl.cs >>= 1;
+    if (pl.cs < 8 && units * 8 <= 296 && (rows / 8) * bw >= 4096) {
+      pl.cs = 8;
+      big8 = true;  // streamed by 512 threads (the measured best; holding 12+ chunks per thread was 35 vs 21 us)
+      hold = false;
+    }
   }
   while (pl.cs > 1 && rows / pl.cs < 64) pl.cs >>= 1;
 #ifdef ASVA_DEBUG_SWITCHES  // plan overrides for tools/norm_probe.py --sweep (experiment builds only)
@@ -959,10 +966,12 @@ static GnClusterPlan gn_cluster_plan(int n_inst, int64_t rows, int Ctot, int gro
   if (e_cs != nullptr) pl.cs = atoi(e_cs);
   const int64_t rows_cta = (rows + pl.cs - 1) / pl.cs;
   const int64_t chunks = rows_cta * bw;
-  if (hold)
+  if (small_unit)
+    pl.threads = 128;
+  else if (hold)
     pl.threads = chunks >= 1024 ? 512 : (chunks >= 256 ? 256 : 128);
   else
-    pl.threads = chunks >= 512 ? 256 : 128;
+    pl.threads = (pl.cs == 1 || big8) ? 512 : (chunks >= 512 ? 256 : 128);
   if (e_t != nullptr) pl.threads = atoi(e_t);
   if (pl.threads < bw) pl.threads = ((bw + 31) / 32) * 32;
   const int rpp = pl.threads / bw;
@@ -1105,9 +1114,10 @@ static int gn_pick_form(int n_inst, int64_t rows, int Ctot, int groups, GnCluste
   int form = (cp.ok && !narrow) ? 0 : 1;
   const bool two_ok = Ctot / 8 <= 128 && rows >= 8 * 4 * (512 / (Ctot / 8));  // 8 statistics CTAs of >= 4 passes
   if (form == 1 && two_ok && bytes > (4ll << 20)) form = 2;
-  // whole-clip norms (a few instances of >= 10 MB): the two-launch form also beats the cluster kernel's column strips
-  // (2 x 12288 x 640: 32.4 vs 36.3 us; 2 x 12288 x 960: 42.5 vs 54.4)
-  if (form == 0 && two_ok && n_inst <= 4 && bytes > (10ll << 20)) form = 2;
+  // whole-clip norms with few, wide-strided units (>= 10 MB, <= 16 units): the two-launch form also beats the cluster
+  // kernel's column strips (2 x 12288 x 960: 42.4 vs 54.3 us; 2 x 3072 x 960: 20.0 vs 23.6); with 32 units the cluster
+  // kernel streams with 8 CTAs per unit and wins (2 x 12288 x 640: 26.7 vs 32.3 us)
+  if (form == 0 && two_ok && n_inst <= 4 && bytes > (10ll << 20) && (int64_t)n_inst * (groups / cp.gb) <= 16) form = 2;
 #ifdef ASVA_DEBUG_SWITCHES
   if (const char* e = getenv("ASVA_GN_NO_CLUSTER"))
     if (e[0] == '1' && form == 0) form = 1;
