@@ -443,7 +443,7 @@ int temporal_attention_rows(const void* qkv, void* out, int B, int F, int N, int
 // Shared memory rows are padded by 16 bytes so the 8 rows of an ldmatrix tile fall into distinct bank groups.
 // ------------------------------------------------------------------------------------------------
 template <int MT>  // 16-frame tiles: F <= 16 * MT
-__global__ void __launch_bounds__(128) temporal_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(256) temporal_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                            __nv_bfloat16* __restrict__ out, int F, int N, int H, int d,
                                                            int P, float scale_log2) {
   extern __shared__ __align__(128) uint8_t tsm[];
@@ -611,7 +611,13 @@ static int launch_temporal_mma(const void* qkv, void* out, int B, int F, int N, 
     configured[dev] = true;
   }
   const unsigned grid = static_cast<unsigned>(B) * static_cast<unsigned>((N + P - 1) / P);
-  ASVA_CUDA_OK(launch_k(temporal_mma_kernel<MT>, dim3(grid), dim3(128), smem, stream, 1,
+  // one warp per (pixel, head) for the longer problems; two heads per warp for d = 40 x <= 16 frames, where more CTAs in
+  // flight beat more warps per CTA (18.6 vs 19.8 us at level 0; 6.6 vs 7.6 us the other way at d = 160)
+  int threads = (P * H >= 8 && (d >= 80 || F > 16)) ? 256 : 128;
+#ifdef ASVA_DEBUG_SWITCHES
+  if (const char* e = getenv("ASVA_TMMA_T")) threads = atoi(e) == 128 ? 128 : 256;
+#endif
+  ASVA_CUDA_OK(launch_k(temporal_mma_kernel<MT>, dim3(grid), dim3(threads), smem, stream, 1,
                         reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), F, N, H, d, P,
                         scale * 1.4426950408889634f));
   ASVA_CUDA_OK(cudaGetLastError());
@@ -624,9 +630,15 @@ int temporal_attention_mma(const void* qkv, void* out, int B, int F, int N, int 
   const int C = H * d;
   const int64_t slab = static_cast<int64_t>(F) * (3 * C * 2 + 16);  // one pixel: F padded rows of q | k | v
   if (F > 32 || slab + 16 > 220 * 1024 || static_cast<int64_t>(B) * N > (1ll << 30)) return 1;
-  int P = static_cast<int>((48 * 1024) / slab);  // ~4 CTAs per SM
-  if (P < 1) P = 1;
-  if (P > 4) P = 4;
+  // one pixel per CTA: measured best on every level (tools/temporal_probe.py with ASVA_TMMA_P = 1 / 2 / 3 / 4: 18.3 /
+  // 22.4 / 26.0 / 28.3 us at 12 frames x 1024 px x 320 channels) - small CTAs, many in flight, overlap loads and stores
+  int P = 1;
+#ifdef ASVA_DEBUG_SWITCHES
+  if (const char* e = getenv("ASVA_TMMA_P")) {  // pixels per CTA (tools/temporal_probe.py sweeps)
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8 && static_cast<int64_t>(v) * slab + 16 <= 220 * 1024) P = v;
+  }
+#endif
   if (P > N) P = N;
   const size_t smem = static_cast<size_t>(P) * slab + 16;
   if (F <= 16) return launch_temporal_mma<1>(qkv, out, B, F, N, H, d, P, scale, smem, stream);

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_rows_kernel(const __nv_bfloa
                                                                 float eps, int N, int F, int lanes_log2) {
   extern __shared__ float gb[];  // gamma[C] | beta[C]
   pdl_trigger();
-  for (int i = threadIdx.x; i < (C >> 2); i += 256) {
+  for (int i = threadIdx.x; i < (C >> 2); i += blockDim.x) {
     reinterpret_cast<float4*>(gb)[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
     reinterpret_cast<float4*>(gb + C)[i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
   }
@@ -108,9 +108,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_rows_kernel(const __nv_bfloa
   const int lanes = 1 << lanes_log2, rows_per_warp = 32 >> lanes_log2;
   const int lane = threadIdx.x & 31;
   const int sub = lane >> lanes_log2, li = lane & (lanes - 1);
-  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * 8;
+  const int wpb = blockDim.x >> 5;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * wpb;
   const float inv_c = 1.0f / static_cast<float>(C);
-  int64_t grp = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  int64_t grp = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
   uint4 nxt[NCH];
   auto fetch = [&](int64_t g) {
     const int64_t row = g * rows_per_warp + sub;
@@ -1020,15 +1021,21 @@ extern "C" int asva_layernorm(const void* x, const float* gamma, const float* be
     if (C % (8 * lanes) != 0 || C / (8 * lanes) > 5) continue;
     const int nch = C / (8 * lanes);
     const int64_t groups = (M + (32 / lanes) - 1) / (32 / lanes);
-    const int64_t cap = static_cast<int64_t>(device_sms()) * 2 * 8;  // resident warps at 2 CTAs per SM
+    int threads = 256, per_sm = 2;  // CTA size and CTAs per SM the grid is sized for (registers allow 512 threads / SM)
+#ifdef ASVA_DEBUG_SWITCHES
+    if (const char* e = getenv("ASVA_LNR_T")) threads = atoi(e) == 128 ? 128 : 256;
+    if (const char* e = getenv("ASVA_LNR_PER_SM")) per_sm = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : per_sm;
+#endif
+    const int wpb = threads / 32;
+    const int64_t cap = static_cast<int64_t>(device_sms()) * per_sm * wpb;  // resident warps
     const int64_t iters = (groups + cap - 1) / cap;
-    const unsigned blocks = static_cast<unsigned>((groups + 8 * iters - 1) / (8 * iters));
+    const unsigned blocks = static_cast<unsigned>((groups + wpb * iters - 1) / (wpb * iters));
     const size_t smem = static_cast<size_t>(C) * 8;
 #define ASVA_LNR_CASE(K) \
-  case K: ASVA_CUDA_OK(launch_k(layernorm_rows_kernel<K>, dim3(blocks), dim3(256), smem, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f, ll)); break;
+  case K: ASVA_CUDA_OK(launch_k(layernorm_rows_kernel<K>, dim3(blocks), dim3(threads), smem, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f, ll)); break;
     switch (nch) {
       ASVA_LNR_CASE(1) ASVA_LNR_CASE(2) ASVA_LNR_CASE(3) ASVA_LNR_CASE(4)
-      default: ASVA_CUDA_OK(launch_k(layernorm_rows_kernel<5>, dim3(blocks), dim3(256), smem, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f, ll)); break;
+      default: ASVA_CUDA_OK(launch_k(layernorm_rows_kernel<5>, dim3(blocks), dim3(threads), smem, stream, 1, xp, gamma, beta, pos, op, M, C, eps, n, f, ll)); break;
     }
 #undef ASVA_LNR_CASE
     ASVA_CUDA_OK(cudaGetLastError());
