@@ -1188,7 +1188,12 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
     if (const char* e = getenv("ASVA_GN2_CS")) gcs = atoi(e);
     if (gcs != 1 && gcs != 2 && gcs != 4 && gcs != 8) gcs = 2;
 #endif
-    int64_t splits = (2 * sms) / n_inst;  // statistics CTAs per instance: two per SM, in clusters of gcs
+    int st_per_sm = 2, ap_per_sm = 4;  // CTAs per SM the two grids are sized for
+#ifdef ASVA_DEBUG_SWITCHES
+    if (const char* e = getenv("ASVA_GN2_ST_PER_SM")) st_per_sm = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : st_per_sm;
+    if (const char* e = getenv("ASVA_GN2_AP_PER_SM")) ap_per_sm = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : ap_per_sm;
+#endif
+    int64_t splits = (static_cast<int64_t>(st_per_sm) * sms) / n_inst;  // statistics CTAs per instance, in clusters of gcs
     const int64_t max_splits = rows / (4 * static_cast<int64_t>(rpp_a));
     if (splits > max_splits) splits = max_splits;
     const int64_t ws_cap = kGn2WsBytes / (static_cast<int64_t>(n_inst) * groups * 8) * gcs;
@@ -1204,7 +1209,7 @@ extern "C" int asva_groupnorm(const void* x0, int32_t C0, const void* x1, int32_
     ASVA_CUDA_OK(launch_k(gn2_stats_kernel, dim3(static_cast<unsigned>(splits), n_inst), dim3(512), smem_a, stream, gcs, a0,
                           C0, a1, C1, rows, static_cast<int>(splits), cw, rpp_a, groups, gcs, ws2));
     ASVA_CUDA_OK(cudaGetLastError());
-    int64_t bpi = (static_cast<int64_t>(sms) * 4 + n_inst - 1) / n_inst;
+    int64_t bpi = (static_cast<int64_t>(sms) * ap_per_sm + n_inst - 1) / n_inst;
     const int64_t need = rows / (4 * static_cast<int64_t>(rpp));  // at least four passes of rows per CTA
     if (bpi > need) bpi = need;
     if (bpi < 1) bpi = 1;
