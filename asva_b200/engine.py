@@ -573,11 +573,23 @@ class GraphRunner:
             self.fn()
             self.launches_per_call = self.be.launches - n0
         elif self.graph is None:
+            # Dead Python cycles that hold CUDA memory (an engine dropped by its model, a finished session) must not be
+            # collected INSIDE the capture window: releasing their blocks there invalidates the capture
+            # ("operation failed due to a previous error during capture"; torch >= 2.9 no longer runs gc.collect() at
+            # capture entry).  Collect them now and keep the cyclic collector off until the capture has ended.
+            import gc
+            gc.collect()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = self.be.launches
-            with torch.cuda.graph(g):
-                self.fn()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    self.fn()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             self.launches_per_call = self.be.launches - n0
             self.graph = g
             g.replay()

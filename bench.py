@@ -15,6 +15,7 @@ scaling, no collective on the data path; a single NCCL all-gather of the final l
                cores on a bounded sample (rank 0, N = 1 only)
 `--impl reference` times that CPU implementation as its own arm."""
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -303,9 +304,14 @@ def run_product_arm(args):
             continue
         n0 = be.launches
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for fn, a, k in calls:
-                fn(*a, **k)
+        gc.collect()  # nothing may be garbage-collected inside the capture window (see engine.GraphRunner)
+        gc.disable()
+        try:
+            with torch.cuda.graph(g):
+                for fn, a, k in calls:
+                    fn(*a, **k)
+        finally:
+            gc.enable()
         n_launch = be.launches - n0
         g.replay()
         torch.cuda.synchronize()
